@@ -1,0 +1,473 @@
+"""Seeded synthetic fixtures for the decode path.
+
+Writes exactly the on-disk formats the reference loads, so the SAME files feed the
+reference oracle and the CUDA path:
+
+* acoustic models  -> JMBI binary   (reference reader: src/HTKModels.cpp:1112-1245,
+                                     record layouts :1309-1372, :1440-1492, :1580-1633,
+                                     :1697-1739, :1805-1851, :2002-2089)
+* network          -> AT&T FSM text + symbol tables (reference reader:
+                                     src/WFSTNetwork.cpp:371-616, symbols :52-112)
+* features         -> float32 [T, 39] sampled along a random accepted path, so every
+                      utterance has a planted right answer.
+
+numpy only; nothing here touches the GPU or the oracle.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+D_FEAT = 39
+LOG_2_PI = 1.83787706640934548355
+
+
+# --------------------------------------------------------------------------------------
+# acoustic models
+# --------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class TransMat:
+    n_states: int
+    sucs: List[List[int]]            # successors per state
+    probs: List[List[float]]         # linear probabilities per successor
+
+
+@dataclasses.dataclass
+class Models:
+    """HTK-style model set: GMM pool + HMM table + transition matrices."""
+    dim: int
+    weights: List[np.ndarray]        # per GMM: [M_g] float32 mixture weights
+    means: List[np.ndarray]          # per GMM: [M_g, D] float32
+    vars_: List[np.ndarray]          # per GMM: [M_g, D] float32 (variances, not inverse)
+    tmats: List[TransMat]
+    hmm_nstates: List[int]
+    hmm_gmm: List[List[int]]         # per HMM: gmm id per state (-1 for entry / exit)
+    hmm_tmat: List[int]
+    hmm_names: List[str]
+
+    @property
+    def n_gmm(self) -> int:
+        return len(self.weights)
+
+    @property
+    def n_hmm(self) -> int:
+        return len(self.hmm_nstates)
+
+
+def left_to_right_tmat(n_states: int = 5, self_loop: float = 0.6) -> TransMat:
+    """Entry -> 1 with p=1; emitting states self-loop / forward; no tee."""
+    sucs: List[List[int]] = [[1]]
+    probs: List[List[float]] = [[1.0]]
+    for s in range(1, n_states - 1):
+        sucs.append([s, s + 1])
+        probs.append([self_loop, 1.0 - self_loop])
+    sucs.append([])
+    probs.append([])
+    return TransMat(n_states, sucs, probs)
+
+
+def tee_tmat(p_skip: float = 0.3, self_loop: float = 0.6) -> TransMat:
+    """3-state 'sp' model with an entry->exit tee transition.  The reference only sees a tee
+    when the exit is successor index >= 1 of the entry state (src/HTKModels.cpp:1358-1370)."""
+    return TransMat(3, [[1, 2], [1, 2], []], [[1.0 - p_skip, p_skip], [self_loop, 1.0 - self_loop], []])
+
+
+def skip_tmat(n_states: int = 6) -> TransMat:
+    """Left-to-right with skip transitions (wider SEIndex ranges, gaps filled with LOG_ZERO)."""
+    sucs: List[List[int]] = [[1, 2]]
+    probs: List[List[float]] = [[0.8, 0.2]]
+    for s in range(1, n_states - 1):
+        nxt = [s, s + 1] + ([s + 2] if s + 2 <= n_states - 1 else [])
+        p = [0.5, 0.35, 0.15][: len(nxt)]
+        tot = sum(p)
+        sucs.append(nxt)
+        probs.append([x / tot for x in p])
+    sucs.append([])
+    probs.append([])
+    return TransMat(n_states, sucs, probs)
+
+
+def make_models(n_hmm: int, n_mix: int, *, sigma_mu: float = 0.8, seed: int = 0,
+                n_gmm_pool: Optional[int] = None, ragged_mix: bool = False,
+                with_tee: bool = False, mixed_topology: bool = False) -> Models:
+    """n_hmm physical HMMs (5 states, 3 emitting) over untied (gmm = 3*hmm + s) or tied GMMs.
+
+    sigma_mu is the workload knob: smaller -> more confusable states -> more active
+    hypotheses.  with_tee appends one 3-state tee model as the LAST
+    HMM; mixed_topology makes every 7th HMM a 6-state skip model and every 5th a 4-state one
+    (exercises variable nStates and SEIndex gaps).
+    """
+    rng = np.random.default_rng(seed)
+    tmats = [left_to_right_tmat(5)]
+    if mixed_topology:
+        tmats += [skip_tmat(6), left_to_right_tmat(4)]
+    hmm_nstates: List[int] = []
+    hmm_tmat: List[int] = []
+    for h in range(n_hmm):
+        if mixed_topology and h % 7 == 3:
+            hmm_nstates.append(6); hmm_tmat.append(1)
+        elif mixed_topology and h % 5 == 2:
+            hmm_nstates.append(4); hmm_tmat.append(2)
+        else:
+            hmm_nstates.append(5); hmm_tmat.append(0)
+    if with_tee:
+        tmats.append(tee_tmat())
+        hmm_nstates.append(3); hmm_tmat.append(len(tmats) - 1)
+    n_emit = sum(n - 2 for n in hmm_nstates)
+    n_gmm = n_emit if n_gmm_pool is None else n_gmm_pool
+    if n_gmm_pool is None:
+        assign = np.arange(n_emit)
+    else:
+        assign = rng.integers(0, n_gmm, size=n_emit)
+        assign[: min(n_gmm, n_emit)] = rng.permutation(n_gmm)[: min(n_gmm, n_emit)]
+    hmm_gmm: List[List[int]] = []
+    k = 0
+    for n in hmm_nstates:
+        row = [-1] + [int(assign[k + i]) for i in range(n - 2)] + [-1]
+        k += n - 2
+        hmm_gmm.append(row)
+    weights, means, vars_ = [], [], []
+    for g in range(n_gmm):
+        m = n_mix if not ragged_mix else int(rng.integers(1, n_mix + 1))
+        w = rng.dirichlet(np.full(m, 5.0)).astype(np.float32)
+        weights.append(w)
+        means.append((rng.standard_normal((m, D_FEAT)) * sigma_mu).astype(np.float32))
+        vars_.append(rng.uniform(0.5, 2.0, size=(m, D_FEAT)).astype(np.float32))
+    names = [f"h{h}" for h in range(len(hmm_nstates))]
+    if with_tee:
+        names[-1] = "sp"
+    return Models(D_FEAT, weights, means, vars_, tmats, hmm_nstates, hmm_gmm, hmm_tmat, names)
+
+
+def _rec(tag: bytes, *parts: bytes) -> bytes:
+    return tag + b"".join(parts)
+
+
+def _i32(*v: int) -> bytes:
+    return np.asarray(v, dtype="<i4").tobytes()
+
+
+def _name(s: Optional[str]) -> bytes:
+    if not s:
+        return _i32(0)
+    b = s.encode() + b"\0"
+    return _i32(len(b)) + b
+
+
+def write_jmbi(m: Models, path: str) -> None:
+    """One mean/var vector per Gaussian, one mixture per GMM in GMM order (HTKFlatModels
+    assumes gMMs[i].mixtureInd == i, src/HTKFlatModels.cpp:143-176)."""
+    D = m.dim
+    n_gauss = int(sum(len(w) for w in m.weights))
+    out: List[bytes] = [b"JMBI", _i32(D, n_gauss, n_gauss, m.n_gmm, m.n_gmm, len(m.tmats), m.n_hmm)]
+    all_means = np.concatenate(m.means, axis=0).astype("<f4")
+    all_vars = np.concatenate(m.vars_, axis=0).astype("<f4")
+    # JMMN: tag, nameLen=0, means[D]
+    rec = np.zeros(n_gauss, dtype=[("tag", "S4"), ("len", "<i4"), ("v", "<f4", (D,))])
+    rec["tag"] = b"JMMN"; rec["v"] = all_means
+    out.append(rec.tobytes())
+    # JMVR: tag, nameLen=0, vars[D], minusHalfOverVars[D], gconst   (src/HTKModels.cpp:857-866)
+    rec = np.zeros(n_gauss, dtype=[("tag", "S4"), ("len", "<i4"), ("v", "<f4", (D,)),
+                                   ("mh", "<f4", (D,)), ("g", "<f4")])
+    rec["tag"] = b"JMVR"; rec["v"] = all_vars
+    rec["mh"] = (np.float32(-0.5) / all_vars).astype("<f4")
+    g = np.full(n_gauss, np.float32(D * LOG_2_PI), dtype=np.float32)
+    logv = np.log(all_vars.astype(np.float64))
+    for d in range(D):                                  # same accumulation order, float each step
+        g = (g.astype(np.float64) + logv[:, d]).astype(np.float32)
+    rec["g"] = (g.astype(np.float64) * -0.5).astype(np.float32)
+    out.append(rec.tobytes())
+    # JMMX: tag, nameLen=0, nComps, meanInds[n], varInds[n]
+    k = 0
+    for w in m.weights:
+        n = len(w)
+        idx = np.arange(k, k + n, dtype="<i4")
+        out.append(_rec(b"JMMX", _i32(0, n), idx.tobytes(), idx.tobytes()))
+        k += n
+    # JMGM: tag, nameLen=0, mixtureInd, nComps, w[n], logw[n]
+    for gi, w in enumerate(m.weights):
+        lw = np.log(w.astype(np.float64)).astype("<f4")
+        out.append(_rec(b"JMGM", _i32(0, gi, len(w)), w.astype("<f4").tobytes(), lw.tobytes()))
+    # JMTM: tag, nameLen=0, nStates, nSucs[N], sucs[total], probs[total], logProbs[total]
+    for t in m.tmats:
+        nsucs = [len(s) for s in t.sucs]
+        sucs = [x for s in t.sucs for x in s]
+        probs = np.asarray([x for p in t.probs for x in p], dtype="<f4")
+        lp = np.log(probs.astype(np.float64)).astype("<f4")
+        out.append(_rec(b"JMTM", _i32(0, t.n_states), _i32(*nsucs), _i32(*sucs), probs.tobytes(), lp.tobytes()))
+    # JMHM: tag, name, nStates, gmmInds[N], transMatInd
+    for h in range(m.n_hmm):
+        out.append(_rec(b"JMHM", _name(m.hmm_names[h]), _i32(m.hmm_nstates[h]), _i32(*m.hmm_gmm[h]),
+                        _i32(m.hmm_tmat[h])))
+    out.append(b"\0")                                   # hybridMode = false
+    with open(path, "wb") as f:
+        f.write(b"".join(out))
+
+
+# --------------------------------------------------------------------------------------
+# networks
+# --------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class Net:
+    """Arcs in FILE order (grouped by source state, initial state's arcs first).
+    w are FILE weights = -log probabilities (the loader negates, src/WFSTNetwork.cpp:481)."""
+    src: np.ndarray
+    dst: np.ndarray
+    ilab: np.ndarray
+    olab: np.ndarray
+    w: np.ndarray
+    finals: Dict[int, float]          # state -> file weight
+    n_in: int                         # number of input symbols incl. <eps>
+    n_out: int                        # number of output symbols incl. <eps>
+    in_names: Optional[List[str]] = None
+
+    @property
+    def n_arcs(self) -> int:
+        return int(self.src.shape[0])
+
+    @property
+    def n_states(self) -> int:
+        return int(max(self.src.max(), self.dst.max())) + 1
+
+
+def _finish_net(src, dst, ilab, olab, w, finals, n_in, n_out, in_names=None) -> Net:
+    src = np.asarray(src, dtype=np.int64); dst = np.asarray(dst, dtype=np.int64)
+    ilab = np.asarray(ilab, dtype=np.int64); olab = np.asarray(olab, dtype=np.int64)
+    w = np.asarray(w, dtype=np.float64)
+    order = np.argsort(src, kind="stable")             # group by source; state 0 (initial) first
+    return Net(src[order], dst[order], ilab[order], olab[order], w[order], finals, n_in, n_out, in_names)
+
+
+def digit_loop_net(n_words: int = 10) -> Net:
+    """C1: one state, n self-loop arcs (in=h+1, out=h+1, w=ln n), final."""
+    a = np.arange(n_words)
+    z = np.zeros(n_words, dtype=np.int64)
+    return _finish_net(z, z, a + 1, a + 1, np.full(n_words, math.log(n_words)), {0: 0.0},
+                       n_words + 1, n_words + 1)
+
+
+def tee_eps_net(n_words: int = 4, sp_label: Optional[int] = None) -> Net:
+    """Second smoke fixture of SURVEY Appendix E: 0 -w:eps/ln n-> a_w -sp:eps-> b_w -eps:W/0.25-> 0,
+    final 0 / 0.5.  Exercises tee skipping, eps arcs carrying word labels, final weights."""
+    sp = sp_label if sp_label is not None else n_words + 1
+    src, dst, il, ol, w = [], [], [], [], []
+    for v in range(n_words):
+        a, b = 1 + 2 * v, 2 + 2 * v
+        src += [0, a, b]; dst += [a, b, 0]
+        il += [v + 1, sp, 0]; ol += [0, 0, v + 1]
+        w += [math.log(n_words), 0.0, 0.25]
+    return _finish_net(src, dst, il, ol, w, {0: 0.5}, sp + 1, n_words + 1)
+
+
+def bigram_net(n_words: int, n_hmm: int, *, k_bigram: int = 8, seed: int = 0,
+               pron_len: Tuple[int, int] = (3, 8), sp_label: Optional[int] = None,
+               positive_weights: bool = True) -> Net:
+    """C2-shaped C.L.G: unigram hub (state 0, initial+final) with one pronunciation chain per
+    word (word label + LM weight on the first arc); per-word history states with k explicit
+    bigram chains and one eps back-off arc to the hub.  With sp_label, every word chain ends
+    in an optional-silence tee arc.  A few arcs get positive log-weights after negation
+    (SURVEY 7 'Network weights are not guaranteed <= 0')."""
+    rng = np.random.default_rng(seed)
+    V = n_words
+    prons = [rng.integers(1, n_hmm + 1, size=int(rng.integers(pron_len[0], pron_len[1] + 1))) for _ in range(V)]
+    hist0 = 1                                            # history state of word v = 1 + v
+    nxt = 1 + V
+    src: List[int] = []; dst: List[int] = []; il: List[int] = []; ol: List[int] = []; w: List[float] = []
+
+    def chain(s: int, v: int, e: int, lm: float) -> None:
+        nonlocal nxt
+        p = prons[v]
+        cur = s
+        n = len(p) + (1 if sp_label is not None else 0)
+        for i in range(n):
+            to = e if i == n - 1 else nxt
+            if to == nxt:
+                nxt += 1
+            lab = int(p[i]) if i < len(p) else int(sp_label)
+            src.append(cur); dst.append(to); il.append(lab)
+            ol.append(v + 1 if i == 0 else 0); w.append(lm if i == 0 else 0.0)
+            cur = to
+
+    uni = -np.log(rng.dirichlet(np.full(V, 2.0)))
+    for v in range(V):
+        chain(0, v, hist0 + v, float(uni[v]))
+    for v in range(V):
+        succ = rng.choice(V, size=min(k_bigram, V), replace=False)
+        pw = -np.log(rng.dirichlet(np.full(len(succ) + 1, 2.0)))
+        for j, u in enumerate(succ):
+            lm = float(pw[j])
+            if positive_weights and rng.random() < 0.02:
+                lm = -float(rng.uniform(0.05, 0.5))     # file weight < 0 -> positive log-weight
+            chain(hist0 + v, int(u), hist0 + int(u), lm)
+        src.append(hist0 + v); dst.append(0); il.append(0); ol.append(0); w.append(float(pw[-1]))
+    finals = {0: 0.0}
+    fw = rng.uniform(0.0, 1.0, size=V)
+    for v in range(V):
+        finals[hist0 + v] = float(fw[v])
+    n_in = (n_hmm if sp_label is None else max(n_hmm, sp_label)) + 1
+    return _finish_net(src, dst, il, ol, w, finals, n_in, V + 1)
+
+
+def trigram_net(n_words: int, n_hmm: int, *, k_bigram: int = 40, n_trigram: int = 60000,
+                k_trigram: int = 8, seed: int = 0, pron_len: Tuple[int, int] = (3, 8)) -> Net:
+    """C3/C5-shaped network, built vectorised:
+      hub (state 0)        --first phone of w / out=w / unigram weight--> shared tail of w --> h_w
+      bigram state h_v     --k_bigram first arcs into shared tails + eps back-off to hub
+      trigram state t_(u,v): reached from h_u through a DEDICATED chain for v;
+                             k_trigram first arcs into shared tails + eps back-off to h_v
+    Shared tails make arcs >> states with a heavy-tailed out-degree (hub = V arcs); the
+    eps back-off chain tri -> bi -> uni has depth 2.  All history states are final."""
+    rng = np.random.default_rng(seed)
+    V = n_words
+    plen = rng.integers(pron_len[0], pron_len[1] + 1, size=V)
+    pron_off = np.concatenate([[0], np.cumsum(plen)])
+    phones = rng.integers(1, n_hmm + 1, size=int(pron_off[-1]))
+    # state numbering
+    hist0 = 1                                        # h_v = 1 + v
+    tail0 = hist0 + V                                # shared tail of w: states tail_base[w] .. + plen[w]-2
+    tail_len = plen - 1
+    tail_base = tail0 + np.concatenate([[0], np.cumsum(tail_len)])[:-1]
+    tri0 = int(tail0 + tail_len.sum())               # t_k = tri0 + k
+    tri_u = rng.integers(0, V, size=n_trigram)
+    tri_v = rng.integers(0, V, size=n_trigram)
+    ded_len = plen[tri_v] - 1                        # dedicated chain inner states for v from h_u
+    ded0 = tri0 + n_trigram
+    ded_base = ded0 + np.concatenate([[0], np.cumsum(ded_len)])[:-1]
+
+    S: List[np.ndarray] = []; T: List[np.ndarray] = []; I: List[np.ndarray] = []
+    O: List[np.ndarray] = []; W: List[np.ndarray] = []
+
+    def add(s, t, i, o, w):
+        S.append(np.asarray(s, dtype=np.int64)); T.append(np.asarray(t, dtype=np.int64))
+        I.append(np.asarray(i, dtype=np.int64)); O.append(np.asarray(o, dtype=np.int64))
+        W.append(np.asarray(w, dtype=np.float64))
+
+    def first_arcs(src_states: np.ndarray, words: np.ndarray, lm: np.ndarray):
+        """arc src -> (tail_base[w] or h_w if 1-phone) labelled first phone of w, out = w+1."""
+        to = np.where(tail_len[words] > 0, tail_base[words], hist0 + words)
+        add(src_states, to, phones[pron_off[words]], words + 1, lm)
+
+    # shared tails: for word w, phone i (1..plen-1): state tail_base+i-1 -> next (or h_w)
+    w_rep = np.repeat(np.arange(V), tail_len)
+    pos = np.arange(tail_len.sum()) - np.repeat(np.concatenate([[0], np.cumsum(tail_len)])[:-1], tail_len)
+    s_ = tail_base[w_rep] + pos
+    last = pos == tail_len[w_rep] - 1
+    t_ = np.where(last, hist0 + w_rep, s_ + 1)
+    add(s_, t_, phones[pron_off[w_rep] + pos + 1], np.zeros_like(s_), np.zeros(len(s_)))
+    # hub
+    first_arcs(np.zeros(V, dtype=np.int64), np.arange(V), -np.log(rng.dirichlet(np.full(V, 2.0))))
+    # bigram states
+    kb = min(k_bigram, V)
+    bw = rng.integers(0, V, size=(V, kb))
+    lm = rng.gamma(4.0, 1.0, size=(V, kb))
+    first_arcs(np.repeat(hist0 + np.arange(V), kb), bw.ravel(), lm.ravel())
+    add(hist0 + np.arange(V), np.zeros(V), np.zeros(V), np.zeros(V), rng.gamma(2.0, 1.0, size=V))
+    # dedicated chains h_u -> ... -> t_k spelling v (word label on the first arc)
+    k_idx = np.arange(n_trigram)
+    to0 = np.where(ded_len > 0, ded_base, tri0 + k_idx)
+    add(hist0 + tri_u, to0, phones[pron_off[tri_v]], tri_v + 1, rng.gamma(3.0, 1.0, size=n_trigram))
+    k_rep = np.repeat(k_idx, ded_len)
+    pos = np.arange(ded_len.sum()) - np.repeat(np.concatenate([[0], np.cumsum(ded_len)])[:-1], ded_len)
+    s_ = ded_base[k_rep] + pos
+    last = pos == ded_len[k_rep] - 1
+    t_ = np.where(last, tri0 + k_rep, s_ + 1)
+    add(s_, t_, phones[pron_off[tri_v[k_rep]] + pos + 1], np.zeros_like(s_), np.zeros(len(s_)))
+    # trigram states
+    kt = min(k_trigram, V)
+    tw = rng.integers(0, V, size=(n_trigram, kt))
+    first_arcs(np.repeat(tri0 + k_idx, kt), tw.ravel(), rng.gamma(3.0, 1.0, size=n_trigram * kt))
+    add(tri0 + k_idx, hist0 + tri_v, np.zeros(n_trigram), np.zeros(n_trigram), rng.gamma(2.0, 1.0, size=n_trigram))
+
+    finals: Dict[int, float] = {0: 0.0}
+    fw = rng.uniform(0.0, 1.0, size=V + n_trigram)
+    for v in range(V):
+        finals[hist0 + v] = float(fw[v])
+    for k in range(n_trigram):
+        finals[tri0 + k] = float(fw[V + k])
+    return _finish_net(np.concatenate(S), np.concatenate(T), np.concatenate(I), np.concatenate(O),
+                       np.concatenate(W), finals, n_hmm + 1, V + 1)
+
+
+def write_fsm(net: Net, prefix: str) -> Tuple[str, str, str]:
+    """AT&T text + complete, dense symbol tables (SURVEY 8b preconditions)."""
+    fsm, insyms, outsyms = prefix + ".fsm", prefix + ".insyms", prefix + ".outsyms"
+    w = net.w.astype(np.float32)
+    with open(fsm, "w") as f:
+        # %.9g round-trips float32 exactly through sscanf("%f")
+        lines = [f"{s} {t} {i} {o} {x:.9g}\n" for s, t, i, o, x in
+                 zip(net.src.tolist(), net.dst.tolist(), net.ilab.tolist(), net.olab.tolist(), w.tolist())]
+        f.write("".join(lines))
+        for s, fw in net.finals.items():
+            f.write(f"{s} {np.float32(fw):.9g}\n")
+    with open(insyms, "w") as f:
+        f.write("<eps> 0\n")
+        for i in range(1, net.n_in):
+            nm = net.in_names[i] if net.in_names else f"h{i - 1}"
+            f.write(f"{nm} {i}\n")
+    with open(outsyms, "w") as f:
+        f.write("<eps> 0\n")
+        for i in range(1, net.n_out):
+            f.write(f"W{i - 1} {i}\n")
+    return fsm, insyms, outsyms
+
+
+# --------------------------------------------------------------------------------------
+# features with a planted answer
+# --------------------------------------------------------------------------------------
+class PathSampler:
+    """Random accepted walks through a Net, emitting frames from the visited states' GMMs."""
+
+    def __init__(self, net: Net, models: Models, tee_hmms: Sequence[int] = ()):
+        self.net, self.m = net, models
+        n = net.n_states
+        self.first = np.zeros(n, dtype=np.int64)
+        self.count = np.bincount(net.src, minlength=n)
+        self.first[1:] = np.cumsum(self.count)[:-1]
+        self.tee = set(int(h) for h in tee_hmms)
+        self.init = int(net.src[0])
+
+    def sample(self, min_frames: int, rng: np.random.Generator, dur: Tuple[int, int] = (2, 4),
+               max_arcs: int = 100000) -> Tuple[np.ndarray, List[int]]:
+        net, m = self.net, self.m
+        state = self.init
+        frames: List[np.ndarray] = []
+        words: List[int] = []
+        n_fr = 0
+        for _ in range(max_arcs):
+            if n_fr >= min_frames and state in net.finals:
+                break
+            c = int(self.count[state])
+            if c == 0:
+                raise RuntimeError("dead-end state in synthetic network")
+            a = int(self.first[state] + rng.integers(0, c))
+            il, ol = int(net.ilab[a]), int(net.olab[a])
+            if ol:
+                words.append(ol)
+            if il:
+                h = il - 1
+                if not (h in self.tee and rng.random() < 0.5):
+                    for s in range(1, m.hmm_nstates[h] - 1):
+                        g = m.hmm_gmm[h][s]
+                        d = int(rng.integers(dur[0], dur[1] + 1))
+                        comp = rng.integers(0, len(m.weights[g]), size=d)
+                        x = m.means[g][comp] + rng.standard_normal((d, m.dim)) * np.sqrt(m.vars_[g][comp])
+                        frames.append(x.astype(np.float32))
+                        n_fr += d
+            state = int(net.dst[a])
+        else:
+            raise RuntimeError("walk did not terminate on a final state")
+        if not frames:
+            return np.zeros((0, m.dim), dtype=np.float32), words
+        return np.ascontiguousarray(np.concatenate(frames, axis=0)), words
+
+
+def make_fixture(name: str, outdir: str, models: Models, net: Net) -> Dict[str, str]:
+    os.makedirs(outdir, exist_ok=True)
+    jm = os.path.join(outdir, name + ".jmbi")
+    write_jmbi(models, jm)
+    fsm, ins, outs = write_fsm(net, os.path.join(outdir, name))
+    return {"jmbi": jm, "fsm": fsm, "insyms": ins, "outsyms": outs}

@@ -1,0 +1,140 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes bindings for the two CPU checkers.
+
+* ``OracleRef``  : oracle/_ref/liboracle_ref.so — the UNMODIFIED reference objects
+                   (WFSTDecoderLite, HTKFlatModels, WFSTNetwork) behind oracle/ref_driver.cpp.
+* ``OraclePort`` : oracle/liboracle.so — the plain-C restatement (oracle/juicer_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product (juicer_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Dict, List, Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "liboracle_ref.so")
+PORT_SO = os.path.join(HERE, "liboracle.so")
+LOG_ZERO = -np.finfo(np.float32).max
+
+
+def build(ref: bool = True, port: bool = True) -> None:
+    """Compile the checkers.  The reference build needs /root/reference (absent on the GPU
+    box, where the prebuilt oracle/_ref/liboracle_ref.so that travelled with the snapshot is used)."""
+    if port:
+        subprocess.check_call(["make", "-s", "-C", HERE, "port"])
+    if ref and os.path.isdir(os.environ.get("JUICER_REF", "/root/reference")):
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+
+
+class Word(C.Structure):
+    _fields_ = [("label", C.c_int), ("time", C.c_int), ("score", C.c_float), ("ac", C.c_float), ("lm", C.c_float)]
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class DecodeResult:
+    """status: number of words, -1 = no token reached a final state (reference returns NULL),
+    -2 = surviving final token carries no word label (inactive DecHyp)."""
+
+    def __init__(self, status: int, words: List[Dict], totals: np.ndarray,
+                 frame_cnt: Optional[np.ndarray], frame_best: Optional[np.ndarray], seconds: float):
+        self.status = status
+        self.words = words
+        self.score, self.ac, self.lm = (float(np.float32(x)) for x in totals)
+        self.totals = totals
+        self.frame_cnt = frame_cnt
+        self.frame_best = frame_best
+        self.seconds = seconds
+
+    @property
+    def labels(self) -> List[int]:
+        return [w["label"] for w in self.words]
+
+    @property
+    def times(self) -> List[int]:
+        return [w["time"] for w in self.words]
+
+    def __repr__(self) -> str:
+        return (f"DecodeResult(status={self.status}, labels={self.labels}, times={self.times}, "
+                f"score={self.score!r}, ac={self.ac!r}, lm={self.lm!r})")
+
+
+def _words_from(buf, n: int) -> List[Dict]:
+    return [dict(label=buf[i].label, time=buf[i].time, score=float(np.float32(buf[i].score)),
+                 ac=float(np.float32(buf[i].ac)), lm=float(np.float32(buf[i].lm))) for i in range(max(n, 0))]
+
+
+class OracleRef:
+    def __init__(self, files: Dict[str, str], *, main_beam: float, start_beam: float = 0.0,
+                 end_beam: float = 0.0, word_beam: float = 0.0, max_hyps: int = 0,
+                 lm_scale: float = 1.0, ins_penalty: float = 0.0, block_size: int = 5):
+        if not os.path.exists(REF_SO):
+            raise RuntimeError(f"{REF_SO} missing: run `make -C oracle ref` where /root/reference exists")
+        self.lib = C.CDLL(REF_SO)
+        self.lib.oref_create.restype = C.c_void_p
+        self.lib.oref_create.argtypes = [C.c_char_p] * 4 + [C.c_float] * 6 + [C.c_int, C.c_int]
+        self.lib.oref_decode.restype = C.c_int
+        self.lib.oref_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib.oref_gmm_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        self.lib.oref_dims.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.oref_dump_models.argtypes = [C.c_void_p] * 11
+        self.lib.oref_dump_net.argtypes = [C.c_void_p] * 8
+        self.lib.oref_destroy.argtypes = [C.c_void_p]
+        self.h = self.lib.oref_create(files["jmbi"].encode(), files["fsm"].encode(), files["insyms"].encode(),
+                                      files["outsyms"].encode(), lm_scale, ins_penalty, start_beam, main_beam,
+                                      end_beam, word_beam, max_hyps, block_size)
+        d = np.zeros(16, dtype=np.int32)
+        self.lib.oref_dims(self.h, _fp(d))
+        (self.dim, self.n_gmm, self.n_hmm, self.n_tmat, self.max_states, self.max_comps,
+         self.n_states, self.n_arcs, self.init_state) = (int(x) for x in d[:9])
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.oref_destroy(self.h)
+            self.h = None
+
+    def decode(self, feats: np.ndarray, counters: bool = False, max_words: int = 4096) -> DecodeResult:
+        feats = np.ascontiguousarray(feats, dtype=np.float32)
+        T = feats.shape[0]
+        words = (Word * max_words)()
+        totals = np.zeros(3, dtype=np.float32)
+        cnt = np.zeros((T, 6), dtype=np.int32) if counters else None
+        best = np.zeros(T, dtype=np.float32) if counters else None
+        sec = C.c_double(0.0)
+        n = self.lib.oref_decode(self.h, _fp(feats), T, C.byref(words), max_words, _fp(totals),
+                                 _fp(cnt) if counters else None, _fp(best) if counters else None, C.byref(sec))
+        return DecodeResult(n, _words_from(words, min(n, max_words)), totals, cnt, best, sec.value)
+
+    def gmm_scores(self, feats: np.ndarray) -> np.ndarray:
+        feats = np.ascontiguousarray(feats, dtype=np.float32)
+        out = np.zeros((feats.shape[0], self.n_gmm), dtype=np.float32)
+        self.lib.oref_gmm_scores(self.h, _fp(feats), feats.shape[0], _fp(out))
+        return out
+
+    def dump_models(self) -> Dict[str, np.ndarray]:
+        H, S, G, Cc, D = self.n_hmm, self.max_states, self.n_gmm, self.max_comps, self.dim
+        r = dict(hmm_nstates=np.zeros(H, np.int32), hmm_gmm=np.zeros((H, S), np.int32),
+                 hmm_tmat=np.zeros(H, np.int32), hmm_tee=np.zeros(H, np.float32),
+                 trP=np.zeros((H, S, S), np.float32), se=np.zeros((H, S, 2), np.int32),
+                 gmm_ncomp=np.zeros(G, np.int32), dets=np.zeros((G, Cc), np.float32),
+                 means=np.zeros((G, Cc, D), np.float32), ivars=np.zeros((G, Cc, D), np.float32))
+        self.lib.oref_dump_models(self.h, *[_fp(r[k]) for k in ("hmm_nstates", "hmm_gmm", "hmm_tmat", "hmm_tee",
+                                                                "trP", "se", "gmm_ncomp", "dets", "means", "ivars")])
+        return r
+
+    def dump_net(self) -> Dict[str, np.ndarray]:
+        A, S = self.n_arcs, self.n_states
+        r = dict(arc_to=np.zeros(A, np.int32), arc_w=np.zeros(A, np.float32), arc_in=np.zeros(A, np.int32),
+                 arc_out=np.zeros(A, np.int32), st_first=np.zeros(S, np.int32), st_n=np.zeros(S, np.int32),
+                 st_final=np.zeros(S, np.float32))
+        self.lib.oref_dump_net(self.h, *[_fp(r[k]) for k in ("arc_to", "arc_w", "arc_in", "arc_out",
+                                                             "st_first", "st_n", "st_final")])
+        return r
