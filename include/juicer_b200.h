@@ -1,0 +1,213 @@
+/* juicer_b200.h — C ABI of the B200-native WFST Viterbi token-passing decode path.
+ *
+ * One path of idiap/juicer is re-implemented here as hand-written sm_100a CUDA kernels:
+ *   WFSTDecoderLite::processFrame        (reference src/WFSTDecoderLite.cpp:311-372)
+ *   HTKFlatModels::calcOutput            (reference src/HTKFlatModels.cpp:179-262)
+ * plus the per-utterance start/finish around it (recognitionStart :139-228,
+ * recognitionFinish :230-309).  Everything crossing this boundary is a plain pointer, a
+ * size or a POD struct; no C++ or torch types.  All functions return 0 on success, a
+ * negative JGPU_E_* code otherwise; jgpu_last_error() gives the message.  There is no CPU
+ * fallback: without a CUDA device jgpu_create fails with JGPU_E_CUDA.
+ *
+ * Conventions (identical to the reference):
+ *   real == float;  LOG_ZERO == -FLT_MAX is the "dead token" sentinel (Torch3 log_add.h);
+ *   arc weights are +log probabilities, already negated / LM-scaled / insertion-penalised
+ *   the way WFSTNetwork's loader stores them (src/WFSTNetwork.cpp:481-486);
+ *   an arc's input label is HMM index + 1 (src/WFSTDecoderLite.cpp:754), 0 = epsilon;
+ *   an arc's output label is word id + 1, 0 = epsilon.
+ */
+#ifndef JUICER_B200_H
+#define JUICER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JGPU_LOG_ZERO (-3.402823466e+38f)
+
+enum {
+    JGPU_OK          =  0,
+    JGPU_E_ARG       = -1,   /* bad argument / inconsistent tables (validated at create) */
+    JGPU_E_CUDA      = -2,   /* CUDA runtime failure, or no device: there is no CPU path */
+    JGPU_E_CAPACITY  = -3,   /* a device arena overflowed (reported per utterance too) */
+    JGPU_E_STATE     = -4,   /* call sequence error (e.g. push_frames on a lane not begun) */
+    JGPU_E_IO        = -5    /* host loader could not read / parse a file */
+};
+
+/* Flattened WFSTNetwork.  Replaces: WFSTTransition / WFSTState / WFSTFinalState
+ * (src/WFSTNetwork.h:41-68) as seen through getTransitions(prev,&next)
+ * (src/WFSTNetwork.cpp:709-721: a state's out-arcs are arcs [first, first+n) in file
+ * order), transGoesToFinalState / getFinalStateWeight (src/WFSTNetwork.h:161-167) and
+ * getInitState (:126). */
+typedef struct JgpuNet {
+    int32_t        n_states;
+    int32_t        n_arcs;
+    int32_t        init_state;
+    const int32_t* arc_to;        /* [n_arcs] destination state                       */
+    const float*   arc_weight;    /* [n_arcs] log weight as stored by the loader      */
+    const int32_t* arc_in;        /* [n_arcs] input label  (HMM index + 1, 0 = eps)   */
+    const int32_t* arc_out;       /* [n_arcs] output label (word id + 1, 0 = eps)     */
+    const int32_t* state_first;   /* [n_states] id of the state's first out-arc       */
+    const int32_t* state_narcs;   /* [n_states] number of out-arcs                    */
+    const float*   state_final;   /* [n_states] final weight, JGPU_LOG_ZERO if the
+                                     state is not final                               */
+} JgpuNet;
+
+/* HMM topology view of IModels.  Replaces: getNumHMMs / getNumStates / getTransMat /
+ * getSEIndex / getTeeLogProb (src/Models.h:51-66; tables built by
+ * HTKModels::createTrPandSEIndex, src/HTKModels.cpp:2330-2390, tee :1358-1370) and the
+ * state -> GMM map HMM::gmmInds (src/HTKModels.h:75-82).  stride = max_states. */
+typedef struct JgpuHmm {
+    int32_t        n_hmms;
+    int32_t        max_states;    /* S: row stride of the per-HMM tables below (<= 8)  */
+    const int32_t* n_states;      /* [n_hmms] incl. non-emitting entry (0) and exit    */
+    const int32_t* gmm;           /* [n_hmms*S] GMM id per state, -1 if non-emitting   */
+    const float*   trp;           /* [n_hmms*S*S] trP[i][j] = log a_ij or LOG_ZERO     */
+    const int32_t* se;            /* [n_hmms*S*2] SEIndex[j] = {start,end} of preds    */
+    const float*   tee;           /* [n_hmms] entry->exit log prob or LOG_ZERO         */
+} JgpuHmm;
+
+/* Flat diagonal-GMM parameters.  Replaces: HTKFlatModels::fMixtures / fDets / fMeans /
+ * fVars (src/HTKFlatModels.h:43-63, filled at src/HTKFlatModels.cpp:94-177): every GMM is
+ * padded to max_comps slots; ivars = 1/var; dets = gconst + log weight. */
+typedef struct JgpuGmm {
+    int32_t        n_gmms;
+    int32_t        dim;           /* feature vector size (39 in all configs)           */
+    int32_t        max_comps;     /* C: slots per GMM                                  */
+    const int32_t* n_comps;       /* [n_gmms] used slots                               */
+    const float*   dets;          /* [n_gmms*C]                                        */
+    const float*   means;         /* [n_gmms*C*dim]                                    */
+    const float*   ivars;         /* [n_gmms*C*dim]                                    */
+} JgpuGmm;
+
+/* Decoder settings.  The five pruning fields are the constructor arguments of
+ * WFSTDecoderLite (src/WFSTDecoderLite.h:81-89; call site src/juicer.cpp:584-586) with
+ * the same meaning: a beam <= 0 disables that pruning, max_hyps 0 disables the histogram. */
+typedef struct JgpuCfg {
+    float   start_beam;           /* phoneStartPruneWin */
+    float   main_beam;            /* emitPruneWin       */
+    float   end_beam;             /* phoneEndPruneWin   */
+    float   word_beam;            /* wordPruneWin       */
+    int32_t max_hyps;             /* maxEmitHyps        */
+    int32_t device;               /* CUDA device ordinal */
+    int32_t n_lanes;              /* utterances decoded in lock-step per launch (>=1)  */
+    int32_t max_active;           /* capacity: active HMM instances per lane, 0 = auto */
+    int32_t max_frames;           /* capacity: frames per utterance, 0 = 4096          */
+    int32_t max_paths;            /* capacity: word-boundary records per lane, 0 = auto*/
+    int32_t frame_stats;          /* 1 = keep per-frame work counters (parity tests)   */
+    int32_t reserved;
+} JgpuCfg;
+
+/* One word-boundary record of the best path.  Replaces DecHypHist
+ * (src/DecHypHistPool.h:38-49): label = state (output label = word id + 1), time = frame
+ * in which the word's arc was left, score = normalised running score, ac / lm =
+ * un-normalised cumulative acoustic and LM scores. */
+typedef struct JgpuWord {
+    int32_t label;
+    int32_t time;
+    float   score;
+    float   ac;
+    float   lm;
+} JgpuWord;
+
+/* Result of one utterance.  Replaces DecHyp* returned by IDecoder::finish()
+ * (src/Decoder.h:29; built at src/WFSTDecoderLite.cpp:262-308).
+ *   status >= 0 : number of words on the best path (words[] holds min(status,max_words),
+ *                 oldest first; the last record carries the final-weight-inclusive totals);
+ *   status == -1: no token reached a final state in the last frame (reference: NULL hyp);
+ *   status == -2: a final token survived but its path has no word label (reference:
+ *                 non-NULL but inactive DecHyp, WFSTDecoderLite.cpp:273-306);
+ *   status <= -10: the utterance failed (JGPU_E_CAPACITY - 10 ...) — batch continues. */
+typedef struct JgpuResult {
+    int32_t   status;
+    int32_t   n_frames;
+    float     score;
+    float     ac;
+    float     lm;
+    int32_t   max_words;          /* in: capacity of words[]                           */
+    JgpuWord* words;              /* in: caller-owned buffer                           */
+} JgpuResult;
+
+/* Per-utterance work counters, same definitions as the reference's statistics print
+ * (src/WFSTDecoderLite.cpp:231-241), as sums over frames. */
+typedef struct JgpuStats {
+    int64_t n_frames;
+    int64_t total_active_models;     /* sum of nActiveInsts after each frame            */
+    int64_t total_active_emit_hyps;
+    int64_t total_active_end_hyps;
+    int64_t total_proc_emit_hyps;
+    int64_t total_proc_end_hyps;
+    int64_t total_gmm_evals;         /* distinct (GMM, frame) scores computed           */
+    int64_t total_arcs_expanded;     /* X of SURVEY 8d: out-arcs of distinct states     */
+    int64_t total_entry_writes;      /* W: distinct destination arcs written            */
+    int64_t total_paths;             /* P: word-boundary records appended               */
+} JgpuStats;
+
+typedef struct jgpu_handle jgpu_handle;
+
+const char* jgpu_last_error(void);
+const char* jgpu_version(void);
+
+/* Build device-resident tables and arenas.  Validates the reference's unchecked input
+ * preconditions: label ranges, arc ranges, no epsilon/tee cycles. */
+int jgpu_create(const JgpuNet* net, const JgpuHmm* hmm, const JgpuGmm* gmm, const JgpuCfg* cfg,
+                jgpu_handle** out);
+int jgpu_destroy(jgpu_handle* h);
+
+/* Acoustic scorer alone: out[r*n_gmms + g] = log-likelihood of GMM g for feature row r.
+ * Replaces IModels::calcOutput(int gmmInd) (src/HTKFlatModels.cpp:202-262) evaluated for
+ * every GMM of every row.  x and out are HOST pointers. */
+int jgpu_gmm_scores(jgpu_handle* h, const float* x, int32_t n_rows, float* out);
+
+/* Streaming interface on one lane.  Replaces IDecoder::init / processFrame / finish
+ * (src/Decoder.h:18-30): begin == init(); push_frames(x, n) == n consecutive
+ * processFrame() calls on frames x[0..n); end == finish().  x is a HOST pointer to
+ * n*dim floats. */
+int jgpu_utt_begin(jgpu_handle* h, int32_t lane);
+int jgpu_push_frames(jgpu_handle* h, int32_t lane, const float* x, int32_t n_frames);
+int jgpu_utt_end(jgpu_handle* h, int32_t lane, JgpuResult* out);
+
+/* Whole-utterance batch: decodes n_utts independent utterances, n_lanes at a time in
+ * lock-step, refilling lanes as utterances finish.  feats[u] is a HOST pointer to
+ * n_frames[u]*dim floats.  Replaces the per-file loop of DecoderBatchTest::run
+ * (src/DecoderBatchTest.cpp:690-777) around DecoderSingleTest::decodeUtterance. */
+int jgpu_decode_batch(jgpu_handle* h, const float* const* feats, const int32_t* n_frames,
+                      int32_t n_utts, JgpuResult* out);
+
+/* Same, with all features already resident in device memory as one packed buffer:
+ * utterance u occupies rows [row_offset[u], row_offset[u] + n_frames[u]) of d_feats
+ * (DEVICE pointer, row-major [rows, dim]).  No host<->device feature traffic. */
+int jgpu_decode_batch_device(jgpu_handle* h, const float* d_feats, const int64_t* row_offset,
+                             const int32_t* n_frames, int32_t n_utts, JgpuResult* out);
+
+/* Counters of the most recent utterance decoded on `lane` (streaming) or summed over the
+ * most recent batch call (lane = -1). */
+int jgpu_stats(jgpu_handle* h, int32_t lane, JgpuStats* out);
+
+/* Per-frame work counters of the most recent utterance on `lane` (needs cfg.frame_stats):
+ * cnt[t*4 + {0,1,2,3}] = nActiveInsts, nActiveEmitHyps, nActiveEndHyps, nEndHypsProcessed
+ * after frame t; best[t] = bestEmitScore after frame t.  Returns frames written. */
+int jgpu_frame_stats(jgpu_handle* h, int32_t lane, int32_t* cnt, float* best, int32_t max_frames);
+
+/* Number of kernel launches issued by this handle since creation (bench bookkeeping). */
+int64_t jgpu_launch_count(jgpu_handle* h);
+
+/* ---- host-side loaders (C++ mirrors of the reference's file readers) ------------------
+ * jgpu_load_fsm   : AT&T text network + symbol tables, same semantics as
+ *                   WFSTNetwork(fsm, insyms, outsyms, lmScale, insPenalty, REMOVEBOTH)
+ *                   (src/WFSTNetwork.cpp:371-616).
+ * jgpu_load_jmbi  : JMBI model binary, same semantics as HTKFlatModels::readBinary
+ *                   (src/HTKModels.cpp:1112-1245 + src/HTKFlatModels.cpp:94-177).
+ * The returned structs point into library-owned host memory released by jgpu_free_*. */
+int jgpu_load_fsm(const char* fsm, const char* insyms, const char* outsyms, float lm_scale,
+                  float ins_penalty, JgpuNet* out);
+int jgpu_free_net(JgpuNet* net);
+int jgpu_load_jmbi(const char* path, JgpuHmm* hmm, JgpuGmm* gmm);
+int jgpu_free_models(JgpuHmm* hmm, JgpuGmm* gmm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JUICER_B200_H */

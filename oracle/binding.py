@@ -138,3 +138,56 @@ class OracleRef:
         self.lib.oref_dump_net(self.h, *[_fp(r[k]) for k in ("arc_to", "arc_w", "arc_in", "arc_out",
                                                              "st_first", "st_n", "st_final")])
         return r
+
+
+class OraclePort:
+    """Plain-C restatement (oracle/juicer_oracle.c) on the flat tables of include/juicer_b200.h."""
+
+    def __init__(self, tables, cfg):
+        from juicer_b200 import _abi
+        if not os.path.exists(PORT_SO):
+            build(ref=False, port=True)
+        self._abi = _abi
+        self.lib = C.CDLL(PORT_SO)
+        self.lib.jor_create.restype = C.c_void_p
+        self.lib.jor_create.argtypes = [C.c_void_p] * 4
+        self.lib.jor_decode.restype = C.c_int
+        self.lib.jor_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]
+        self.lib.jor_gmm_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        self.lib.jor_stats.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.jor_destroy.argtypes = [C.c_void_p]
+        self.tables, self.cfg = tables, cfg
+        self.h = self.lib.jor_create(C.byref(tables.net), C.byref(tables.hmm), C.byref(tables.gmm), C.byref(cfg))
+        if not self.h:
+            raise RuntimeError("jor_create failed (max_states > 8?)")
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.jor_destroy(self.h)
+            self.h = None
+
+    def decode(self, feats: np.ndarray, counters: bool = False, max_words: int = 4096) -> DecodeResult:
+        abi = self._abi
+        feats = np.ascontiguousarray(feats, dtype=np.float32)
+        T = feats.shape[0]
+        words = (abi.JgpuWord * max_words)()
+        res = abi.JgpuResult(0, 0, 0.0, 0.0, 0.0, max_words, C.cast(words, C.POINTER(abi.JgpuWord)))
+        cnt = np.zeros((T, 6), dtype=np.int32) if counters else None
+        best = np.zeros(T, dtype=np.float32) if counters else None
+        sec = C.c_double(0.0)
+        st = self.lib.jor_decode(self.h, _fp(feats), T, C.byref(res), _fp(cnt) if counters else None,
+                                 _fp(best) if counters else None, C.byref(sec))
+        totals = np.asarray([res.score, res.ac, res.lm], dtype=np.float32)
+        return DecodeResult(st, abi.words_to_list(res), totals, cnt, best, sec.value)
+
+    def gmm_scores(self, feats: np.ndarray) -> np.ndarray:
+        feats = np.ascontiguousarray(feats, dtype=np.float32)
+        out = np.zeros((feats.shape[0], self.tables.n_gmm), dtype=np.float32)
+        self.lib.jor_gmm_scores(self.h, _fp(feats), feats.shape[0], _fp(out))
+        return out
+
+    def stats(self) -> Dict[str, int]:
+        s = self._abi.JgpuStats()
+        self.lib.jor_stats(self.h, C.byref(s))
+        return s.as_dict()
