@@ -1,0 +1,354 @@
+// host_loaders.cpp — host-side file readers feeding the device tables.
+//
+// These mirror, value for value, what the reference's own loaders leave in memory, so the
+// CUDA path decodes the SAME numbers as WFSTDecoderLite would:
+//   jgpu_load_fsm   <-> WFSTNetwork::WFSTNetwork(fsm, insyms, outsyms, scale, insPenalty,
+//                       REMOVEBOTH)                         src/WFSTNetwork.cpp:371-616
+//                       WFSTAlphabet::WFSTAlphabet(file)    src/WFSTNetwork.cpp:52-112
+//                       removeAuxiliarySymbols(true)        src/WFSTNetwork.cpp:1421-1456
+//   jgpu_load_jmbi  <-> HTKModels::readBinary               src/HTKModels.cpp:1112-1245
+//                       createTrPandSEIndex                 src/HTKModels.cpp:2330-2390
+//                       tee weight                          src/HTKModels.cpp:1358-1370
+//                       HTKFlatModels::init                 src/HTKFlatModels.cpp:94-177
+// Host only: no CUDA calls here.
+#include <cfloat>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/juicer_b200.h"
+#include "jgpu_err.h"
+
+std::string& jgpu_err_buf()
+{
+    static thread_local std::string buf;
+    return buf;
+}
+
+namespace {
+
+#define LZ (-FLT_MAX)
+
+int io_fail(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    jgpu_err_buf() = buf;
+    return JGPU_E_IO;
+}
+
+struct Alphabet {
+    int max_label = -1;
+    int n_labels = 0;
+    std::vector<char> present, aux;
+    std::vector<std::string> names;
+};
+
+int read_alphabet(const char* fname, Alphabet* a)
+{
+    FILE* fd = fopen(fname, "rb");
+    if (!fd) return io_fail("cannot open symbols file %s", fname);
+    char line[10000], sym[10000];
+    int id;
+    while (fgets(line, sizeof(line), fd)) {
+        if (sscanf(line, "%s %d", sym, &id) != 2) continue;
+        if (id < 0) { fclose(fd); return io_fail("%s: negative symbol id", fname); }
+        if (id >= (int)a->present.size()) {
+            a->present.resize(id + 1000, 0);
+            a->aux.resize(id + 1000, 0);
+            a->names.resize(id + 1000);
+        }
+        if (a->present[id]) { fclose(fd); return io_fail("%s: duplicate symbol id %d", fname, id); }
+        a->present[id] = 1;
+        a->names[id] = sym;
+        a->aux[id] = sym[0] == '#';                    // auxiliary symbols start with '#'
+        a->n_labels++;
+        if (id > a->max_label) a->max_label = id;
+    }
+    fclose(fd);
+    return JGPU_OK;
+}
+
+template <typename T>
+T* dup_vec(const std::vector<T>& v)
+{
+    T* p = (T*)malloc(sizeof(T) * (v.size() ? v.size() : 1));
+    if (!v.empty()) memcpy(p, v.data(), sizeof(T) * v.size());
+    return p;
+}
+
+bool rd(FILE* f, void* p, size_t sz, size_t n) { return fread(p, sz, n, f) == n; }
+
+bool rd_tag_name(FILE* f, const char* tag)
+{
+    char id[5] = {0};
+    if (!rd(f, id, 4, 1) || strcmp(id, tag) != 0) return false;
+    int len;
+    if (!rd(f, &len, 4, 1) || len < 0) return false;
+    if (len > 0 && fseek(f, len, SEEK_CUR) != 0) return false;
+    return true;
+}
+
+} // namespace
+
+extern "C" int jgpu_load_fsm(const char* fsm, const char* insyms, const char* outsyms, float lm_scale,
+                             float ins_penalty, JgpuNet* out)
+{
+    if (!fsm || !insyms || !outsyms || !out) return io_fail("jgpu_load_fsm: null argument (both symbol files are mandatory)");
+    memset(out, 0, sizeof(*out));
+    FILE* fd = fopen(fsm, "rb");
+    if (!fd) return io_fail("cannot open network file %s", fsm);
+    std::vector<int> to, in, ol, st_first, st_n, fin_id;
+    std::vector<float> w, fin_w;
+    int init_state = -1, max_state = -1, max_in = -1, max_out = -1;
+    char line[10000];
+    int from, t, i, o, fs;
+    float weight;
+    while (fgets(line, sizeof(line), fd)) {
+        if (sscanf(line, "%d %d %d %d %f", &from, &t, &i, &o, &weight) != 5) {
+            if (sscanf(line, "%d %d %d %d", &from, &t, &i, &o) != 4) {
+                if (sscanf(line, "%d %f", &fs, &weight) != 2) {
+                    if (sscanf(line, "%d", &fs) != 1) continue;
+                    weight = 0.0;
+                }
+                fin_id.push_back(fs);
+                fin_w.push_back((float)(-weight * lm_scale));
+                continue;
+            } else {
+                weight = 0.0;
+            }
+        }
+        if (from < 0 || t < 0 || i < 0 || o < 0) { fclose(fd); return io_fail("%s: negative field in arc line", fsm); }
+        if (init_state < 0) init_state = from;          // source state of the first line
+        if (from > max_state) max_state = from;
+        if (t > max_state) max_state = t;
+        float wt = (float)(-weight * lm_scale);          // FSM weights are -log
+        if (o > 0) wt += ins_penalty;
+        const int id = (int)to.size();
+        to.push_back(t); in.push_back(i); ol.push_back(o); w.push_back(wt);
+        if (i > max_in) max_in = i;
+        if (o > max_out) max_out = o;
+        if (max_state >= (int)st_n.size()) {
+            st_n.resize((size_t)max_state * 2 + 1024, 0);
+            st_first.resize(st_n.size(), 0);
+        }
+        if (st_n[from]++ == 0) st_first[from] = id;      // getTransitions: first arc + count
+    }
+    fclose(fd);
+    if (init_state < 0) return io_fail("%s: no arcs", fsm);
+    const int n_states = max_state + 1;
+    st_n.resize(n_states);
+    st_first.resize(n_states);
+    std::vector<float> st_final(n_states, LZ);
+    for (size_t k = 0; k < fin_id.size(); ++k) {
+        if (fin_id[k] < 0 || fin_id[k] > max_state) return io_fail("%s: final state %d out of range", fsm, fin_id[k]);
+        st_final[fin_id[k]] = fin_w[k];
+    }
+    // arcs of one state must be contiguous for the reference's getTransitions(prev,&next)
+    for (int s = 0; s < n_states; ++s)
+        if (st_n[s] > 0 && st_first[s] + st_n[s] > (int)to.size())
+            return io_fail("%s: arcs of state %d are not contiguous", fsm, s);
+
+    Alphabet ia, oa;
+    int rc;
+    if ((rc = read_alphabet(insyms, &ia))) return rc;
+    if ((rc = read_alphabet(outsyms, &oa))) return rc;
+    if (max_in > ia.max_label) return io_fail("maxInLab > inputAlphabet->getMaxLabel()");
+    if (max_out > oa.max_label) return io_fail("maxOutLab=%d > outputAlphabet->getMaxLabel()=%d", max_out, oa.max_label);
+    max_in = ia.max_label;
+    max_out = oa.max_label;
+    int word_end_marker = max_in + 1;
+    if (word_end_marker <= max_out) word_end_marker = max_out + 1;
+    for (size_t a = 0; a < to.size(); ++a) {             // removeAuxiliarySymbols(markAux = true)
+        if (!ia.present[in[a]]) return io_fail("input label %d has no symbol-table entry", in[a]);
+        if (!oa.present[ol[a]]) return io_fail("output label %d has no symbol-table entry", ol[a]);
+        if (ia.aux[in[a]]) in[a] = word_end_marker;
+        if (oa.aux[ol[a]]) ol[a] = word_end_marker;
+    }
+    for (int k = 0; k < ia.n_labels; ++k)                // the reference calls getLabel(i) for i < nLabels
+        if (k > ia.max_label || !ia.present[k]) return io_fail("input symbol table has a hole at id %d", k);
+
+    out->n_states = n_states;
+    out->n_arcs = (int)to.size();
+    out->init_state = init_state;
+    out->arc_to = dup_vec(to);
+    out->arc_weight = dup_vec(w);
+    out->arc_in = dup_vec(in);
+    out->arc_out = dup_vec(ol);
+    out->state_first = dup_vec(st_first);
+    out->state_narcs = dup_vec(st_n);
+    out->state_final = dup_vec(st_final);
+    return JGPU_OK;
+}
+
+extern "C" int jgpu_free_net(JgpuNet* n)
+{
+    if (!n) return JGPU_OK;
+    free((void*)n->arc_to); free((void*)n->arc_weight); free((void*)n->arc_in); free((void*)n->arc_out);
+    free((void*)n->state_first); free((void*)n->state_narcs); free((void*)n->state_final);
+    memset(n, 0, sizeof(*n));
+    return JGPU_OK;
+}
+
+extern "C" int jgpu_load_jmbi(const char* path, JgpuHmm* hmm, JgpuGmm* gmm)
+{
+    if (!path || !hmm || !gmm) return io_fail("jgpu_load_jmbi: null argument");
+    memset(hmm, 0, sizeof(*hmm));
+    memset(gmm, 0, sizeof(*gmm));
+    FILE* f = fopen(path, "rb");
+    if (!f) return io_fail("cannot open model file %s", path);
+#define BAD(msg) do { fclose(f); return io_fail("%s: %s", path, msg); } while (0)
+    char id[5] = {0};
+    int hdr[7];
+    if (!rd(f, id, 4, 1) || strcmp(id, "JMBI") != 0) BAD("not a JMBI file");
+    if (!rd(f, hdr, 4, 7)) BAD("truncated header");
+    const int D = hdr[0], nMean = hdr[1], nVar = hdr[2], nMix = hdr[3], nGMM = hdr[4], nTM = hdr[5], nHMM = hdr[6];
+    if (D <= 0 || nMean < 0 || nVar < 0 || nMix < 0 || nGMM < 0 || nTM < 0 || nHMM < 0) BAD("bad counts");
+    std::vector<float> means((size_t)nMean * D), vars((size_t)nVar * D), gconst(nVar), skip(D);
+    for (int i = 0; i < nMean; ++i) {
+        if (!rd_tag_name(f, "JMMN") || !rd(f, &means[(size_t)i * D], 4, D)) BAD("bad mean vector record");
+    }
+    for (int i = 0; i < nVar; ++i) {
+        if (!rd_tag_name(f, "JMVR") || !rd(f, &vars[(size_t)i * D], 4, D) || !rd(f, skip.data(), 4, D) ||
+            !rd(f, &gconst[i], 4, 1))
+            BAD("bad variance vector record");
+    }
+    std::vector<std::vector<int>> mix_mean(nMix), mix_var(nMix);
+    int maxC = 0;
+    for (int i = 0; i < nMix; ++i) {
+        int nc;
+        if (!rd_tag_name(f, "JMMX") || !rd(f, &nc, 4, 1) || nc < 0) BAD("bad mixture record");
+        mix_mean[i].resize(nc);
+        mix_var[i].resize(nc);
+        if (!rd(f, mix_mean[i].data(), 4, nc) || !rd(f, mix_var[i].data(), 4, nc)) BAD("bad mixture record");
+        for (int c = 0; c < nc; ++c)
+            if (mix_mean[i][c] < 0 || mix_mean[i][c] >= nMean || mix_var[i][c] < 0 || mix_var[i][c] >= nVar) BAD("mixture index out of range");
+        if (nc > maxC) maxC = nc;
+    }
+    std::vector<int> gmm_mix(nGMM);
+    std::vector<std::vector<float>> gmm_logw(nGMM);
+    for (int i = 0; i < nGMM; ++i) {
+        int nc;
+        if (!rd_tag_name(f, "JMGM") || !rd(f, &gmm_mix[i], 4, 1) || !rd(f, &nc, 4, 1) || nc < 0) BAD("bad GMM record");
+        std::vector<float> wts(nc);
+        gmm_logw[i].resize(nc);
+        if (!rd(f, wts.data(), 4, nc) || !rd(f, gmm_logw[i].data(), 4, nc)) BAD("bad GMM record");
+        if (gmm_mix[i] < 0 || gmm_mix[i] >= nMix) BAD("GMM mixture index out of range");
+    }
+    struct TM { int n; std::vector<int> nsucs; std::vector<std::vector<int>> sucs; std::vector<std::vector<float>> logp; };
+    std::vector<TM> tms(nTM);
+    for (int i = 0; i < nTM; ++i) {
+        TM& t = tms[i];
+        if (!rd_tag_name(f, "JMTM") || !rd(f, &t.n, 4, 1) || t.n <= 0 || t.n > 64) BAD("bad transition matrix record");
+        t.nsucs.resize(t.n);
+        if (!rd(f, t.nsucs.data(), 4, t.n)) BAD("bad transition matrix record");
+        int total = 0;
+        for (int s = 0; s < t.n; ++s) { if (t.nsucs[s] < 0) BAD("bad successor count"); total += t.nsucs[s]; }
+        std::vector<int> sucs(total);
+        std::vector<float> probs(total), logp(total);
+        if (!rd(f, sucs.data(), 4, total) || !rd(f, probs.data(), 4, total) || !rd(f, logp.data(), 4, total)) BAD("bad transition matrix record");
+        t.sucs.resize(t.n);
+        t.logp.resize(t.n);
+        int k = 0;
+        for (int s = 0; s < t.n; ++s)
+            for (int j = 0; j < t.nsucs[s]; ++j, ++k) {
+                if (sucs[k] < 0 || sucs[k] >= t.n) BAD("successor out of range");
+                t.sucs[s].push_back(sucs[k]);
+                t.logp[s].push_back(logp[k]);
+            }
+    }
+    std::vector<int> hmm_n(nHMM), hmm_tm(nHMM);
+    std::vector<std::vector<int>> hmm_g(nHMM);
+    int maxS = 0;
+    for (int i = 0; i < nHMM; ++i) {
+        if (!rd_tag_name(f, "JMHM") || !rd(f, &hmm_n[i], 4, 1) || hmm_n[i] <= 0 || hmm_n[i] > 64) BAD("bad HMM record");
+        hmm_g[i].resize(hmm_n[i]);
+        if (!rd(f, hmm_g[i].data(), 4, hmm_n[i]) || !rd(f, &hmm_tm[i], 4, 1)) BAD("bad HMM record");
+        if (hmm_tm[i] < 0 || hmm_tm[i] >= nTM || tms[hmm_tm[i]].n != hmm_n[i]) BAD("HMM / transition matrix mismatch");
+        if (hmm_n[i] > maxS) maxS = hmm_n[i];
+    }
+    unsigned char hybrid = 0;
+    if (!rd(f, &hybrid, 1, 1)) BAD("missing hybridMode flag");
+    fclose(f);
+#undef BAD
+    if (hybrid) return io_fail("%s: hybrid (ANN posterior) models are outside the GMM decode path", path);
+
+    // ---- HMM view: trP / SEIndex / tee (src/HTKModels.cpp:2330-2390, :1358-1370) ----
+    const int S = maxS;
+    std::vector<int> o_n(hmm_n), o_gmm((size_t)nHMM * S, -1), o_se((size_t)nHMM * S * 2, 0);
+    std::vector<float> o_trp((size_t)nHMM * S * S, LZ), o_tee(nHMM, LZ);
+    for (int i = 0; i < nHMM; ++i) {
+        const TM& t = tms[hmm_tm[i]];
+        const int n = t.n;
+        std::vector<float> trp((size_t)n * n, LZ);
+        for (int j = 0; j < n; ++j)
+            for (size_t k = 0; k < t.sucs[j].size(); ++k) trp[(size_t)j * n + t.sucs[j][k]] = t.logp[j][k];
+        for (int a = 0; a < n; ++a) {
+            o_gmm[(size_t)i * S + a] = hmm_g[i][a];
+            for (int b = 0; b < n; ++b) o_trp[((size_t)i * S + a) * S + b] = trp[(size_t)a * n + b];
+        }
+        for (int j = 1; j < n; ++j) {
+            int mn, mx;
+            for (mn = (j == n - 1 ? 1 : 0); mn < n - 1; ++mn)
+                if (trp[(size_t)mn * n + j] > LZ) break;
+            for (mx = n - 1; mx >= 1; --mx)
+                if (trp[(size_t)mx * n + j] > LZ) break;
+            o_se[((size_t)i * S + j) * 2 + 0] = mn;
+            o_se[((size_t)i * S + j) * 2 + 1] = mx + 1;
+        }
+        for (size_t k = 1; k < t.sucs[0].size(); ++k)     // tee: entry -> exit as successor index >= 1
+            if (t.sucs[0][k] == n - 1) {
+                if (o_tee[i] != LZ) return io_fail("more than one tee transition in HMM %d", i);
+                o_tee[i] = t.logp[0][k];
+            }
+    }
+    // ---- flat GMM parameters (src/HTKFlatModels.cpp:94-177) ----
+    if (nGMM > nMix) return io_fail("HTKFlatModels needs one mixture per GMM (nGMMs=%d > nMixtures=%d)", nGMM, nMix);
+    const int C = maxC > 0 ? maxC : 1;
+    std::vector<int> o_nc(nGMM);
+    std::vector<float> o_det((size_t)nGMM * C, LZ), o_mu((size_t)nGMM * C * D, 0.0f), o_iv((size_t)nGMM * C * D, 0.0f);
+    for (int g = 0; g < nGMM; ++g) {
+        // flat parameters of slot g come from mixture g (:143-165); log weights from GMM g's
+        // own mixture (:169-176) — identical when gMMs[g].mixtureInd == g, which the reference assumes
+        const int mi = g;
+        const int nc = (int)mix_mean[mi].size();
+        if ((int)gmm_logw[g].size() < (int)mix_mean[gmm_mix[g]].size()) return io_fail("GMM %d: weight count mismatch", g);
+        o_nc[g] = nc;
+        for (int c = 0; c < nc; ++c) {
+            const float* mo = &means[(size_t)mix_mean[mi][c] * D];
+            const float* vo = &vars[(size_t)mix_var[mi][c] * D];
+            for (int k = 0; k < D; ++k) {
+                o_mu[((size_t)g * C + c) * D + k] = mo[k];
+                o_iv[((size_t)g * C + c) * D + k] = (float)(1.0 / vo[k]);    // :160
+            }
+            o_det[(size_t)g * C + c] = gconst[mix_var[mi][c]];                // :163
+        }
+        const int nc2 = (int)mix_mean[gmm_mix[g]].size();
+        for (int c = 0; c < nc2 && c < C; ++c) o_det[(size_t)g * C + c] += gmm_logw[g][c];   // :174
+    }
+    hmm->n_hmms = nHMM; hmm->max_states = S;
+    hmm->n_states = dup_vec(o_n); hmm->gmm = dup_vec(o_gmm); hmm->trp = dup_vec(o_trp);
+    hmm->se = dup_vec(o_se); hmm->tee = dup_vec(o_tee);
+    gmm->n_gmms = nGMM; gmm->dim = D; gmm->max_comps = C;
+    gmm->n_comps = dup_vec(o_nc); gmm->dets = dup_vec(o_det); gmm->means = dup_vec(o_mu); gmm->ivars = dup_vec(o_iv);
+    return JGPU_OK;
+}
+
+extern "C" int jgpu_free_models(JgpuHmm* hmm, JgpuGmm* gmm)
+{
+    if (hmm) {
+        free((void*)hmm->n_states); free((void*)hmm->gmm); free((void*)hmm->trp); free((void*)hmm->se); free((void*)hmm->tee);
+        memset(hmm, 0, sizeof(*hmm));
+    }
+    if (gmm) {
+        free((void*)gmm->n_comps); free((void*)gmm->dets); free((void*)gmm->means); free((void*)gmm->ivars);
+        memset(gmm, 0, sizeof(*gmm));
+    }
+    return JGPU_OK;
+}

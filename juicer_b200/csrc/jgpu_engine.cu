@@ -1,0 +1,768 @@
+// jgpu_engine.cu — host engine + C ABI (include/juicer_b200.h) over the sm_100a kernels.
+//
+// The engine owns the device-resident network / model tables and the per-lane decoding
+// state, turns utterances into a lock-step schedule (one table row per frame step and
+// lane), and enqueues the per-step kernel sequence on one CUDA stream.  Nothing in the
+// decode loop synchronises with the host: thresholds, list sizes and round counts all live
+// in device memory; the host only waits in utt_end / at the end of a batch.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <queue>
+#include <string>
+#include <vector>
+
+#include "jgpu_device.cuh"
+#include "jgpu_err.h"
+#include "jgpu_gmm.cuh"
+#include "jgpu_search.cuh"
+
+namespace {
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    jgpu_err_buf() = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(JGPU_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct LaneHost {
+    bool begun = false;
+    bool seeded = false;
+    int frames = 0;
+};
+
+} // namespace
+
+struct jgpu_handle {
+    Dev d{};
+    GmmDev g{};
+    JgpuCfg cfg{};
+    int device = 0;
+    int S = 5;              // kernel template parameter (5 or 8)
+    int DP = 40;            // padded feature dimension
+    int dim = 39;
+    int FB = 16;            // frames per GMM scoring block
+    int bpl = 8;            // CTAs per lane for the search kernels
+    bool has_huge = false;
+    int max_deg = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> allocs;
+    size_t bytes = 0;
+    // schedule
+    int sched_chunk = 2048;
+    int4* d_sched = nullptr;
+    int* d_rows = nullptr;
+    // features / scores
+    float* d_feats = nullptr;
+    size_t feats_cap = 0;   // rows
+    float* d_stream_feats = nullptr;
+    int stream_chunk = 256;
+    float* d_scores = nullptr;
+    float* d_gmm_out = nullptr;   // jgpu_gmm_scores scratch
+    int gmm_chunk = 1024;
+    // results
+    size_t res_cap = 0;
+    std::vector<LaneHost> lanes;
+    int64_t launches = 0;
+    JgpuStats batch_stats{};
+
+    template <typename T>
+    int alloc(T** p, size_t n, bool zero = true)
+    {
+        void* q = nullptr;
+        const size_t b = std::max<size_t>(n, 1) * sizeof(T);
+        cudaError_t e = cudaMalloc(&q, b);
+        if (e != cudaSuccess)
+            return fail(JGPU_E_CUDA, "cudaMalloc(%zu bytes) failed: %s (already holding %zu bytes)", b,
+                        cudaGetErrorString(e), bytes);
+        if (zero) {
+            e = cudaMemsetAsync(q, 0, b, stream);
+            if (e != cudaSuccess) return fail(JGPU_E_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+        }
+        allocs.push_back(q);
+        bytes += b;
+        *p = (T*)q;
+        return JGPU_OK;
+    }
+    void release(void* p)
+    {
+        if (!p) return;
+        auto it = std::find(allocs.begin(), allocs.end(), p);
+        if (it != allocs.end()) allocs.erase(it);
+        cudaFree(p);
+    }
+};
+
+namespace {
+
+template <typename T>
+int upload(jgpu_handle* h, T** dst, const std::vector<T>& src)
+{
+    int rc = h->alloc(dst, src.size(), false);
+    if (rc) return rc;
+    if (!src.empty()) CK(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return JGPU_OK;
+}
+
+// longest chain of pass-through arcs (epsilon input or tee model); -1 on a cycle.
+int passthrough_depth(const JgpuNet* n, const std::vector<char>& pass)
+{
+    const int S = n->n_states;
+    std::vector<int> indeg(S, 0), depth(S, 0);
+    for (int s = 0; s < S; ++s)
+        for (int b = n->state_first[s]; b < n->state_first[s] + n->state_narcs[s]; ++b)
+            if (pass[b]) ++indeg[n->arc_to[b]];
+    std::vector<int> q;
+    q.reserve(S);
+    for (int s = 0; s < S; ++s)
+        if (indeg[s] == 0) q.push_back(s);
+    size_t head = 0;
+    int best = 0;
+    while (head < q.size()) {
+        const int s = q[head++];
+        for (int b = n->state_first[s]; b < n->state_first[s] + n->state_narcs[s]; ++b) {
+            if (!pass[b]) continue;
+            const int t = n->arc_to[b];
+            depth[t] = std::max(depth[t], depth[s] + 1);
+            best = std::max(best, depth[t]);
+            if (--indeg[t] == 0) q.push_back(t);
+        }
+    }
+    if ((int)q.size() != S) return -1;
+    return best;
+}
+
+int validate(const JgpuNet* n, const JgpuHmm* m, const JgpuGmm* g, const JgpuCfg* c)
+{
+    if (!n || !m || !g || !c) return fail(JGPU_E_ARG, "null argument");
+    if (n->n_states <= 0 || n->n_arcs < 0) return fail(JGPU_E_ARG, "empty network");
+    if (n->init_state < 0 || n->init_state >= n->n_states) return fail(JGPU_E_ARG, "init_state out of range");
+    if (m->n_hmms <= 0 || m->max_states < 2 || m->max_states > 8)
+        return fail(JGPU_E_ARG, "max_states=%d unsupported (2..8)", m->max_states);
+    if (g->dim <= 0 || g->dim > JG_GMM_DMAX) return fail(JGPU_E_ARG, "feature dim %d unsupported (1..%d)", g->dim, JG_GMM_DMAX);
+    if (g->max_comps <= 0 || g->max_comps > 256) return fail(JGPU_E_ARG, "max_comps %d unsupported (1..256)", g->max_comps);
+    if (c->n_lanes < 1 || c->n_lanes > 4096) return fail(JGPU_E_ARG, "n_lanes %d out of range", c->n_lanes);
+    for (int s = 0; s < n->n_states; ++s) {
+        const int f = n->state_first[s], k = n->state_narcs[s];
+        if (k < 0 || (k > 0 && (f < 0 || f + k > n->n_arcs))) return fail(JGPU_E_ARG, "state %d arc range invalid", s);
+    }
+    for (int a = 0; a < n->n_arcs; ++a) {
+        if (n->arc_to[a] < 0 || n->arc_to[a] >= n->n_states) return fail(JGPU_E_ARG, "arc %d: toState out of range", a);
+        // the reference never checks this (checkConsistency is dead code, src/juicer.cpp:1001-1061)
+        if (n->arc_in[a] < 0 || n->arc_in[a] > m->n_hmms)
+            return fail(JGPU_E_ARG, "arc %d: input label %d is not an HMM index + 1 (n_hmms=%d)", a, n->arc_in[a], m->n_hmms);
+        if (n->arc_out[a] < 0) return fail(JGPU_E_ARG, "arc %d: negative output label", a);
+    }
+    for (int h = 0; h < m->n_hmms; ++h) {
+        const int ns = m->n_states[h];
+        if (ns < 2 || ns > m->max_states) return fail(JGPU_E_ARG, "hmm %d: n_states %d invalid", h, ns);
+        for (int s = 1; s < ns - 1; ++s) {
+            const int gi = m->gmm[h * m->max_states + s];
+            if (gi < 0 || gi >= g->n_gmms) return fail(JGPU_E_ARG, "hmm %d state %d: gmm %d out of range", h, s, gi);
+        }
+    }
+    for (int i = 0; i < g->n_gmms; ++i)
+        if (g->n_comps[i] < 1 || g->n_comps[i] > g->max_comps) return fail(JGPU_E_ARG, "gmm %d: n_comps invalid", i);
+    return JGPU_OK;
+}
+
+int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuGmm* g)
+{
+    Dev& d = h->d;
+    const int A = n->n_arcs, NS = n->n_states, H = m->n_hmms, M = m->max_states;
+    const int S = M <= 5 ? 5 : 8;
+    h->S = S;
+    d.S = S;
+    d.n_arcs = A; d.n_states = NS; d.init_state = n->init_state; d.n_hmms = H; d.n_gmms = g->n_gmms;
+
+    // network
+    std::vector<int4> arcs(A);
+    for (int a = 0; a < A; ++a) {
+        int wbits;
+        memcpy(&wbits, &n->arc_weight[a], 4);
+        arcs[a] = make_int4(n->arc_to[a], wbits, n->arc_in[a], n->arc_out[a]);
+    }
+    std::vector<int2> states(NS);
+    std::vector<float> fin(n->state_final, n->state_final + NS);
+    int max_deg = 0;
+    for (int s = 0; s < NS; ++s) {
+        states[s] = make_int2(n->state_first[s], n->state_narcs[s]);
+        max_deg = std::max(max_deg, n->state_narcs[s]);
+    }
+    h->max_deg = max_deg;
+    bool any_tee = false;
+    for (int i = 0; i < H; ++i) any_tee |= m->tee[i] > JG_LZ;
+    std::vector<char> pass(A);
+    std::vector<float> arc_tee(A, JG_LZ);
+    for (int a = 0; a < A; ++a) {
+        const int in = n->arc_in[a];
+        if (in > 0) arc_tee[a] = m->tee[in - 1];
+        pass[a] = (in == 0) || (arc_tee[a] > JG_LZ);
+    }
+    const int depth = passthrough_depth(n, pass);
+    if (depth < 0) return fail(JGPU_E_ARG, "network has a cycle of epsilon/tee arcs (the reference would recurse forever)");
+    if (depth + 1 > JG_MAX_ROUNDS) return fail(JGPU_E_ARG, "epsilon/tee chains of depth %d exceed %d rounds", depth, JG_MAX_ROUNDS);
+    d.n_rounds = depth + 1;
+
+    // HMM classes: deduplicate (nst, trP, SEIndex)
+    std::map<std::string, int> cls_of;
+    std::vector<float> trp;
+    std::vector<int2> se;
+    std::vector<int> info((size_t)H * 8, -1);
+    for (int i = 0; i < H; ++i) {
+        const int ns = m->n_states[i];
+        std::vector<float> t((size_t)S * S, JG_LZ);
+        std::vector<int2> e(S, make_int2(0, 0));
+        for (int a = 0; a < ns; ++a) {
+            for (int b = 0; b < ns; ++b) t[a * S + b] = m->trp[((size_t)i * M + a) * M + b];
+            e[a] = make_int2(m->se[((size_t)i * M + a) * 2], m->se[((size_t)i * M + a) * 2 + 1]);
+        }
+        std::string key((const char*)&ns, 4);
+        key.append((const char*)t.data(), t.size() * 4);
+        key.append((const char*)e.data(), e.size() * 8);
+        auto it = cls_of.find(key);
+        int cls;
+        if (it == cls_of.end()) {
+            cls = (int)cls_of.size();
+            cls_of.emplace(key, cls);
+            trp.insert(trp.end(), t.begin(), t.end());
+            se.insert(se.end(), e.begin(), e.end());
+        } else {
+            cls = it->second;
+        }
+        int teebits;
+        memcpy(&teebits, &m->tee[i], 4);
+        info[(size_t)i * 8 + 0] = ns | (cls << 8);
+        info[(size_t)i * 8 + 1] = teebits;
+        for (int s = 1; s < ns - 1; ++s) info[(size_t)i * 8 + 1 + s] = m->gmm[i * M + s];
+    }
+
+    int rc;
+    int4* d_arcs; int2* d_states; float* d_fin; float* d_tee = nullptr; int* d_info; float* d_trp; int2* d_se;
+    if ((rc = upload(h, &d_arcs, arcs))) return rc;
+    if ((rc = upload(h, &d_states, states))) return rc;
+    if ((rc = upload(h, &d_fin, fin))) return rc;
+    if (any_tee && (rc = upload(h, &d_tee, arc_tee))) return rc;
+    if ((rc = upload(h, &d_info, info))) return rc;
+    if ((rc = upload(h, &d_trp, trp))) return rc;
+    if ((rc = upload(h, &d_se, se))) return rc;
+    d.arcs = d_arcs; d.states = d_states; d.state_final = d_fin; d.arc_tee = d_tee;
+    d.hmm_info = d_info; d.trp = d_trp; d.se = d_se;
+
+    // GMM parameters, transposed [d][c][g], zero padded
+    GmmDev& G = h->g;
+    const int C = g->max_comps, D = g->dim;
+    const int DP = (D + 3) & ~3;
+    h->DP = DP <= 16 ? 16 : DP <= 28 ? 28 : DP <= 40 ? 40 : DP <= 52 ? 52 : 64;
+    h->dim = D;
+    G.n_gmms = g->n_gmms; G.C = C; G.D = D; G.gpb = std::max(1, 256 / C);
+    G.g_pad = (g->n_gmms + G.gpb - 1) / G.gpb * G.gpb;
+    const size_t plane = (size_t)C * G.g_pad;
+    std::vector<float> mu((size_t)h->DP * plane, 0.0f), iv((size_t)h->DP * plane, 0.0f), det(plane, JG_LZ);
+    std::vector<int> nc(G.g_pad, 0);
+    for (int gi = 0; gi < g->n_gmms; ++gi) {
+        nc[gi] = g->n_comps[gi];
+        for (int c = 0; c < g->n_comps[gi]; ++c) {
+            det[(size_t)c * G.g_pad + gi] = g->dets[(size_t)gi * C + c];
+            for (int dd = 0; dd < D; ++dd) {
+                mu[(size_t)dd * plane + (size_t)c * G.g_pad + gi] = g->means[((size_t)gi * C + c) * D + dd];
+                iv[(size_t)dd * plane + (size_t)c * G.g_pad + gi] = g->ivars[((size_t)gi * C + c) * D + dd];
+            }
+        }
+    }
+    float *d_mu, *d_iv, *d_det; int* d_nc;
+    if ((rc = upload(h, &d_mu, mu))) return rc;
+    if ((rc = upload(h, &d_iv, iv))) return rc;
+    if ((rc = upload(h, &d_det, det))) return rc;
+    if ((rc = upload(h, &d_nc, nc))) return rc;
+    G.mu = d_mu; G.iv = d_iv; G.det = d_det; G.ncomp = d_nc;
+    return JGPU_OK;
+}
+
+int build_state(jgpu_handle* h)
+{
+    Dev& d = h->d;
+    const JgpuCfg& c = h->cfg;
+    const size_t L = c.n_lanes;
+    d.start_beam = c.start_beam; d.main_beam = c.main_beam; d.end_beam = c.end_beam; d.word_beam = c.word_beam;
+    d.max_hyps = c.max_hyps;
+    d.hist_min = 0; d.hist_max = 0; d.hist_nbins = 1;
+    if (c.max_hyps > 0) {                                 // src/WFSTDecoderLite.cpp:76-82, src/Histogram.cpp:29-37
+        const float mn = c.main_beam > 0.0 ? (float)(-c.main_beam - 800.0) : (float)-1000.0;
+        d.hist_min = (int)(mn - 1.0);
+        d.hist_max = (int)((float)200.0 + 1.0);
+        d.hist_nbins = d.hist_max - d.hist_min + 1;
+    }
+    d.n_lanes = c.n_lanes;
+    d.cap = c.max_active > 0 ? c.max_active : std::min(d.n_arcs + 1, 1 << 18);
+    d.cap = std::max(d.cap, 64);
+    d.cap_arr = 2 * d.cap + 1024;
+    d.cap_paths = c.max_paths > 0 ? c.max_paths : (1 << 21);
+    d.cap_huge = 1024;
+    d.max_frames = c.max_frames > 0 ? c.max_frames : 4096;
+    d.frame_stats = c.frame_stats;
+    d.max_words = 256;
+    d.small_deg = 4;
+    d.huge_deg = 1024;
+    h->has_huge = h->max_deg >= d.huge_deg;
+    h->bpl = std::max(2, std::min(296, (1184 + c.n_lanes - 1) / c.n_lanes));
+
+    const size_t cap = d.cap, P = d.S - 1;
+    size_t need = L * (2 * cap * 4 + 2 * P * cap * 16 + (size_t)d.n_arcs * 12 + (size_t)d.n_states * 8 + cap * 24 +
+                       (size_t)d.cap_arr * 36 + (size_t)d.cap_paths * 32);
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    if (need + (1ull << 30) > free_b)
+        return fail(JGPU_E_CAPACITY, "decoder state needs %.1f GB for %d lanes but only %.1f GB of device memory is free",
+                    need / 1e9, c.n_lanes, free_b / 1e9);
+    int rc;
+    if ((rc = h->alloc(&d.ctl, L))) return rc;
+    if ((rc = h->alloc(&d.inst_arc, L * 2 * cap, false))) return rc;
+    if ((rc = h->alloc(&d.tok, L * 2 * P * cap, false))) return rc;
+    if ((rc = h->alloc(&d.arc2slot, L * d.n_arcs))) return rc;
+    if ((rc = h->alloc(&d.entry_key, L * d.n_arcs))) return rc;
+    if ((rc = h->alloc(&d.state_key, L * d.n_states))) return rc;
+    if ((rc = h->alloc(&d.exit_arc, L * cap, false))) return rc;
+    if ((rc = h->alloc(&d.exit_tok, L * cap, false))) return rc;
+    if ((rc = h->alloc(&d.arr_tok, L * d.cap_arr, false))) return rc;
+    if ((rc = h->alloc(&d.arr_via, L * d.cap_arr, false))) return rc;
+    if ((rc = h->alloc(&d.front, L * 2 * d.cap_arr, false))) return rc;
+    if ((rc = h->alloc(&d.huge, L * 2 * d.cap_huge, false))) return rc;
+    if ((rc = h->alloc(&d.commit_arc, L * cap, false))) return rc;
+    if ((rc = h->alloc(&d.touched, L * d.cap_arr, false))) return rc;
+    if ((rc = h->alloc(&d.paths, L * d.cap_paths, false))) return rc;
+    if ((rc = h->alloc(&d.hist, L * d.hist_nbins))) return rc;
+    if ((rc = h->alloc(&d.fstat_cnt, d.frame_stats ? L * d.max_frames * 4 : 1))) return rc;
+    if ((rc = h->alloc(&d.fstat_best, d.frame_stats ? L * d.max_frames : 1))) return rc;
+    // schedule + score ring + streaming feature staging
+    if ((rc = h->alloc(&h->d_sched, (size_t)(h->sched_chunk + 1) * L, false))) return rc;
+    if ((rc = h->alloc(&h->d_rows, (size_t)h->sched_chunk * L, false))) return rc;
+    if ((rc = h->alloc(&h->d_scores, (size_t)h->FB * L * d.n_gmms, false))) return rc;
+    if ((rc = h->alloc(&h->d_stream_feats, L * h->stream_chunk * h->dim, false))) return rc;
+    if ((rc = h->alloc(&h->d_gmm_out, (size_t)h->gmm_chunk * d.n_gmms, false))) return rc;
+    d.scores = h->d_scores;
+    d.sched = h->d_sched;
+    // results: at least one slot per lane for the streaming interface
+    h->res_cap = std::max<size_t>(L, 64);
+    if ((rc = h->alloc(&d.res_hdr, h->res_cap))) return rc;
+    if ((rc = h->alloc(&d.res_words, h->res_cap * d.max_words))) return rc;
+    h->lanes.assign(L, LaneHost());
+    return JGPU_OK;
+}
+
+int ensure_results(jgpu_handle* h, size_t n)
+{
+    if (n <= h->res_cap) return JGPU_OK;
+    Dev& d = h->d;
+    CK(cudaStreamSynchronize(h->stream));
+    h->release(d.res_hdr);
+    h->release(d.res_words);
+    d.res_hdr = nullptr; d.res_words = nullptr;
+    h->res_cap = n;
+    int rc;
+    if ((rc = h->alloc(&d.res_hdr, n))) return rc;
+    if ((rc = h->alloc(&d.res_words, n * d.max_words))) return rc;
+    return JGPU_OK;
+}
+
+int launch_gmm(jgpu_handle* h, const float* d_x, const int* d_rows, int n_rows, float* d_out, long long out_base)
+{
+    if (n_rows <= 0) return JGPU_OK;
+    const GmmDev& G = h->g;
+    dim3 grid((G.n_gmms + G.gpb - 1) / G.gpb, (n_rows + JG_GMM_RT - 1) / JG_GMM_RT);
+    const int cstride = JG_GMM_RT * G.gpb + (G.gpb & 31);
+    const size_t smem = ((size_t)JG_GMM_RT * h->DP + (size_t)G.C * cstride) * sizeof(float);
+    switch (h->DP) {
+#define GMM_CASE(DPV)                                                                                          \
+    case DPV:                                                                                                  \
+        CK(cudaFuncSetAttribute(k_gmm_scores<DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        k_gmm_scores<DPV><<<grid, 256, smem, h->stream>>>(G, d_x, d_rows, n_rows, d_out, out_base);            \
+        break;
+        GMM_CASE(16) GMM_CASE(28) GMM_CASE(40) GMM_CASE(52) GMM_CASE(64)
+#undef GMM_CASE
+    default: return fail(JGPU_E_ARG, "unsupported padded dim %d", h->DP);
+    }
+    ++h->launches;
+    CK(cudaGetLastError());
+    return JGPU_OK;
+}
+
+int launch_step(jgpu_handle* h, int rel_step)
+{
+    const Dev& d = h->d;
+    const dim3 grid(h->bpl, d.n_lanes);
+    k_boundary<<<d.n_lanes, 32, 0, h->stream>>>(d, rel_step, 1);
+    if (h->S == 5) k_internal<5><<<grid, JG_THREADS, 0, h->stream>>>(d);
+    else k_internal<8><<<grid, JG_THREADS, 0, h->stream>>>(d);
+    k_seed<<<grid, JG_THREADS, 0, h->stream>>>(d);
+    for (int r = 0; r < d.n_rounds; ++r) {
+        k_expand<<<grid, JG_THREADS, 0, h->stream>>>(d, r);
+        if (h->has_huge) { k_expand_huge<<<grid, JG_THREADS, 0, h->stream>>>(d, r); ++h->launches; }
+    }
+    k_commit<<<grid, JG_THREADS, 0, h->stream>>>(d);
+    h->launches += 4 + d.n_rounds;
+    CK(cudaGetLastError());
+    return JGPU_OK;
+}
+
+// Runs `n_steps` schedule rows (plus the trailing close-only row n_steps).
+// sched: (n_steps + 1) * n_lanes entries {feature row, -, flags, utt}; d_x: feature base.
+int run_schedule(jgpu_handle* h, const std::vector<int4>& sched, int n_steps, const float* d_x)
+{
+    const Dev& d = h->d;
+    const int L = d.n_lanes, CH = h->sched_chunk, FB = h->FB;
+    std::vector<int4> chunk;
+    std::vector<int> rows;
+    for (int s0 = 0; s0 <= n_steps; s0 += CH) {
+        const int ns = std::min(CH, n_steps - s0);          // frame/seed steps in this chunk
+        const bool last = s0 + ns == n_steps;
+        const int n_entries = ns + (last ? 1 : 0);
+        if (n_entries == 0) break;
+        chunk.assign(sched.begin() + (size_t)s0 * L, sched.begin() + (size_t)(s0 + n_entries) * L);
+        rows.resize((size_t)std::max(ns, 1) * L);
+        for (int i = 0; i < ns; ++i)
+            for (int l = 0; l < L; ++l) {
+                int4& e = chunk[(size_t)i * L + l];
+                e.y = (i % FB) * L + l;                     // score-ring row of (step, lane)
+                rows[(size_t)i * L + l] = ((e.z & 3) == JG_MODE_FRAME) ? e.x : -1;
+            }
+        CK(cudaMemcpyAsync(h->d_sched, chunk.data(), chunk.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+        if (ns) CK(cudaMemcpyAsync(h->d_rows, rows.data(), (size_t)ns * L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        for (int b0 = 0; b0 < ns; b0 += FB) {
+            const int nb = std::min(FB, ns - b0);
+            int rc = launch_gmm(h, d_x, h->d_rows + (size_t)b0 * L, nb * L, h->d_scores, 0);
+            if (rc) return rc;
+            for (int i = b0; i < b0 + nb; ++i)
+                if ((rc = launch_step(h, i))) return rc;
+        }
+        if (last) {
+            k_boundary<<<L, 32, 0, h->stream>>>(d, ns, 1);   // close the last step, run pending finishes
+            ++h->launches;
+            CK(cudaGetLastError());
+            break;
+        }
+        // the host vectors are reused next iteration: pageable copies are staged before return
+    }
+    return JGPU_OK;
+}
+
+int fetch_result(jgpu_handle* h, int slot, JgpuResult* out)
+{
+    const Dev& d = h->d;
+    ResHdr hdr;
+    CK(cudaMemcpy(&hdr, d.res_hdr + slot, sizeof(hdr), cudaMemcpyDeviceToHost));
+    out->status = hdr.status; out->n_frames = hdr.n_frames;
+    out->score = hdr.score; out->ac = hdr.ac; out->lm = hdr.lm;
+    if (hdr.status > 0 && out->words && out->max_words > 0) {
+        const int n = std::min(std::min(hdr.status, out->max_words), d.max_words);
+        CK(cudaMemcpy(out->words, d.res_words + (size_t)slot * d.max_words, (size_t)n * sizeof(JgpuWord), cudaMemcpyDeviceToHost));
+    }
+    return JGPU_OK;
+}
+
+int decode_common(jgpu_handle* h, const float* d_feats, const int64_t* row_offset, const int32_t* n_frames,
+                  int32_t n_utts, JgpuResult* out)
+{
+    Dev& d = h->d;
+    const int L = d.n_lanes;
+    for (auto& l : h->lanes)
+        if (l.begun) return fail(JGPU_E_STATE, "streaming utterance in flight: finish it before a batch call");
+    int rc = ensure_results(h, (size_t)n_utts);
+    if (rc) return rc;
+    // LPT assignment of utterances to lanes (longest first, to the least loaded lane)
+    std::vector<int> order(n_utts);
+    for (int i = 0; i < n_utts; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n_frames[a] > n_frames[b]; });
+    typedef std::pair<long long, int> LoadLane;
+    std::priority_queue<LoadLane, std::vector<LoadLane>, std::greater<LoadLane>> pq;
+    for (int l = 0; l < L; ++l) pq.push(LoadLane(0, l));
+    std::vector<std::vector<int>> per_lane(L);
+    long long n_steps = 0;
+    for (int i : order) {
+        if (n_frames[i] < 0) return fail(JGPU_E_ARG, "utterance %d: negative frame count", i);
+        LoadLane t = pq.top();
+        pq.pop();
+        per_lane[t.second].push_back(i);
+        t.first += (long long)n_frames[i] + 1;             // +1: the seeding step
+        n_steps = std::max(n_steps, t.first);
+        pq.push(t);
+    }
+    if (n_steps > (1ll << 30)) return fail(JGPU_E_ARG, "schedule too long");
+    std::vector<int4> sched((size_t)(n_steps + 1) * L, make_int4(-1, 0, JG_MODE_IDLE, -1));
+    for (int l = 0; l < L; ++l) {
+        long long s = 0;
+        for (int u : per_lane[l]) {
+            int4& e = sched[(size_t)s * L + l];
+            e.z |= JG_MODE_SEED;                            // keeps a FINISH flag set by the previous utterance
+            e.w = u;
+            ++s;
+            for (int t = 0; t < n_frames[u]; ++t, ++s) {
+                int4& f = sched[(size_t)s * L + l];
+                f.x = (int)(row_offset[u] + t);
+                f.z = JG_MODE_FRAME;
+                f.w = u;
+            }
+            sched[(size_t)s * L + l].z |= JG_FLAG_FINISH;   // row after the last frame
+        }
+    }
+    k_reset_batch_stats<<<(L + 127) / 128, 128, 0, h->stream>>>(d);
+    ++h->launches;
+    rc = run_schedule(h, sched, (int)n_steps, d_feats);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    {
+        std::vector<LaneCtl> ctl(L);
+        CK(cudaMemcpy(ctl.data(), d.ctl, (size_t)L * sizeof(LaneCtl), cudaMemcpyDeviceToHost));
+        long long b[10] = {0};
+        for (int l = 0; l < L; ++l)
+            for (int i = 0; i < 10; ++i) b[i] += ctl[l].b_stats[i];
+        JgpuStats& st = h->batch_stats;
+        st.n_frames = b[0]; st.total_active_models = b[1]; st.total_active_emit_hyps = b[2];
+        st.total_active_end_hyps = b[3]; st.total_proc_emit_hyps = b[4]; st.total_proc_end_hyps = b[5];
+        st.total_gmm_evals = b[6]; st.total_arcs_expanded = b[7]; st.total_entry_writes = b[8]; st.total_paths = b[9];
+    }
+    // results
+    std::vector<ResHdr> hdr(n_utts);
+    if (n_utts) CK(cudaMemcpy(hdr.data(), d.res_hdr, (size_t)n_utts * sizeof(ResHdr), cudaMemcpyDeviceToHost));
+    std::vector<JgpuWord> words;
+    bool need_words = false;
+    for (int u = 0; u < n_utts; ++u) need_words |= (hdr[u].status > 0 && out[u].words && out[u].max_words > 0);
+    if (need_words) {
+        words.resize((size_t)n_utts * d.max_words);
+        CK(cudaMemcpy(words.data(), d.res_words, words.size() * sizeof(JgpuWord), cudaMemcpyDeviceToHost));
+    }
+    for (int u = 0; u < n_utts; ++u) {
+        out[u].status = hdr[u].status; out[u].n_frames = hdr[u].n_frames;
+        out[u].score = hdr[u].score; out[u].ac = hdr[u].ac; out[u].lm = hdr[u].lm;
+        if (hdr[u].status > 0 && out[u].words && out[u].max_words > 0) {
+            const int n = std::min(std::min(hdr[u].status, out[u].max_words), d.max_words);
+            memcpy(out[u].words, words.data() + (size_t)u * d.max_words, (size_t)n * sizeof(JgpuWord));
+        }
+    }
+    return JGPU_OK;
+}
+
+int lane_stats(jgpu_handle* h, int lane, JgpuStats* out)
+{
+    LaneCtl c;
+    CK(cudaMemcpy(&c, h->d.ctl + lane, sizeof(c), cudaMemcpyDeviceToHost));
+    out->n_frames += c.s_frames;
+    out->total_active_models += c.s_active_models;
+    out->total_active_emit_hyps += c.s_active_emit;
+    out->total_active_end_hyps += c.s_active_end;
+    out->total_proc_emit_hyps += c.s_proc_emit;
+    out->total_proc_end_hyps += c.s_proc_end;
+    out->total_gmm_evals += c.s_gmm;
+    out->total_arcs_expanded += c.s_arcs;
+    out->total_entry_writes += c.s_entry;
+    out->total_paths += c.s_paths;
+    return JGPU_OK;
+}
+
+} // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char* jgpu_last_error(void) { return jgpu_err_buf().c_str(); }
+const char* jgpu_version(void) { return "juicer_b200 0.1 (sm_100a)"; }
+
+int jgpu_create(const JgpuNet* net, const JgpuHmm* hmm, const JgpuGmm* gmm, const JgpuCfg* cfg, jgpu_handle** out)
+{
+    if (!out) return fail(JGPU_E_ARG, "null out");
+    *out = nullptr;
+    int rc = validate(net, hmm, gmm, cfg);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(JGPU_E_CUDA, "no CUDA device (%s): juicer_b200 has no CPU path", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(JGPU_E_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+    CK(cudaSetDevice(cfg->device));
+    jgpu_handle* h = new jgpu_handle;
+    h->cfg = *cfg;
+    h->device = cfg->device;
+    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return fail(JGPU_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    rc = build_tables(h, net, hmm, gmm);
+    if (!rc) rc = build_state(h);
+    if (!rc) {
+        e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(JGPU_E_CUDA, "create sync: %s", cudaGetErrorString(e));
+    }
+    if (rc) { jgpu_destroy(h); return rc; }
+    *out = h;
+    return JGPU_OK;
+}
+
+int jgpu_destroy(jgpu_handle* h)
+{
+    if (!h) return JGPU_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->d_feats) cudaFree(h->d_feats);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return JGPU_OK;
+}
+
+int jgpu_gmm_scores(jgpu_handle* h, const float* x, int32_t n_rows, float* out)
+{
+    if (!h || !x || !out || n_rows < 0) return fail(JGPU_E_ARG, "bad argument");
+    CK(cudaSetDevice(h->device));
+    const int CH = h->gmm_chunk, G = h->d.n_gmms, D = h->dim;
+    float* d_x = nullptr;
+    int* d_rows = nullptr;
+    CK(cudaMalloc(&d_x, (size_t)std::max(CH, 1) * D * sizeof(float)));
+    CK(cudaMalloc(&d_rows, (size_t)CH * sizeof(int)));
+    std::vector<int> rows(CH);
+    for (int i = 0; i < CH; ++i) rows[i] = i;
+    cudaMemcpyAsync(d_rows, rows.data(), CH * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    int rc = JGPU_OK;
+    for (int r0 = 0; r0 < n_rows && !rc; r0 += CH) {
+        const int n = std::min(CH, n_rows - r0);
+        cudaMemcpyAsync(d_x, x + (size_t)r0 * D, (size_t)n * D * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+        rc = launch_gmm(h, d_x, d_rows, n, h->d_gmm_out, 0);
+        if (rc) break;
+        cudaMemcpyAsync(out + (size_t)r0 * G, h->d_gmm_out, (size_t)n * G * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(JGPU_E_CUDA, "gmm_scores: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaFree(d_x);
+    cudaFree(d_rows);
+    return rc;
+}
+
+int jgpu_utt_begin(jgpu_handle* h, int32_t lane)
+{
+    if (!h || lane < 0 || lane >= h->d.n_lanes) return fail(JGPU_E_ARG, "bad lane");
+    h->lanes[lane] = LaneHost();
+    h->lanes[lane].begun = true;
+    return JGPU_OK;
+}
+
+int jgpu_push_frames(jgpu_handle* h, int32_t lane, const float* x, int32_t n_frames)
+{
+    if (!h || lane < 0 || lane >= h->d.n_lanes || n_frames < 0 || (n_frames > 0 && !x)) return fail(JGPU_E_ARG, "bad argument");
+    LaneHost& lh = h->lanes[lane];
+    if (!lh.begun) return fail(JGPU_E_STATE, "push_frames on lane %d without utt_begin", lane);
+    CK(cudaSetDevice(h->device));
+    const int L = h->d.n_lanes, D = h->dim;
+    int f0 = 0;
+    do {
+        // later copies into the staging buffer are stream-ordered behind the kernels reading it
+        const int n = std::min(h->stream_chunk, n_frames - f0);
+        const int seed = lh.seeded ? 0 : 1;
+        const int steps = seed + n;
+        if (n > 0)
+            CK(cudaMemcpyAsync(h->d_stream_feats + (size_t)lane * h->stream_chunk * D, x + (size_t)f0 * D,
+                               (size_t)n * D * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        if (steps > 0) {
+            std::vector<int4> sched((size_t)(steps + 1) * L, make_int4(-1, 0, JG_MODE_IDLE, -1));
+            if (seed) sched[lane] = make_int4(-1, 0, JG_MODE_SEED, lane);
+            for (int t = 0; t < n; ++t)
+                sched[(size_t)(seed + t) * L + lane] = make_int4(lane * h->stream_chunk + t, 0, JG_MODE_FRAME, lane);
+            int rc = run_schedule(h, sched, steps, h->d_stream_feats);
+            if (rc) return rc;
+        }
+        lh.seeded = true;
+        lh.frames += n;
+        f0 += n;
+    } while (f0 < n_frames);
+    return JGPU_OK;
+}
+
+int jgpu_utt_end(jgpu_handle* h, int32_t lane, JgpuResult* out)
+{
+    if (!h || lane < 0 || lane >= h->d.n_lanes || !out) return fail(JGPU_E_ARG, "bad argument");
+    LaneHost& lh = h->lanes[lane];
+    if (!lh.begun) return fail(JGPU_E_STATE, "utt_end on lane %d without utt_begin", lane);
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if (!lh.seeded && (rc = jgpu_push_frames(h, lane, nullptr, 0))) return rc;
+    const int L = h->d.n_lanes;
+    std::vector<int4> sched((size_t)L, make_int4(-1, 0, JG_MODE_IDLE, -1));
+    sched[lane].z |= JG_FLAG_FINISH;
+    if ((rc = run_schedule(h, sched, 0, h->d_stream_feats))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    lh.begun = false;
+    return fetch_result(h, lane, out);
+}
+
+int jgpu_decode_batch_device(jgpu_handle* h, const float* d_feats, const int64_t* row_offset, const int32_t* n_frames,
+                             int32_t n_utts, JgpuResult* out)
+{
+    if (!h || n_utts < 0 || (n_utts > 0 && (!d_feats || !row_offset || !n_frames || !out))) return fail(JGPU_E_ARG, "bad argument");
+    CK(cudaSetDevice(h->device));
+    return decode_common(h, d_feats, row_offset, n_frames, n_utts, out);
+}
+
+int jgpu_decode_batch(jgpu_handle* h, const float* const* feats, const int32_t* n_frames, int32_t n_utts, JgpuResult* out)
+{
+    if (!h || n_utts < 0 || (n_utts > 0 && (!feats || !n_frames || !out))) return fail(JGPU_E_ARG, "bad argument");
+    CK(cudaSetDevice(h->device));
+    std::vector<int64_t> off(n_utts + 1, 0);
+    for (int u = 0; u < n_utts; ++u) {
+        if (n_frames[u] < 0) return fail(JGPU_E_ARG, "utterance %d: negative frame count", u);
+        off[u + 1] = off[u] + n_frames[u];
+    }
+    const size_t rows = (size_t)off[n_utts];
+    if (rows > h->feats_cap) {
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->d_feats) cudaFree(h->d_feats);
+        h->d_feats = nullptr;
+        h->feats_cap = 0;
+        CK(cudaMalloc(&h->d_feats, std::max<size_t>(rows, 1) * h->dim * sizeof(float)));
+        h->feats_cap = rows;
+    }
+    for (int u = 0; u < n_utts; ++u)
+        if (n_frames[u] > 0)
+            CK(cudaMemcpyAsync(h->d_feats + (size_t)off[u] * h->dim, feats[u], (size_t)n_frames[u] * h->dim * sizeof(float),
+                               cudaMemcpyHostToDevice, h->stream));
+    return decode_common(h, h->d_feats, off.data(), n_frames, n_utts, out);
+}
+
+int jgpu_stats(jgpu_handle* h, int32_t lane, JgpuStats* out)
+{
+    if (!h || !out || lane < -1 || lane >= h->d.n_lanes) return fail(JGPU_E_ARG, "bad argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    memset(out, 0, sizeof(*out));
+    if (lane >= 0) return lane_stats(h, lane, out);
+    *out = h->batch_stats;
+    return JGPU_OK;
+}
+
+int jgpu_frame_stats(jgpu_handle* h, int32_t lane, int32_t* cnt, float* best, int32_t max_frames)
+{
+    if (!h || lane < 0 || lane >= h->d.n_lanes) return fail(JGPU_E_ARG, "bad argument");
+    if (!h->d.frame_stats) return fail(JGPU_E_STATE, "handle created without cfg.frame_stats");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    LaneCtl c;
+    CK(cudaMemcpy(&c, h->d.ctl + lane, sizeof(c), cudaMemcpyDeviceToHost));
+    const int n = std::min(std::min(c.frame, h->d.max_frames), max_frames);
+    if (n > 0 && cnt) CK(cudaMemcpy(cnt, h->d.fstat_cnt + (size_t)lane * h->d.max_frames * 4, (size_t)n * 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    if (n > 0 && best) CK(cudaMemcpy(best, h->d.fstat_best + (size_t)lane * h->d.max_frames, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    return n;
+}
+
+int64_t jgpu_launch_count(jgpu_handle* h) { return h ? h->launches : 0; }
+
+} // extern "C"

@@ -1,0 +1,131 @@
+// jgpu_gmm.cuh — diagonal-GMM log-likelihood, bit-exact to HTKFlatModels::calcGMMOutput
+// (src/HTKFlatModels.cpp:226-262) and its private logAdd (:266-293).
+//
+//   out[row][g] = logAdd_{c < nComp(g)} ( -0.5 * sum_{d<D} ((x_d - mu_gcd)^2 * ivar_gcd) + det_gc )
+//
+// Exactness rules:
+//   * the d-sum is a sequential fp32 accumulation with separate sub, mul, mul, add — written
+//     with __fsub_rn/__fmul_rn/__fadd_rn so ptxas can never contract it into an FMA;
+//   * "-0.5*sumxmu + det" is evaluated in double and narrowed once (:254);
+//   * components are folded in order 0..n-1 by logAdd: float diff, double threshold -18.42,
+//     double log(1.0 + exp(diff)), narrowed once (:289).  No tree reduction anywhere.
+// Parallelism comes from (Gaussians) x (feature rows), never from inside one Gaussian.
+//
+// Mapping: CTA = 256 threads; thread <-> one Gaussian slot (c, g_local) holding its mu/ivar
+// row in registers for a tile of RT feature rows staged in shared memory (broadcast float4
+// reads).  Per-component values go through shared memory to phase 2, where thread <->
+// (row, gmm) runs the serial logAdd chain with all lanes busy.  Parameters are stored
+// transposed [d][c][g] so that both phases read and write coalesced.
+#pragma once
+
+#include "jgpu_device.cuh"
+
+#define JG_GMM_RT 32          // feature rows per CTA tile
+#define JG_GMM_DMAX 64        // max feature dimension held in registers
+
+struct GmmDev {
+    const float* mu;          // [DP][C][Gpad], zero padded
+    const float* iv;          // [DP][C][Gpad], zero padded
+    const float* det;         // [C][Gpad]
+    const int*   ncomp;       // [Gpad]
+    int n_gmms, g_pad, C, D, gpb;   // gpb = GMMs per CTA = 256 / C
+};
+
+__device__ __forceinline__ float jg_log_add(float x, float y)
+{
+    if (x < y) { const float t = x; x = y; y = t; }
+    const float diff = __fsub_rn(y, x);
+    if ((double)diff < -18.42) return x;
+    return (float)((double)x + log(1.0 + exp((double)diff)));
+}
+
+// rows: list of feature-row indices into x (row-major [*, D]); -1 = skip.  Output row i of
+// the list goes to out[(out_base + i) * n_gmms + g].
+// DP = feature dimension padded to a multiple of 4 with mu = ivar = x = 0: the padded terms
+// add (0-0)^2*0 = +0.0f to a non-negative sum, which is exact.
+template <int DP>
+__global__ void __launch_bounds__(256, 2)
+k_gmm_scores(GmmDev g, const float* __restrict__ x, const int* __restrict__ rows, int n_rows,
+             float* __restrict__ out, long long out_base)
+{
+    constexpr int RT = JG_GMM_RT;
+    constexpr int D = DP;
+    extern __shared__ float smem[];
+    float* xs = smem;                          // [RT][DP]
+    float* vals = smem + RT * DP;              // [C][RT*gpb + pad]
+    __shared__ int row_id[RT];
+
+    const int gpb = g.gpb, C = g.C;
+    const int cstride = RT * gpb + (gpb & 31);   // consecutive components land on different banks
+    const int tid = threadIdx.x;
+    const int g0 = blockIdx.x * gpb;
+    const int r0 = blockIdx.y * RT;
+
+    // stage the feature tile
+    if (tid < RT) {
+        const int i = r0 + tid;
+        int rid = -1;
+        if (i < n_rows) rid = rows[i];
+        row_id[tid] = rid;
+    }
+    __syncthreads();
+    bool any = false;
+    for (int i = 0; i < RT; ++i) any |= row_id[i] >= 0;
+    if (!any) return;
+    for (int i = tid; i < RT * DP; i += 256) {
+        const int r = i / DP, dd = i - r * DP;
+        const int rid = row_id[r];
+        xs[i] = (rid >= 0 && dd < g.D) ? x[(size_t)rid * g.D + dd] : 0.0f;
+    }
+
+    // phase 1: thread <-> Gaussian slot
+    const int c = tid / gpb, gl = tid - c * gpb;
+    const int gi = g0 + gl;
+    const bool active = c < C && gi < g.n_gmms;
+    float mu[D], iv[D];
+    float det = 0.0f;
+    if (active) {
+        const size_t plane = (size_t)C * g.g_pad, off = (size_t)c * g.g_pad + gi;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            mu[d] = __ldg(g.mu + d * plane + off);
+            iv[d] = __ldg(g.iv + d * plane + off);
+        }
+        det = __ldg(g.det + off);
+    }
+    __syncthreads();
+    if (active) {
+        const double ddet = (double)det;
+#pragma unroll 2
+        for (int r = 0; r < RT; ++r) {
+            const float4* xr = reinterpret_cast<const float4*>(xs + r * DP);
+            float s = 0.0f;
+#pragma unroll
+            for (int q = 0; q < DP / 4; ++q) {
+                const float4 xv = xr[q];
+                const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int d = q * 4 + e;
+                    const float xmu = __fsub_rn(xa[e], mu[d]);
+                    s = __fadd_rn(s, __fmul_rn(__fmul_rn(xmu, xmu), iv[d]));
+                }
+            }
+            vals[c * cstride + r * gpb + gl] = (float)(-0.5 * (double)s + ddet);
+        }
+    }
+    __syncthreads();
+
+    // phase 2: thread <-> (row, gmm); serial logAdd chain in component order
+    for (int p = tid; p < RT * gpb; p += 256) {
+        const int r = p / gpb, l = p - r * gpb;
+        const int gg = g0 + l;
+        const int rid = row_id[r];
+        if (gg < g.n_gmms && rid >= 0) {
+            const int nc = __ldg(g.ncomp + gg);
+            float lp = JG_LZ;
+            for (int cc = 0; cc < nc; ++cc) lp = jg_log_add(lp, vals[cc * cstride + p]);
+            out[(size_t)(out_base + r0 + r) * g.n_gmms + gg] = lp;
+        }
+    }
+}
