@@ -194,6 +194,19 @@ int jgpu_frame_stats(jgpu_handle* h, int32_t lane, int32_t* cnt, float* best, in
 /* Number of kernel launches issued by this handle since creation (bench bookkeeping). */
 int64_t jgpu_launch_count(jgpu_handle* h);
 
+/* Enqueue all work of this handle on a caller-owned CUDA stream (a cudaStream_t passed as
+ * void*), e.g. so that the caller's CUDA events bracket the decoder's kernels. */
+int jgpu_set_stream(jgpu_handle* h, void* cuda_stream);
+
+/* Per-kernel device timing: while enabled, every launch is bracketed by CUDA events on the
+ * launching stream.  jgpu_profile_read fills ms[k] / count[k] for k < JGPU_N_KERNELS (summed
+ * since the last enable) and returns JGPU_N_KERNELS. */
+enum { JGPU_K_GMM = 0, JGPU_K_BOUNDARY, JGPU_K_INTERNAL, JGPU_K_SEED, JGPU_K_EXPAND, JGPU_K_EXPAND_HUGE,
+       JGPU_K_COMMIT, JGPU_N_KERNELS };
+int jgpu_profile(jgpu_handle* h, int32_t enable);
+int jgpu_profile_read(jgpu_handle* h, double* ms, int64_t* count);
+const char* jgpu_kernel_name(int32_t kind);
+
 /* ---- host-side loaders (C++ mirrors of the reference's file readers) ------------------
  * jgpu_load_fsm   : AT&T text network + symbol tables, same semantics as
  *                   WFSTNetwork(fsm, insyms, outsyms, lmScale, insPenalty, REMOVEBOTH)

@@ -54,6 +54,11 @@ def load_library() -> C.CDLL:
     lib.jgpu_frame_stats.argtypes = [vp, i32, vp, vp, i32]
     lib.jgpu_launch_count.argtypes = [vp]
     lib.jgpu_launch_count.restype = i64
+    lib.jgpu_set_stream.argtypes = [vp, vp]
+    lib.jgpu_profile.argtypes = [vp, i32]
+    lib.jgpu_profile_read.argtypes = [vp, vp, vp]
+    lib.jgpu_kernel_name.argtypes = [i32]
+    lib.jgpu_kernel_name.restype = C.c_char_p
     lib.jgpu_load_fsm.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_float, C.c_float, vp]
     lib.jgpu_free_net.argtypes = [vp]
     lib.jgpu_load_jmbi.argtypes = [C.c_char_p, vp, vp]
@@ -269,6 +274,19 @@ class WFSTDecoderLite:
         n = self.lib.jgpu_frame_stats(self.h, lane, cnt.ctypes.data, best.ctypes.data, max_frames)
         _check(n, "jgpu_frame_stats")
         return cnt[:n], best[:n]
+
+    def set_stream(self, cuda_stream: int) -> None:
+        _check(self.lib.jgpu_set_stream(self.h, C.c_void_p(cuda_stream)), "jgpu_set_stream")
+
+    def profile(self, enable: bool) -> None:
+        _check(self.lib.jgpu_profile(self.h, int(enable)), "jgpu_profile")
+
+    def profile_read(self) -> Dict[str, Dict[str, float]]:
+        ms = (C.c_double * 16)()
+        cnt = (C.c_int64 * 16)()
+        n = self.lib.jgpu_profile_read(self.h, ms, cnt)
+        _check(n, "jgpu_profile_read")
+        return {self.lib.jgpu_kernel_name(k).decode(): dict(ms=float(ms[k]), launches=int(cnt[k])) for k in range(n)}
 
     @property
     def launch_count(self) -> int:

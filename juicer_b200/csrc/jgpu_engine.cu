@@ -79,6 +79,48 @@ struct jgpu_handle {
     std::vector<LaneHost> lanes;
     int64_t launches = 0;
     JgpuStats batch_stats{};
+    bool own_stream = true;
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_kind;
+    size_t prof_used = 0;
+    double prof_ms[JGPU_N_KERNELS] = {0};
+    int64_t prof_cnt[JGPU_N_KERNELS] = {0};
+
+    void prof_begin(int kind)
+    {
+        if (!prof_on) return;
+        if (prof_used + 2 > prof_ev.size()) {
+            const size_t n = prof_ev.size() + 4096;
+            while (prof_ev.size() < n) {
+                cudaEvent_t e;
+                cudaEventCreate(&e);
+                prof_ev.push_back(e);
+            }
+        }
+        prof_kind.push_back(kind);
+        cudaEventRecord(prof_ev[prof_used++], stream);
+    }
+    void prof_end()
+    {
+        if (!prof_on) return;
+        cudaEventRecord(prof_ev[prof_used++], stream);
+    }
+    void prof_collect()
+    {
+        if (prof_used == 0) return;
+        cudaStreamSynchronize(stream);
+        for (size_t i = 0; i + 1 < prof_used; i += 2) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, prof_ev[i], prof_ev[i + 1]);
+            const int k = prof_kind[i / 2];
+            prof_ms[k] += ms;
+            prof_cnt[k] += 1;
+        }
+        prof_used = 0;
+        prof_kind.clear();
+    }
 
     template <typename T>
     int alloc(T** p, size_t n, bool zero = true)
@@ -386,6 +428,7 @@ int launch_gmm(jgpu_handle* h, const float* d_x, const int* d_rows, int n_rows, 
     dim3 grid((G.n_gmms + G.gpb - 1) / G.gpb, (n_rows + JG_GMM_RT - 1) / JG_GMM_RT);
     const int cstride = JG_GMM_RT * G.gpb + (G.gpb & 31);
     const size_t smem = ((size_t)JG_GMM_RT * h->DP + (size_t)G.C * cstride) * sizeof(float);
+    h->prof_begin(JGPU_K_GMM);
     switch (h->DP) {
 #define GMM_CASE(DPV)                                                                                          \
     case DPV:                                                                                                  \
@@ -396,6 +439,7 @@ int launch_gmm(jgpu_handle* h, const float* d_x, const int* d_rows, int n_rows, 
 #undef GMM_CASE
     default: return fail(JGPU_E_ARG, "unsupported padded dim %d", h->DP);
     }
+    h->prof_end();
     ++h->launches;
     CK(cudaGetLastError());
     return JGPU_OK;
@@ -405,15 +449,30 @@ int launch_step(jgpu_handle* h, int rel_step)
 {
     const Dev& d = h->d;
     const dim3 grid(h->bpl, d.n_lanes);
+    h->prof_begin(JGPU_K_BOUNDARY);
     k_boundary<<<d.n_lanes, 32, 0, h->stream>>>(d, rel_step, 1);
+    h->prof_end();
+    h->prof_begin(JGPU_K_INTERNAL);
     if (h->S == 5) k_internal<5><<<grid, JG_THREADS, 0, h->stream>>>(d);
     else k_internal<8><<<grid, JG_THREADS, 0, h->stream>>>(d);
+    h->prof_end();
+    h->prof_begin(JGPU_K_SEED);
     k_seed<<<grid, JG_THREADS, 0, h->stream>>>(d);
+    h->prof_end();
     for (int r = 0; r < d.n_rounds; ++r) {
+        h->prof_begin(JGPU_K_EXPAND);
         k_expand<<<grid, JG_THREADS, 0, h->stream>>>(d, r);
-        if (h->has_huge) { k_expand_huge<<<grid, JG_THREADS, 0, h->stream>>>(d, r); ++h->launches; }
+        h->prof_end();
+        if (h->has_huge) {
+            h->prof_begin(JGPU_K_EXPAND_HUGE);
+            k_expand_huge<<<grid, JG_THREADS, 0, h->stream>>>(d, r);
+            h->prof_end();
+            ++h->launches;
+        }
     }
+    h->prof_begin(JGPU_K_COMMIT);
     k_commit<<<grid, JG_THREADS, 0, h->stream>>>(d);
+    h->prof_end();
     h->launches += 4 + d.n_rounds;
     CK(cudaGetLastError());
     return JGPU_OK;
@@ -450,7 +509,9 @@ int run_schedule(jgpu_handle* h, const std::vector<int4>& sched, int n_steps, co
                 if ((rc = launch_step(h, i))) return rc;
         }
         if (last) {
+            h->prof_begin(JGPU_K_BOUNDARY);
             k_boundary<<<L, 32, 0, h->stream>>>(d, ns, 1);   // close the last step, run pending finishes
+            h->prof_end();
             ++h->launches;
             CK(cudaGetLastError());
             break;
@@ -618,7 +679,8 @@ int jgpu_destroy(jgpu_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : h->allocs) cudaFree(p);
     if (h->d_feats) cudaFree(h->d_feats);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return JGPU_OK;
 }
@@ -764,5 +826,44 @@ int jgpu_frame_stats(jgpu_handle* h, int32_t lane, int32_t* cnt, float* best, in
 }
 
 int64_t jgpu_launch_count(jgpu_handle* h) { return h ? h->launches : 0; }
+
+int jgpu_set_stream(jgpu_handle* h, void* cuda_stream)
+{
+    if (!h) return fail(JGPU_E_ARG, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)cuda_stream;
+    h->own_stream = false;
+    return JGPU_OK;
+}
+
+int jgpu_profile(jgpu_handle* h, int32_t enable)
+{
+    if (!h) return fail(JGPU_E_ARG, "null handle");
+    CK(cudaSetDevice(h->device));
+    h->prof_collect();
+    h->prof_on = enable != 0;
+    if (enable) {
+        for (int k = 0; k < JGPU_N_KERNELS; ++k) { h->prof_ms[k] = 0; h->prof_cnt[k] = 0; }
+    }
+    return JGPU_OK;
+}
+
+int jgpu_profile_read(jgpu_handle* h, double* ms, int64_t* count)
+{
+    if (!h || !ms || !count) return fail(JGPU_E_ARG, "bad argument");
+    CK(cudaSetDevice(h->device));
+    h->prof_collect();
+    for (int k = 0; k < JGPU_N_KERNELS; ++k) { ms[k] = h->prof_ms[k]; count[k] = h->prof_cnt[k]; }
+    return JGPU_N_KERNELS;
+}
+
+const char* jgpu_kernel_name(int32_t kind)
+{
+    static const char* names[JGPU_N_KERNELS] = {"k_gmm_scores", "k_boundary", "k_internal", "k_seed", "k_expand",
+                                                "k_expand_huge", "k_commit"};
+    return (kind >= 0 && kind < JGPU_N_KERNELS) ? names[kind] : "";
+}
 
 } // extern "C"

@@ -471,3 +471,49 @@ def make_fixture(name: str, outdir: str, models: Models, net: Net) -> Dict[str, 
     write_jmbi(models, jm)
     fsm, ins, outs = write_fsm(net, os.path.join(outdir, name))
     return {"jmbi": jm, "fsm": fsm, "insyms": ins, "outsyms": outs}
+
+
+# --------------------------------------------------------------------------------------
+# named configurations (BASELINE.json configs + parity fixtures)
+# --------------------------------------------------------------------------------------
+def named_config(name: str):
+    """Returns (models, net, tee_hmms, decoder_kwargs) for a named, seeded configuration.
+
+    c1      BASELINE configs[0]: 10-word digit loop, 3-state monophones, 1-mix
+    tee     tee model + eps arcs with word labels + final weight
+    mixed   4/5/6-state HMMs with skips, ragged mixtures, optional-silence tee, all four beams + histogram
+    c2mini  small bigram network with tied states
+    c2      BASELINE configs[1]: 1k-vocab bigram, 2000 triphone HMMs x 16-mix, ~42k states
+    c3      BASELINE configs[2]: 20k-vocab trigram-shaped network, ~440k states / ~1.8M arcs, beam 250
+    c3s     c3 topology at 1/8 scale (parity at sizes the CPU oracle finishes in seconds)
+    """
+    if name == "c1":
+        return make_models(10, 1, sigma_mu=2.0, seed=1), digit_loop_net(10), (), dict(main_beam=200.0)
+    if name == "c1h":
+        return make_models(10, 1, sigma_mu=2.0, seed=1), digit_loop_net(10), (), dict(main_beam=200.0, max_hyps=12)
+    if name == "nolabel":                       # final tokens without any word label -> inactive DecHyp
+        net = digit_loop_net(4)
+        net.olab[:] = 0
+        return make_models(4, 1, sigma_mu=2.0, seed=5), net, (), dict(main_beam=200.0)
+    if name == "tee":
+        return (make_models(4, 2, sigma_mu=2.0, seed=2, with_tee=True), tee_eps_net(4, sp_label=5), (4,),
+                dict(main_beam=200.0))
+    if name == "mixed":
+        return (make_models(40, 3, sigma_mu=1.0, seed=7, with_tee=True, mixed_topology=True, ragged_mix=True),
+                bigram_net(30, 40, k_bigram=4, seed=8, sp_label=41), (40,),
+                dict(main_beam=150.0, end_beam=100.0, word_beam=80.0, start_beam=120.0, max_hyps=300))
+    if name == "c2mini":
+        return (make_models(120, 4, sigma_mu=0.9, seed=11, n_gmm_pool=150), bigram_net(100, 120, k_bigram=5, seed=12),
+                (), dict(main_beam=180.0, end_beam=140.0))
+    if name == "c2":
+        return (make_models(2000, 16, sigma_mu=0.8, seed=3), bigram_net(1000, 2000, k_bigram=8, seed=4), (),
+                dict(main_beam=200.0))
+    if name == "c3":
+        return (make_models(4000, 16, sigma_mu=1.3, seed=21, n_gmm_pool=6000),
+                trigram_net(20000, 4000, k_bigram=40, n_trigram=60000, k_trigram=8, seed=22), (),
+                dict(main_beam=250.0))
+    if name == "c3s":
+        return (make_models(600, 8, sigma_mu=1.0, seed=23, n_gmm_pool=900),
+                trigram_net(2500, 600, k_bigram=20, n_trigram=6000, k_trigram=6, seed=24), (),
+                dict(main_beam=220.0))
+    raise KeyError(name)

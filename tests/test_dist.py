@@ -1,0 +1,70 @@
+"""CPU suite: the N>1 path (utterance sharding + result gather + timing reduction) with
+world_size 2 over gloo.  The per-rank decoder here is the oracle port — the sharding logic is
+what is under test; the CUDA decoder takes its place on the GPU box."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from helpers import Golden, flat_tables_from_files
+
+from juicer_b200 import _abi, dist as jdist
+
+
+def test_shard_balance_and_coverage():
+    rng = np.random.default_rng(0)
+    n = rng.integers(1, 1000, size=257)
+    for world in (1, 2, 3, 8):
+        sh = jdist.shard_utterances(n, world)
+        flat = sorted(i for s in sh for i in s)
+        assert flat == list(range(len(n)))
+        loads = [sum(int(n[i]) + 1 for i in s) for s in sh]
+        assert max(loads) - min(loads) <= int(n.max()) + 1
+    assert jdist.shard_utterances([], 4) == [[], [], [], []]
+    assert jdist.shard_utterances([5], 2) == [[0], []]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from oracle.binding import OraclePort
+    d = jdist.init_process_group("gloo")
+    g = Golden("mixed")
+    tabs, _n, _m = flat_tables_from_files(g.files)
+    p = OraclePort(tabs, _abi.make_cfg(**g.kw))
+    feats = [g.feats(u) for u in range(g.n_utts)] + [g.feats(0)[:37]]
+    shards = jdist.shard_utterances([f.shape[0] for f in feats], world)
+    local = {}
+    for u in shards[rank]:
+        r = p.decode(feats[u])
+        local[u] = dict(status=r.status, labels=r.labels, times=r.times, totals=r.totals.view(np.uint32).tolist())
+    allr = jdist.gather_results(local, len(feats))
+    ms, frames = jdist.reduce_time_and_frames(10.0 * (rank + 1), sum(feats[u].shape[0] for u in shards[rank]))
+    if rank == 0:
+        q.put((allr, ms, frames))
+    d.barrier()
+    d.destroy_process_group()
+
+
+def test_two_rank_gloo_matches_single_process(oracle_port_lib, product_lib):
+    from oracle.binding import OraclePort
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    allr, ms, frames = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = Golden("mixed")
+    tabs, _n, _m = flat_tables_from_files(g.files)
+    single = OraclePort(tabs, _abi.make_cfg(**g.kw))
+    feats = [g.feats(u) for u in range(g.n_utts)] + [g.feats(0)[:37]]
+    assert frames == sum(f.shape[0] for f in feats) and ms == 20.0
+    for u, f in enumerate(feats):
+        r = single.decode(f)
+        assert allr[u]["status"] == r.status and allr[u]["labels"] == r.labels and allr[u]["times"] == r.times
+        assert allr[u]["totals"] == r.totals.view(np.uint32).tolist()
