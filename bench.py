@@ -109,23 +109,28 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------
 # reference arm: the reference CPU decoder on the host cores
 # ---------------------------------------------------------------------------------------
-def _ref_worker(args):
-    files, kw, feats, use_ref = args
+_REF_DEC = None
+
+
+def _ref_init(files, kw, use_ref):
+    """Pool initializer: every worker process loads the network and models once."""
+    global _REF_DEC
     sys.path.insert(0, ROOT)
     from oracle.binding import OraclePort, OracleRef
     if use_ref:
-        dec = OracleRef(files, **kw)
+        _REF_DEC = OracleRef(files, **kw)
     else:
         from juicer_b200 import _abi, api
         net = api.WFSTNetwork(files["fsm"], files["insyms"], files["outsyms"])
         models = api.HTKFlatModels(files["jmbi"])
-        dec = OraclePort(_abi.FlatTables(net.arrays(), net.init_state, models.arrays()), _abi.make_cfg(**kw))
+        _REF_DEC = OraclePort(_abi.FlatTables(net.arrays(), net.init_state, models.arrays()), _abi.make_cfg(**kw))
+        _REF_DEC._keep = (net, models)
+
+
+def _ref_worker(x):
     t0 = time.perf_counter()
-    n = 0
-    for x in feats:
-        dec.decode(x)
-        n += x.shape[0]
-    return n, time.perf_counter() - t0
+    _REF_DEC.decode(x)
+    return x.shape[0], time.perf_counter() - t0
 
 
 def run_reference(args) -> None:
@@ -147,15 +152,14 @@ def run_reference(args) -> None:
     feats = sample_utterances(net, m, tee, cores, lo, hi, seed=12345)
     ctx = mp.get_context("spawn")
     times = []
-    with ctx.Pool(cores) as pool:
+    with ctx.Pool(cores, initializer=_ref_init, initargs=(files, kw, use_ref)) as pool:
+        pool.map(_ref_worker, [f[:2] for f in feats], chunksize=1)        # force every worker to finish loading
         for step in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            res = pool.map(_ref_worker, [(files, kw, [feats[c]], use_ref) for c in range(cores)])
-            dt = time.perf_counter() - t0
-            # loading the network/models is excluded: use the slowest worker's decode time
-            dt_dec = max(r[1] for r in res)
+            res = pool.map(_ref_worker, feats, chunksize=1)
+            dt = time.perf_counter() - t0                                  # wall time of the step (all cores busy)
             if step >= args.warmup:
-                times.append((sum(r[0] for r in res), dt_dec, dt))
+                times.append((sum(r[0] for r in res), dt, max(r[1] for r in res)))
     frames = sum(t[0] for t in times)
     sec = sum(t[1] for t in times)
     value = frames / sec

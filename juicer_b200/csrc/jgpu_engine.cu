@@ -353,7 +353,7 @@ int build_state(jgpu_handle* h)
     d.cap = c.max_active > 0 ? c.max_active : std::min(d.n_arcs + 1, 1 << 18);
     d.cap = std::max(d.cap, 64);
     d.cap_arr = 2 * d.cap + 1024;
-    d.cap_paths = c.max_paths > 0 ? c.max_paths : (1 << 21);
+    d.cap_paths = c.max_paths > 0 ? c.max_paths : (1 << 21);   // re-sized from free memory below when 0
     d.cap_huge = 1024;
     d.max_frames = c.max_frames > 0 ? c.max_frames : 4096;
     d.frame_stats = c.frame_stats;
@@ -368,6 +368,16 @@ int build_state(jgpu_handle* h)
                        (size_t)d.cap_arr * 36 + (size_t)d.cap_paths * 32);
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
+    if (c.max_paths <= 0) {
+        // word-boundary arena: no garbage collection yet, so give it a quarter of the free memory
+        // (1M .. 32M records of 32 B per lane); an utterance that still overflows fails alone
+        const size_t fixed = need - L * (size_t)d.cap_paths * 32;
+        const size_t budget = free_b > fixed + (2ull << 30) ? (free_b - fixed - (2ull << 30)) / 4 : 0;
+        size_t per_lane = budget / (L * 32);
+        per_lane = std::min<size_t>(std::max<size_t>(per_lane, 1u << 20), 1u << 25);
+        d.cap_paths = (int)per_lane;
+        need = fixed + L * (size_t)d.cap_paths * 32;
+    }
     if (need + (1ull << 30) > free_b)
         return fail(JGPU_E_CAPACITY, "decoder state needs %.1f GB for %d lanes but only %.1f GB of device memory is free",
                     need / 1e9, c.n_lanes, free_b / 1e9);
