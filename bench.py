@@ -51,8 +51,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--utts", type=int, default=128, help="utterances per step per GPU")
-    ap.add_argument("--lanes", type=int, default=64, help="utterances decoded in lock-step")
+    ap.add_argument("--utts", type=int, default=256, help="utterances per step per GPU")
+    ap.add_argument("--lanes", type=int, default=128, help="utterances decoded in lock-step")
     ap.add_argument("--min-frames", type=int, default=300)
     ap.add_argument("--max-frames", type=int, default=1000)
     ap.add_argument("--cpu-sample-utts", type=int, default=2)
@@ -182,22 +182,32 @@ def run_reference(args) -> None:
 # roofline bookkeeping
 # ---------------------------------------------------------------------------------------
 def algorithmic_bytes(stats: Dict[str, int], dims: Dict[str, int], n_rows: int) -> Dict[str, float]:
-    """Algorithmic bytes moved by each kernel over one whole step (DESIGN.md
-    'Kernels'): device token 16 B, arc record 16 B, state row 8 B, path record 24 B, S=5 states."""
+    """Algorithmic bytes moved by each kernel over one whole step, from the decoder's own work
+    counters and the device record sizes of DESIGN.md ("Kernels"): instance meta 8 B, token 16 B,
+    exit record 20 B, arrival record 32 B, state key 8 B, arc row entry 16 B, per-arc dynamic
+    record 16 B, word-boundary record 32 B.  Minimal traffic: every record counted once."""
     A = stats["total_active_models"]          # instances walked by the internal phase (sum over frames)
-    E = stats["total_proc_end_hyps"]          # exit tokens passing the end/word beam
-    X = stats["total_arcs_expanded"]          # out-arcs of distinct states reached
-    W = stats["total_entry_writes"]           # distinct destination arcs written
+    H = stats["total_active_emit_hyps"]       # live emitting tokens after the internal phase
+    Ea = stats["total_active_end_hyps"]       # live exit tokens
+    E = stats["total_proc_end_hyps"]          # exit tokens passing the end/word beam = first-round arrivals
+    X = stats["total_arcs_expanded"]          # out-arcs of the distinct states expanded
+    W = stats["total_entry_writes"]           # distinct destination arcs whose entry token was written
     P = stats["total_paths"]                  # word-boundary records appended
-    S, D, G, M = dims["S"], dims["D"], dims["n_gmm"], dims["C"]
+    D, G, M = dims["D"], dims["n_gmm"], dims["C"]
     return {
-        "k_internal": A * (2 * S * 16 + 16),
-        "k_seed": E * (16 + 8),
-        "k_expand": X * 16 + X * 8 + P * 24,
-        "k_expand_huge": 0.0,
-        "k_commit": W * 16,
+        # read meta + entry token per instance, emitting tokens read + written, GMM score per live token,
+        # exit records written
+        "k_internal": A * (8 + 16) + H * (16 + 16 + 4) + Ea * 20,
+        # exit records read, arc record, arrival record + state key written
+        "k_seed": Ea * 20 + E * (16 + 32 + 8),
+        # arrival record + state key read per expanded record, arc rows, candidate keys, path records
+        "k_expand": E * (32 + 8) + X * 16 + X * 8 + P * 32,
+        "k_expand_huge": 0.0,                 # its arc rows are counted in k_expand's X
+        # second walk: arrival record + state key, arc rows, per-arc dynamic record; winners write
+        # the dynamic record, the entry token and the instance meta
+        "k_commit": E * (32 + 8) + X * 16 + X * 16 + W * (16 + 16 + 8),
         "k_boundary": 0.0,
-        # one parameter pass per launch (16 frames x lanes rows share it) + features in, scores out
+        # one parameter pass per launch (frames x lanes rows share it) + features in, scores out
         "k_gmm_scores": dims["gmm_launches"] * G * M * (2 * D + 1) * 4 + n_rows * (D * 4 + G * 4),
     }
 

@@ -11,13 +11,13 @@
 //   static, shared by all lanes : arcs int4{to,w,in,out} | states int2{first,n} | final f32
 //                                 | hmm_info 8 x i32 per HMM | trP/SE per transition-matrix class
 //                                 | GMM parameters transposed [d][comp][gmm]
-//   per lane, double buffered   : active-instance list  inst_arc[2][cap]
+//   per lane, double buffered   : active-instance list  inst_meta[2][cap] int2{arc, hmm | FRESH}
 //                                 token planes          tok[2][S-1][cap] float4{score,ac,lm,path}
-//   per lane, dense, self-cleaning:
-//                                 arc2slot[nArcs]  u32  (the GPU form of WFSTTransition::hook)
-//                                 entry_key[nArcs] u64  (atomicMax recombination of entry tokens)
-//                                 state_key[nStates] u64 (per-state max of arriving tokens)
-//   per lane, per frame scratch : exit list, arrival records, frontier lists, commit list
+//   per lane, dense             : arcdyn[nArcs] 16 B {u64 entry key, u32 slot, u32 stamp}
+//                                   key  : atomicMax recombination of entry tokens, zeroed by k_commit
+//                                   slot : the GPU form of WFSTTransition::hook, valid iff stamp == epoch
+//                                 state_key[nStates] u64 (per-state max of arriving tokens, self-cleaning)
+//   per lane, per frame scratch : exit list, arrival records (32 B, stored round after round)
 //   per lane, per utterance     : word-boundary arena paths[cap_paths] (32 B records)
 #pragma once
 
@@ -48,16 +48,32 @@ struct ResHdr {           // 32 B per utterance
     int   error, pad1, pad2;
 };
 
+struct ArcDyn {           // 16 B per arc and lane
+    u64      key;         // (orderable score << 32) | arrival record of the best entry candidate, 0 = none
+    unsigned slot;        // slot + 1 of the arc's instance in the list being built
+    unsigned stamp;       // epoch in which `slot` was written
+};
+
+struct Arrival {          // 32 B: one sector
+    float4 tok;
+    int    via;           // arc through which the token arrived, -1 = utterance seed, -2 = dropped
+    int    q;             // state reached
+    int    pad[2];
+};
+
+#define JG_FRESH 0x40000000   // inst_meta.y flag: only the entry token of this instance is valid
+
 struct LaneCtl {
-    int n_cur, n_next, n_exit, n_arr, n_commit, n_touched, n_paths, flip;
-    int n_front[JG_MAX_ROUNDS + 1];
-    int n_huge[JG_MAX_ROUNDS + 1];
+    int n_cur, n_next, n_exit, n_clean, n_paths, flip;
+    unsigned epoch;           // advances every non-idle step of this lane, never repeats
+    int n_arr[JG_MAX_ROUNDS + 2];    // arrivals feeding expansion round k (records are stored back to back)
+    int n_huge[JG_MAX_ROUNDS + 1];   // hub-like states met in round k
     unsigned best_int;        // orderable max of emitting scores of this frame   (WFSTDecoderLite.cpp:417-418)
     unsigned best_ext;        // orderable max of entry scores of this frame      (:572-573)
     u64      best_final;      // key of the best arrival at a final state          (:513-520)
     float norm, thr_emit, thr_start;
-    int mode, srow, frame, utt, error, dirty;
-    int c_active_emit, c_active_end, c_end_proc, c_arcs;
+    int mode, srow, frame, utt, error, pad_;
+    int c_active_emit, c_active_end, c_end_proc, c_arcs, c_entry;
     int hist_count;
     int final_valid;
     float4 final_tok;
@@ -69,8 +85,7 @@ struct LaneCtl {
 struct Dev {
     // static tables
     const int4*  arcs;
-    const int2*  states;
-    const float* state_final;
+    const int4*  states;       // {first arc, n arcs, final weight bits, 0}
     const float* arc_tee;      // per-arc tee weight of the arc's HMM, nullptr when no tee model exists
     const int*   hmm_info;     // [n_hmms][8] : nst | class<<8, tee bits, gmm of states 1..6
     const float* trp;          // [n_class][S*S]
@@ -81,21 +96,17 @@ struct Dev {
     int max_hyps, hist_min, hist_max, hist_nbins;
     int n_lanes, cap, cap_arr, cap_paths, cap_huge, n_rounds, max_frames, frame_stats, max_words;
     int small_deg, huge_deg;
+    int grid_internal, grid_other;   // CTAs of the lane-balanced kernels
     // per-lane state
     LaneCtl*  ctl;
-    int*      inst_arc;
+    int2*     inst_meta;
     float4*   tok;
-    unsigned* arc2slot;
-    u64*      entry_key;
+    ArcDyn*   arcdyn;
     u64*      state_key;
     int*      exit_arc;
     float4*   exit_tok;
-    float4*   arr_tok;
-    int*      arr_via;
-    int2*     front;
-    int2*     huge;
-    int*      commit_arc;
-    int*      touched;
+    Arrival*  arr;
+    int2*     huge;            // [n_lanes][JG_MAX_ROUNDS + 1][cap_huge] {state, arrival record}
     PathRec*  paths;
     int*      hist;
     const float* scores;       // [ring rows][n_gmms]
@@ -133,4 +144,19 @@ __device__ __forceinline__ int warp_alloc(int* counter, bool want)
     if (lane_id() == leader) base = atomicAdd(counter, __popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
     return want ? base + __popc(m & ((1u << lane_id()) - 1u)) : -1;
+}
+
+// two allocations per warp-iteration with both atomics in flight before either result is used
+__device__ __forceinline__ void warp_alloc2(int* c1, bool w1, int* c2, bool w2, int& p1, int& p2)
+{
+    const unsigned m1 = __ballot_sync(0xffffffffu, w1), m2 = __ballot_sync(0xffffffffu, w2);
+    const int l1 = m1 ? __ffs(m1) - 1 : 0, l2 = m2 ? __ffs(m2) - 1 : 1;
+    int b1 = 0, b2 = 0;
+    if (m1 && lane_id() == l1) b1 = atomicAdd(c1, __popc(m1));
+    if (m2 && lane_id() == l2) b2 = atomicAdd(c2, __popc(m2));
+    b1 = __shfl_sync(0xffffffffu, b1, l1);
+    b2 = __shfl_sync(0xffffffffu, b2, l2);
+    const unsigned lt = (1u << lane_id()) - 1u;
+    p1 = w1 ? b1 + __popc(m1 & lt) : -1;
+    p2 = w2 ? b2 + __popc(m2 & lt) : -1;
 }

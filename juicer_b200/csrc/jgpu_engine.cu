@@ -197,7 +197,7 @@ int validate(const JgpuNet* n, const JgpuHmm* m, const JgpuGmm* g, const JgpuCfg
         return fail(JGPU_E_ARG, "max_states=%d unsupported (2..8)", m->max_states);
     if (g->dim <= 0 || g->dim > JG_GMM_DMAX) return fail(JGPU_E_ARG, "feature dim %d unsupported (1..%d)", g->dim, JG_GMM_DMAX);
     if (g->max_comps <= 0 || g->max_comps > 256) return fail(JGPU_E_ARG, "max_comps %d unsupported (1..256)", g->max_comps);
-    if (c->n_lanes < 1 || c->n_lanes > 4096) return fail(JGPU_E_ARG, "n_lanes %d out of range", c->n_lanes);
+    if (c->n_lanes < 1 || c->n_lanes > JG_MAX_LANES) return fail(JGPU_E_ARG, "n_lanes %d out of range (1..%d)", c->n_lanes, JG_MAX_LANES);
     for (int s = 0; s < n->n_states; ++s) {
         const int f = n->state_first[s], k = n->state_narcs[s];
         if (k < 0 || (k > 0 && (f < 0 || f + k > n->n_arcs))) return fail(JGPU_E_ARG, "state %d arc range invalid", s);
@@ -238,11 +238,12 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
         memcpy(&wbits, &n->arc_weight[a], 4);
         arcs[a] = make_int4(n->arc_to[a], wbits, n->arc_in[a], n->arc_out[a]);
     }
-    std::vector<int2> states(NS);
-    std::vector<float> fin(n->state_final, n->state_final + NS);
+    std::vector<int4> states(NS);
     int max_deg = 0;
     for (int s = 0; s < NS; ++s) {
-        states[s] = make_int2(n->state_first[s], n->state_narcs[s]);
+        int fbits;
+        memcpy(&fbits, &n->state_final[s], 4);
+        states[s] = make_int4(n->state_first[s], n->state_narcs[s], fbits, 0);
         max_deg = std::max(max_deg, n->state_narcs[s]);
     }
     h->max_deg = max_deg;
@@ -294,15 +295,14 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
     }
 
     int rc;
-    int4* d_arcs; int2* d_states; float* d_fin; float* d_tee = nullptr; int* d_info; float* d_trp; int2* d_se;
+    int4* d_arcs; int4* d_states; float* d_tee = nullptr; int* d_info; float* d_trp; int2* d_se;
     if ((rc = upload(h, &d_arcs, arcs))) return rc;
     if ((rc = upload(h, &d_states, states))) return rc;
-    if ((rc = upload(h, &d_fin, fin))) return rc;
     if (any_tee && (rc = upload(h, &d_tee, arc_tee))) return rc;
     if ((rc = upload(h, &d_info, info))) return rc;
     if ((rc = upload(h, &d_trp, trp))) return rc;
     if ((rc = upload(h, &d_se, se))) return rc;
-    d.arcs = d_arcs; d.states = d_states; d.state_final = d_fin; d.arc_tee = d_tee;
+    d.arcs = d_arcs; d.states = d_states; d.arc_tee = d_tee;
     d.hmm_info = d_info; d.trp = d_trp; d.se = d_se;
 
     // GMM parameters, transposed [d][c][g], zero padded
@@ -352,27 +352,34 @@ int build_state(jgpu_handle* h)
     d.n_lanes = c.n_lanes;
     d.cap = c.max_active > 0 ? c.max_active : std::min(d.n_arcs + 1, 1 << 18);
     d.cap = std::max(d.cap, 64);
+    d.cap = std::min(d.cap, 1000000);                    // arrival records are addressed with 21 bits
     d.cap_arr = 2 * d.cap + 1024;
     d.cap_paths = c.max_paths > 0 ? c.max_paths : (1 << 21);   // re-sized from free memory below when 0
-    d.cap_huge = 1024;
+    d.cap_huge = 256;
     d.max_frames = c.max_frames > 0 ? c.max_frames : 4096;
     d.frame_stats = c.frame_stats;
     d.max_words = 256;
     d.small_deg = 4;
     d.huge_deg = 1024;
     h->has_huge = h->max_deg >= d.huge_deg;
-    h->bpl = std::max(2, std::min(296, (1184 + c.n_lanes - 1) / c.n_lanes));
+    h->bpl = std::max(2, std::min(64, (1184 + c.n_lanes - 1) / c.n_lanes));   // k_expand_huge only
+    {
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
+        d.grid_internal = n_sm * (h->S <= 5 ? 4 : 2);   // __launch_bounds__ of k_internal
+        d.grid_other = n_sm * 6;                       // __launch_bounds__(256, 6)
+    }
 
     const size_t cap = d.cap, P = d.S - 1;
-    size_t need = L * (2 * cap * 4 + 2 * P * cap * 16 + (size_t)d.n_arcs * 12 + (size_t)d.n_states * 8 + cap * 24 +
-                       (size_t)d.cap_arr * 36 + (size_t)d.cap_paths * 32);
+    size_t need = L * (2 * cap * 8 + 2 * P * cap * 16 + (size_t)d.n_arcs * 16 + (size_t)d.n_states * 8 + cap * 20 +
+                       (size_t)d.cap_arr * 32 + (size_t)d.cap_paths * 32);
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     if (c.max_paths <= 0) {
-        // word-boundary arena: no garbage collection yet, so give it a quarter of the free memory
+        // word-boundary arena: no garbage collection yet, so give it half of the free memory
         // (1M .. 32M records of 32 B per lane); an utterance that still overflows fails alone
         const size_t fixed = need - L * (size_t)d.cap_paths * 32;
-        const size_t budget = free_b > fixed + (2ull << 30) ? (free_b - fixed - (2ull << 30)) / 4 : 0;
+        const size_t budget = free_b > fixed + (2ull << 30) ? (free_b - fixed - (2ull << 30)) / 2 : 0;
         size_t per_lane = budget / (L * 32);
         per_lane = std::min<size_t>(std::max<size_t>(per_lane, 1u << 20), 1u << 25);
         d.cap_paths = (int)per_lane;
@@ -383,19 +390,14 @@ int build_state(jgpu_handle* h)
                     need / 1e9, c.n_lanes, free_b / 1e9);
     int rc;
     if ((rc = h->alloc(&d.ctl, L))) return rc;
-    if ((rc = h->alloc(&d.inst_arc, L * 2 * cap, false))) return rc;
+    if ((rc = h->alloc(&d.inst_meta, L * 2 * cap, false))) return rc;
     if ((rc = h->alloc(&d.tok, L * 2 * P * cap, false))) return rc;
-    if ((rc = h->alloc(&d.arc2slot, L * d.n_arcs))) return rc;
-    if ((rc = h->alloc(&d.entry_key, L * d.n_arcs))) return rc;
+    if ((rc = h->alloc(&d.arcdyn, L * d.n_arcs))) return rc;
     if ((rc = h->alloc(&d.state_key, L * d.n_states))) return rc;
     if ((rc = h->alloc(&d.exit_arc, L * cap, false))) return rc;
     if ((rc = h->alloc(&d.exit_tok, L * cap, false))) return rc;
-    if ((rc = h->alloc(&d.arr_tok, L * d.cap_arr, false))) return rc;
-    if ((rc = h->alloc(&d.arr_via, L * d.cap_arr, false))) return rc;
-    if ((rc = h->alloc(&d.front, L * 2 * d.cap_arr, false))) return rc;
-    if ((rc = h->alloc(&d.huge, L * 2 * d.cap_huge, false))) return rc;
-    if ((rc = h->alloc(&d.commit_arc, L * cap, false))) return rc;
-    if ((rc = h->alloc(&d.touched, L * d.cap_arr, false))) return rc;
+    if ((rc = h->alloc(&d.arr, L * d.cap_arr, false))) return rc;
+    if ((rc = h->alloc(&d.huge, L * (JG_MAX_ROUNDS + 1) * d.cap_huge, false))) return rc;
     if ((rc = h->alloc(&d.paths, L * d.cap_paths, false))) return rc;
     if ((rc = h->alloc(&d.hist, L * d.hist_nbins))) return rc;
     if ((rc = h->alloc(&d.fstat_cnt, d.frame_stats ? L * d.max_frames * 4 : 1))) return rc;
@@ -458,30 +460,31 @@ int launch_gmm(jgpu_handle* h, const float* d_x, const int* d_rows, int n_rows, 
 int launch_step(jgpu_handle* h, int rel_step)
 {
     const Dev& d = h->d;
-    const dim3 grid(h->bpl, d.n_lanes);
+    const dim3 grid_huge(h->bpl, d.n_lanes);
     h->prof_begin(JGPU_K_BOUNDARY);
     k_boundary<<<d.n_lanes, 32, 0, h->stream>>>(d, rel_step, 1);
     h->prof_end();
     h->prof_begin(JGPU_K_INTERNAL);
-    if (h->S == 5) k_internal<5><<<grid, JG_THREADS, 0, h->stream>>>(d);
-    else k_internal<8><<<grid, JG_THREADS, 0, h->stream>>>(d);
+    if (h->S == 5) k_internal<5><<<d.grid_internal, JG_THREADS, 0, h->stream>>>(d);
+    else k_internal<8><<<d.grid_internal, JG_THREADS, 0, h->stream>>>(d);
     h->prof_end();
     h->prof_begin(JGPU_K_SEED);
-    k_seed<<<grid, JG_THREADS, 0, h->stream>>>(d);
+    k_seed<<<d.grid_other, JG_THREADS, 0, h->stream>>>(d);
     h->prof_end();
     for (int r = 0; r < d.n_rounds; ++r) {
         h->prof_begin(JGPU_K_EXPAND);
-        k_expand<<<grid, JG_THREADS, 0, h->stream>>>(d, r);
+        k_walk<0><<<d.grid_other, JG_THREADS, 0, h->stream>>>(d, r);
         h->prof_end();
         if (h->has_huge) {
             h->prof_begin(JGPU_K_EXPAND_HUGE);
-            k_expand_huge<<<grid, JG_THREADS, 0, h->stream>>>(d, r);
+            k_walk_huge<0><<<grid_huge, JG_THREADS, 0, h->stream>>>(d, r);
             h->prof_end();
             ++h->launches;
         }
     }
     h->prof_begin(JGPU_K_COMMIT);
-    k_commit<<<grid, JG_THREADS, 0, h->stream>>>(d);
+    k_walk<1><<<d.grid_other, JG_THREADS, 0, h->stream>>>(d, 0);
+    if (h->has_huge) { k_walk_huge<1><<<grid_huge, JG_THREADS, 0, h->stream>>>(d, 0); ++h->launches; }
     h->prof_end();
     h->launches += 4 + d.n_rounds;
     CK(cudaGetLastError());
@@ -872,7 +875,7 @@ int jgpu_profile_read(jgpu_handle* h, double* ms, int64_t* count)
 const char* jgpu_kernel_name(int32_t kind)
 {
     static const char* names[JGPU_N_KERNELS] = {"k_gmm_scores", "k_boundary", "k_internal", "k_seed", "k_expand",
-                                                "k_expand_huge", "k_commit"};
+                                                "k_expand_huge", "k_commit"};   // expand = k_walk<0>, commit = k_walk<1>
     return (kind >= 0 && kind < JGPU_N_KERNELS) ? names[kind] : "";
 }
 

@@ -1,26 +1,34 @@
 // jgpu_search.cuh — the per-frame token-passing kernels (sm_100a).
 //
 // One frame step of every lane is the launch sequence
-//   k_boundary -> k_internal -> k_seed -> { k_expand [-> k_expand_huge] } x n_rounds -> k_commit
+//   k_boundary -> k_internal -> k_seed -> { k_walk<0> [-> k_walk_huge<0>] } x n_rounds
+//              -> k_walk<1> [-> k_walk_huge<1>]
 // which restates WFSTDecoderLite::processFrame (src/WFSTDecoderLite.cpp:311-372) as
 // data-parallel passes.  All float arithmetic on scores is plain fp32 add/sub in the
 // reference's per-token order (compiled with -fmad=false; there are no multiplies), so
 // every token carries bit-identical scores to the CPU decoder.
+//
+// Work distribution: the per-lane work lists (active instances, exit tokens, frontier,
+// commit list) have very different lengths (a lane whose hub state was just expanded holds
+// 20k fresh instances, its neighbour 2k), so every kernel runs a fixed grid (a multiple of
+// the 148 SMs) and each CTA takes an equal, contiguous slice of the CONCATENATION of all
+// lanes' lists (prefix of the per-lane counts in shared memory).
 #pragma once
 
 #include "jgpu_device.cuh"
 
+#define JG_MAX_LANES 1024
+
 // Per-lane views -------------------------------------------------------------------------
 struct LaneView {
     LaneCtl* c;
-    int* arc_cur;  int* arc_nxt;
+    int2* meta_cur; int2* meta_nxt;
     float4* tok_cur; float4* tok_nxt;
-    unsigned* a2s;
-    u64* ekey; u64* skey;
+    ArcDyn* ad;
+    u64* skey;
     int* exit_arc; float4* exit_tok;
-    float4* arr_tok; int* arr_via;
-    int2* front; int2* huge;
-    int* commit_arc; int* touched;
+    Arrival* arr;
+    int2* huge;
     PathRec* paths;
     int* hist;
 };
@@ -31,24 +39,98 @@ __device__ __forceinline__ LaneView lane_view(const Dev& d, int lane)
     v.c = d.ctl + lane;
     const int flip = v.c->flip;
     const size_t cap = (size_t)d.cap, P = (size_t)(d.S - 1);
-    v.arc_cur = d.inst_arc + ((size_t)lane * 2 + flip) * cap;
-    v.arc_nxt = d.inst_arc + ((size_t)lane * 2 + (flip ^ 1)) * cap;
+    v.meta_cur = d.inst_meta + ((size_t)lane * 2 + flip) * cap;
+    v.meta_nxt = d.inst_meta + ((size_t)lane * 2 + (flip ^ 1)) * cap;
     v.tok_cur = d.tok + ((size_t)lane * 2 + flip) * P * cap;
     v.tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * P * cap;
-    v.a2s = d.arc2slot + (size_t)lane * d.n_arcs;
-    v.ekey = d.entry_key + (size_t)lane * d.n_arcs;
+    v.ad = d.arcdyn + (size_t)lane * d.n_arcs;
     v.skey = d.state_key + (size_t)lane * d.n_states;
     v.exit_arc = d.exit_arc + (size_t)lane * cap;
     v.exit_tok = d.exit_tok + (size_t)lane * cap;
-    v.arr_tok = d.arr_tok + (size_t)lane * d.cap_arr;
-    v.arr_via = d.arr_via + (size_t)lane * d.cap_arr;
-    v.front = d.front + (size_t)lane * 2 * d.cap_arr;
-    v.huge = d.huge + (size_t)lane * 2 * d.cap_huge;
-    v.commit_arc = d.commit_arc + (size_t)lane * cap;
-    v.touched = d.touched + (size_t)lane * d.cap_arr;
+    v.arr = d.arr + (size_t)lane * d.cap_arr;
+    v.huge = d.huge + (size_t)lane * (JG_MAX_ROUNDS + 1) * d.cap_huge;
     v.paths = d.paths + (size_t)lane * d.cap_paths;
     v.hist = d.hist + (size_t)lane * d.hist_nbins;
     return v;
+}
+
+// aggregated counter bump: the threads of the warp that are here together share one
+// atomicAdd.  All of them must target the SAME counter (one lane per CTA segment).
+__device__ __forceinline__ int agg_inc(int* counter)
+{
+    const unsigned peers = __activemask();
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane_id() == leader) base = atomicAdd(counter, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + __popc(peers & ((1u << lane_id()) - 1u));
+}
+
+// ---- lane-balanced slicing ---------------------------------------------------------------
+enum { JG_CNT_CUR = 0, JG_CNT_EXIT, JG_CNT_ROUND, JG_CNT_ALL };
+
+// first arrival record of expansion round k (arrivals of earlier rounds are final by then)
+__device__ __forceinline__ int arr_base(const LaneCtl* c, int round)
+{
+    int b = 0;
+    for (int j = 0; j < round; ++j) b += c->n_arr[j];
+    return b;
+}
+
+__device__ __forceinline__ int lane_count(const Dev& d, int lane, int which, int round)
+{
+    const LaneCtl* c = d.ctl + lane;
+    const int mode = c->mode;
+    if (mode == JG_MODE_IDLE) return 0;
+    switch (which) {
+    case JG_CNT_CUR: return mode == JG_MODE_FRAME ? c->n_cur : 0;
+    case JG_CNT_EXIT: return mode == JG_MODE_FRAME ? c->n_exit : 0;
+    case JG_CNT_ROUND: {
+        const int b = arr_base(c, round);
+        return max(0, min(c->n_arr[round], d.cap_arr - b));
+    }
+    default: return min(arr_base(c, d.n_rounds + 1), d.cap_arr);
+    }
+}
+
+// sh_pref[0..L] = exclusive prefix of the lane counts; returns this CTA's global slice [g0, g1)
+__device__ __forceinline__ void balanced_slice(const Dev& d, int which, int round, int* sh_pref, int& g0, int& g1)
+{
+    const int L = d.n_lanes;
+    for (int l = threadIdx.x; l < L; l += blockDim.x) sh_pref[l + 1] = lane_count(d, l, which, round);
+    if (threadIdx.x == 0) sh_pref[0] = 0;
+    __syncthreads();
+    if (threadIdx.x < 32) {                                  // warp 0: scan L values, L/32 per thread
+        const int per = (L + 31) / 32;
+        const int b = threadIdx.x * per;
+        int sum = 0;
+        for (int i = 0; i < per; ++i)
+            if (b + i < L) sum += sh_pref[b + i + 1];
+        int incl = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)threadIdx.x >= o) incl += t;
+        }
+        int run = incl - sum;
+        for (int i = 0; i < per; ++i)
+            if (b + i < L) { run += sh_pref[b + i + 1]; sh_pref[b + i + 1] = run; }
+    }
+    __syncthreads();
+    const int total = sh_pref[L];
+    int per = (total + gridDim.x - 1) / gridDim.x;
+    per = (per + 31) & ~31;
+    g0 = min(blockIdx.x * per, total);
+    g1 = min(g0 + per, total);
+}
+
+__device__ __forceinline__ int first_lane_of(const int* sh_pref, int L, int g)
+{
+    int lo = 0, hi = L;                                      // largest l with sh_pref[l] <= g
+    while (lo + 1 < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sh_pref[mid] <= g) lo = mid; else hi = mid;
+    }
+    return lo;
 }
 
 // =========================================================================================
@@ -156,15 +238,15 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d, int step, int open)
     // ---- (A) close the previous step ----------------------------------------------------
     if (l == 0 && prev_mode != JG_MODE_IDLE) {
         const int n_after = min(c->n_next, d.cap);
+        const int n_arr_total = arr_base(c, d.n_rounds + 1);
         if (c->n_next > d.cap) c->error |= JG_ERR_ACTIVE;
-        if (c->n_arr > d.cap_arr) c->error |= JG_ERR_ARRIVALS;
+        if (n_arr_total > d.cap_arr) c->error |= JG_ERR_ARRIVALS;
         if (c->n_paths > d.cap_paths) c->error |= JG_ERR_PATHS;
         const u64 key = c->best_final;
         if (key) {
-            const unsigned r = (unsigned)key;
-            float4 t = v.arr_tok[r];
-            const int via = v.arr_via[r];
-            const float fw = d.state_final[d.arcs[via].x];
+            const Arrival a = v.arr[(unsigned)key];
+            float4 t = a.tok;
+            const float fw = __int_as_float(d.states[a.q].z);
             t.x += fw;                                        // :517-518
             t.z += fw;
             c->final_tok = t;
@@ -179,7 +261,7 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d, int step, int open)
             c->s_proc_emit += c->c_active_emit;
             c->s_proc_end += c->c_end_proc;
             c->s_arcs += c->c_arcs;
-            c->s_entry += min(c->n_commit, d.cap);
+            c->s_entry += c->c_entry;
             c->s_gmm += d.n_gmms;
             c->s_frames += 1;
             if (d.frame_stats) {
@@ -199,6 +281,10 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d, int step, int open)
     __syncwarp();
 
     // ---- (B) open this step -------------------------------------------------------------
+    if (mode != JG_MODE_IDLE && ((c->epoch + 1u) & 0x7ffu) == 0u) {      // 11-bit epoch of the state keys wraps
+        for (int i = l; i < d.n_states; i += 32) v.skey[i] = 0;
+    }
+    __syncwarp();
     float thr_emit = JG_LZ;
     if (mode == JG_MODE_FRAME && d.max_hyps > 0) {
         thr_emit = hist_thresh_warp(d, v);                   // whole warp
@@ -210,16 +296,18 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d, int step, int open)
             c->flip ^= 1;
             c->n_cur = min(c->n_next, d.cap);
         }
-        c->n_next = 0; c->n_exit = 0; c->n_arr = 0; c->n_commit = 0; c->n_touched = 0;
-        for (int i = 0; i <= JG_MAX_ROUNDS; ++i) { c->n_front[i] = 0; c->n_huge[i] = 0; }
+        c->n_next = 0; c->n_exit = 0;
+        for (int i = 0; i <= JG_MAX_ROUNDS; ++i) { c->n_arr[i] = 0; c->n_huge[i] = 0; }
+        c->n_arr[JG_MAX_ROUNDS + 1] = 0;
         c->best_final = 0;
-        c->c_active_emit = c->c_active_end = c->c_end_proc = c->c_arcs = 0;
+        c->c_active_emit = c->c_active_end = c->c_end_proc = c->c_arcs = c->c_entry = 0;
         c->mode = mode;
+        if (mode != JG_MODE_IDLE) c->epoch += 1;             // invalidates every arcdyn.slot of older steps
         if (mode == JG_MODE_SEED) {                          // recognitionStart :139-228
             c->utt = s.w;
             c->frame = 0;
-            c->dirty = c->error;
             c->error = 0;
+            c->n_cur = 0;                                    // previous utterance's instances are dropped (:148-158)
             c->n_paths = 0;
             c->best_int = f2o(JG_LZ);
             c->best_ext = f2o(JG_LZ);
@@ -288,134 +376,127 @@ __device__ __forceinline__ float4 viterbi_into(const float4 (&src)[S], const flo
 }
 
 template <int S>
-__global__ void __launch_bounds__(JG_THREADS) k_internal(Dev d)
+__global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? 4 : 2)) k_internal(Dev d)
 {
-    const int lane = blockIdx.y;
-    LaneView v = lane_view(d, lane);
-    LaneCtl* c = v.c;
-    const int mode = c->mode;
-    if (mode == JG_MODE_IDLE) return;
-    const int n = c->n_cur;
+    __shared__ int sh_pref[JG_MAX_LANES + 1];
+    __shared__ float sh_best[JG_THREADS / 32];
+    __shared__ int sh_cnt[3][JG_THREADS / 32];
+    int g0, g1;
+    balanced_slice(d, JG_CNT_CUR, 0, sh_pref, g0, g1);
+    if (g0 >= g1) return;
     const size_t cap = (size_t)d.cap;
     constexpr int P = S - 1;
-
-    if (mode == JG_MODE_SEED) {
-        // new utterance on this lane: drop the previous utterance's instances
-        // (recognitionStart :148-158); after a failed utterance wipe the dense tables.
-        const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-        if (c->dirty) {
-            for (int i = gtid; i < d.n_arcs; i += gsz) { v.a2s[i] = 0; v.ekey[i] = 0; }
-            for (int i = gtid; i < d.n_states; i += gsz) v.skey[i] = 0;
-        } else {
-            for (int k = gtid; k < n; k += gsz) v.a2s[v.arc_cur[k]] = 0;
-        }
-        return;
-    }
-
-    const float norm = c->norm, thr_emit = c->thr_emit, thr_start = c->thr_start;
-    const float* __restrict__ scores = d.scores + (size_t)c->srow * d.n_gmms;
     const bool hist_on = d.max_hyps > 0;
-    float best = JG_LZ;
-    int cnt_emit = 0, cnt_end = 0, cnt_hist = 0;
+    const int L = d.n_lanes;
 
-    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const int k = base + threadIdx.x;
-        const bool valid = k < n;
-        bool survive = false, has_exit = false;
-        int arc = 0, nst = 2;
-        float4 nt[S];
-        float4 ex = null_tok();
+    for (int lane = first_lane_of(sh_pref, L, g0); lane < L && sh_pref[lane] < g1; ++lane) {
+        const int i0 = max(g0, sh_pref[lane]) - sh_pref[lane];
+        const int i1 = min(g1, sh_pref[lane + 1]) - sh_pref[lane];
+        if (i1 <= i0) continue;
+        LaneView v = lane_view(d, lane);
+        LaneCtl* c = v.c;
+        const float norm = c->norm, thr_emit = c->thr_emit, thr_start = c->thr_start;
+        const unsigned epoch = c->epoch;
+        const float* __restrict__ scores = d.scores + (size_t)c->srow * d.n_gmms;
+        float best = JG_LZ;
+        int cnt_emit = 0, cnt_end = 0, cnt_hist = 0;
+
+        for (int base = i0; base < i1; base += blockDim.x) {
+            const int k = base + threadIdx.x;
+            const bool valid = k < i1;
+            bool survive = false, has_exit = false;
+            int arc = 0, nst = 2, hmm = 0;
+            float4 nt[S];
+            float4 ex = null_tok();
 #pragma unroll
-        for (int i = 0; i < S; ++i) nt[i] = null_tok();
-        if (valid) {
-            arc = v.arc_cur[k];
-            const int4 a = __ldg(&d.arcs[arc]);
-            const int hmm = a.z - 1;
-            const int4 i0 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2);
-            const int4 i1 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2 + 1);
-            nst = i0.x & 0xff;
-            const int cls = i0.x >> 8;
-            const int gm[6] = {i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-            const float* __restrict__ trp = d.trp + (size_t)cls * S * S;
-            const int2* __restrict__ se = d.se + (size_t)cls * S;
-            float4 old[S];
+            for (int i = 0; i < S; ++i) nt[i] = null_tok();
+            if (valid) {
+                const int2 meta = v.meta_cur[k];
+                arc = meta.x;
+                hmm = meta.y & ~JG_FRESH;
+                const bool fresh = (meta.y & JG_FRESH) != 0;
+                const int4 h0 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2);
+                const int4 h1 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2 + 1);
+                nst = h0.x & 0xff;
+                const int cls = h0.x >> 8;
+                const int gm[6] = {h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                const float* __restrict__ trp = d.trp + (size_t)cls * S * S;
+                const int2* __restrict__ se = d.se + (size_t)cls * S;
+                float4 old[S];
+                old[0] = v.tok_cur[k];
 #pragma unroll
-            for (int i = 0; i < P; ++i) old[i] = (i < nst - 1) ? v.tok_cur[(size_t)i * cap + k] : null_tok();
-            old[S - 1] = null_tok();
-            if (old[0].x > JG_LZ && old[0].x < thr_start) old[0] = null_tok();   // :915-918
-            int nlive = 0;
+                for (int i = 1; i < P; ++i)
+                    old[i] = (!fresh && i < nst - 1) ? v.tok_cur[(size_t)i * cap + k] : null_tok();
+                old[S - 1] = null_tok();
+                if (old[0].x > JG_LZ && old[0].x < thr_start) old[0] = null_tok();   // :915-918
+                int nlive = 0;
 #pragma unroll
-            for (int j = 1; j < S - 1; ++j) {
-                if (j < nst - 1) {
-                    float4 res = viterbi_into<S>(old, trp, __ldg(se + j), j, nst);
-                    res.x = res.x - norm;                                          // :408
-                    if (res.x > thr_emit) {
-                        const float o = __ldg(scores + gm[j - 1]);                 // calcOutput :411
-                        res.x = res.x + o;
-                        res.y = res.y + o;
-                        if (hist_on) {                                             // Histogram::addScore
-                            int sc;
-                            if (res.x < 0.0f) sc = (int)((double)res.x - 0.5);
-                            else sc = (int)((double)res.x + 0.5);
-                            if (sc > d.hist_max) atomicOr(&c->error, JG_ERR_HIST);
-                            else if (sc >= d.hist_min) { atomicAdd(&v.hist[sc - d.hist_min], 1); ++cnt_hist; }
+                for (int j = 1; j < S - 1; ++j) {
+                    if (j < nst - 1) {
+                        float4 res = viterbi_into<S>(old, trp, __ldg(se + j), j, nst);
+                        res.x = res.x - norm;                                          // :408
+                        if (res.x > thr_emit) {
+                            const float o = __ldg(scores + gm[j - 1]);                 // calcOutput :411
+                            res.x = res.x + o;
+                            res.y = res.y + o;
+                            if (hist_on) {                                             // Histogram::addScore
+                                int sc;
+                                if (res.x < 0.0f) sc = (int)((double)res.x - 0.5);
+                                else sc = (int)((double)res.x + 0.5);
+                                if (sc > d.hist_max) atomicOr(&c->error, JG_ERR_HIST);
+                                else if (sc >= d.hist_min) { atomicAdd(&v.hist[sc - d.hist_min], 1); ++cnt_hist; }
+                            }
+                            if (res.x > best) best = res.x;
+                            if (res.x > JG_LZ) { ++nlive; nt[j] = res; }
                         }
-                        if (res.x > best) best = res.x;
-                        if (res.x > JG_LZ) { ++nlive; nt[j] = res; }
                     }
                 }
+                cnt_emit += nlive;
+                survive = nlive > 0;
+                // exit state from the NEW emitting tokens (:443-483)
+                {
+                    float4 res = viterbi_into<S>(nt, trp, __ldg(se + (nst - 1)), nst - 1, nst);
+                    if (res.x > JG_LZ) { ex = res; has_exit = true; ++cnt_end; }
+                }
             }
-            cnt_emit += nlive;
-            survive = nlive > 0;
-            // exit state from the NEW emitting tokens (:443-483)
-            {
-                float4 res = viterbi_into<S>(nt, trp, __ldg(se + (nst - 1)), nst - 1, nst);
-                if (res.x > JG_LZ) { ex = res; has_exit = true; ++cnt_end; }
-            }
-        }
-        // survivors -> next list (warp-ballot compaction)
-        const int pos = warp_alloc(&c->n_next, survive);
-        if (survive) {
-            if (pos < d.cap) {
-                v.arc_nxt[pos] = arc;
+            // survivors -> next list (warp-ballot compaction); instances that die simply stop
+            // being listed: their arcdyn.slot goes stale with the epoch (:924-925)
+            int pos, e;
+            warp_alloc2(&c->n_next, survive, &c->n_exit, has_exit, pos, e);
+            if (survive && pos < d.cap) {
+                v.meta_nxt[pos] = make_int2(arc, hmm);
                 v.tok_nxt[pos] = null_tok();                  // entry token consumed (:426-435)
 #pragma unroll
                 for (int i = 1; i < P; ++i)
                     if (i < nst - 1) v.tok_nxt[(size_t)i * cap + pos] = nt[i];
-                v.a2s[arc] = (unsigned)pos + 1u;
-            } else {
-                v.a2s[arc] = 0;
+                *reinterpret_cast<uint2*>(&v.ad[arc].slot) = make_uint2((unsigned)pos + 1u, epoch);
             }
-        } else if (valid) {
-            v.a2s[arc] = 0;                                   // instance deactivated (:924-925)
+            if (has_exit) {                                   // n_exit <= n_cur <= cap
+                v.exit_arc[e] = arc;
+                v.exit_tok[e] = ex;
+            }
         }
-        const int e = warp_alloc(&c->n_exit, has_exit);
-        if (has_exit) {                                       // n_exit <= n_cur <= cap
-            v.exit_arc[e] = arc;
-            v.exit_tok[e] = ex;
+        // per-lane block reductions
+        for (int o = 16; o > 0; o >>= 1) {
+            best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+            cnt_emit += __shfl_xor_sync(0xffffffffu, cnt_emit, o);
+            cnt_end += __shfl_xor_sync(0xffffffffu, cnt_end, o);
+            cnt_hist += __shfl_xor_sync(0xffffffffu, cnt_hist, o);
         }
-    }
-    // block reductions
-    __shared__ float sh_best[JG_THREADS / 32];
-    __shared__ int sh_cnt[3][JG_THREADS / 32];
-    for (int o = 16; o > 0; o >>= 1) {
-        best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
-        cnt_emit += __shfl_xor_sync(0xffffffffu, cnt_emit, o);
-        cnt_end += __shfl_xor_sync(0xffffffffu, cnt_end, o);
-        cnt_hist += __shfl_xor_sync(0xffffffffu, cnt_hist, o);
-    }
-    const int w = threadIdx.x >> 5;
-    if (lane_id() == 0) { sh_best[w] = best; sh_cnt[0][w] = cnt_emit; sh_cnt[1][w] = cnt_end; sh_cnt[2][w] = cnt_hist; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 1; i < JG_THREADS / 32; ++i) {
-            best = fmaxf(best, sh_best[i]);
-            cnt_emit += sh_cnt[0][i]; cnt_end += sh_cnt[1][i]; cnt_hist += sh_cnt[2][i];
+        const int w = threadIdx.x >> 5;
+        __syncthreads();
+        if (lane_id() == 0) { sh_best[w] = best; sh_cnt[0][w] = cnt_emit; sh_cnt[1][w] = cnt_end; sh_cnt[2][w] = cnt_hist; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < JG_THREADS / 32; ++i) {
+                best = fmaxf(best, sh_best[i]);
+                cnt_emit += sh_cnt[0][i]; cnt_end += sh_cnt[1][i]; cnt_hist += sh_cnt[2][i];
+            }
+            if (best > JG_LZ) atomicMax(&c->best_int, f2o(best));
+            if (cnt_emit) atomicAdd(&c->c_active_emit, cnt_emit);
+            if (cnt_end) atomicAdd(&c->c_active_end, cnt_end);
+            if (cnt_hist) atomicAdd(&c->hist_count, cnt_hist);
         }
-        if (best > JG_LZ) atomicMax(&c->best_int, f2o(best));
-        if (cnt_emit) atomicAdd(&c->c_active_emit, cnt_emit);
-        if (cnt_end) atomicAdd(&c->c_active_end, cnt_end);
-        if (cnt_hist) atomicAdd(&c->hist_count, cnt_hist);
     }
 }
 
@@ -423,256 +504,293 @@ __global__ void __launch_bounds__(JG_THREADS) k_internal(Dev d)
 // External propagation (doHMMExternalPropagation :937-982 + propagateToken :491-605) as
 // level-synchronous rounds over WFST states.
 //   arrival  = a token reaching state q through arc `via` (exit of an instance, epsilon arc,
-//              or tee pass-through).  Arrivals are max-reduced per state (64-bit atomicMax on
-//              state_key: score bits | record index); only the winner of a state is expanded,
-//              once per round, instead of the reference's re-expansion per token.
-//   expansion= per out-arc of q: epsilon arc -> arrival for the next round (:533-540);
-//              model arc -> entry-token candidate, atomicMax on entry_key (:542-582);
-//              tee model -> additional pass-through arrival (:584-600).
+//              or tee pass-through).  Arrivals are max-reduced per state by a fire-and-forget
+//              64-bit atomicMax on state_key (score bits | record index); the records of one
+//              round are stored back to back, so round k simply walks its slice of records and
+//              expands those that still own their state — once per round instead of the
+//              reference's re-expansion per token.
+//   pass 0   = expansion, per out-arc of q: epsilon arc -> arrival for the next round
+//              (:533-540); model arc -> entry-token candidate, atomicMax on arcdyn.key
+//              (:542-582); tee model -> additional pass-through arrival (:584-600).
+//   pass 1   = commit: every record that owns its state walks its arc row again; the candidate
+//              that owns arcdyn.key writes the entry token into the next list, attaching a new
+//              instance when the arc had none (attachNetInst :751-774), and clears the key.
+// No atomic in pass 0 returns a value the thread has to wait for, except the per-round record
+// counter (one aggregated atomicAdd per warp).
 // =========================================================================================
-__device__ __forceinline__ void arrive(const Dev& d, const LaneView& v, int q, int via, float4 tok, int out_round)
+// state key = epoch (11 bits) | orderable score (32 bits) | arrival record (21 bits): keys of older
+// steps always lose the atomicMax and never compare equal, so state_key needs no per-frame cleaning
+// (k_boundary wipes a lane's table when its 11-bit epoch wraps, once every 2048 steps).
+#define JG_R_BITS 21
+__device__ __forceinline__ u64 state_key_of(unsigned epoch, float score, unsigned r)
 {
-    const int r = atomicAdd(&v.c->n_arr, 1);
+    return ((u64)(epoch & 0x7ffu) << 53) | ((u64)f2o(score) << JG_R_BITS) | (u64)r;
+}
+
+__device__ __forceinline__ void arrive(const Dev& d, const LaneView& v, int q, int via, float4 tok, int out_round,
+                                       int out_base)
+{
+    const int r = out_base + agg_inc(&v.c->n_arr[out_round]);
     if (r >= d.cap_arr) return;                              // flagged by k_boundary
-    v.arr_tok[r] = tok;
-    v.arr_via[r] = via;
-    const u64 key = ((u64)f2o(tok.x) << 32) | (unsigned)r;
-    const u64 old = atomicMax(&v.skey[q], key);
-    if (old < key) {
-        const int f = atomicAdd(&v.c->n_front[out_round], 1);   // <= n_arr <= cap_arr
-        v.front[(size_t)(out_round & 1) * d.cap_arr + f] = make_int2(q, r);
-    }
-    if (old == 0) {
-        const int t = atomicAdd(&v.c->n_touched, 1);
-        v.touched[t] = q;
-    }
+    Arrival a;
+    a.tok = tok; a.via = via; a.q = q; a.pad[0] = a.pad[1] = 0;
+    v.arr[r] = a;
+    atomicMax(&v.skey[q], state_key_of(v.c->epoch, tok.x, (unsigned)r));
 }
 
-__global__ void __launch_bounds__(JG_THREADS) k_seed(Dev d)
+__global__ void __launch_bounds__(JG_THREADS, 6) k_seed(Dev d)
 {
-    const int lane = blockIdx.y;
-    LaneView v = lane_view(d, lane);
-    LaneCtl* c = v.c;
-    const int mode = c->mode;
-    if (mode == JG_MODE_IDLE) return;
-    if (mode == JG_MODE_SEED) {
-        // propagateToken(&zeroToken, NULL) (:221-226): an arrival at the initial state
-        if (blockIdx.x == 0 && threadIdx.x == 0)
-            arrive(d, v, d.init_state, -1, make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1)), 0);
-        return;
-    }
-    const float be = o2f(c->best_int);
-    const float thr_end = (d.end_beam > 0.0f ? (be - d.end_beam) : JG_LZ);     // :349
-    const float thr_word = (d.word_beam > 0.0f ? (be - d.word_beam) : JG_LZ);  // :350
-    const int n = c->n_exit;
-    int proc = 0;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        const int arc = v.exit_arc[e];
-        const float4 t = v.exit_tok[e];
-        const int4 a = __ldg(&d.arcs[arc]);
-        const float thr = a.w == 0 ? thr_end : thr_word;                        // :952-962
-        if (t.x > thr) {
-            ++proc;
-            arrive(d, v, a.x, arc, t, 0);
+    __shared__ int sh_pref[JG_MAX_LANES + 1];
+    // utterance seeds: propagateToken(&zeroToken, NULL) (:221-226) = an arrival at the initial state
+    if (blockIdx.x == 0 && threadIdx.x < 32)
+        for (int lane = threadIdx.x; lane < d.n_lanes; lane += 32)
+            if (d.ctl[lane].mode == JG_MODE_SEED) {
+                LaneView v = lane_view(d, lane);
+                Arrival a;
+                a.tok = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
+                a.via = -1; a.q = d.init_state; a.pad[0] = a.pad[1] = 0;
+                v.arr[0] = a;                                 // seed lanes have no exit tokens: record 0 is free
+                v.c->n_arr[0] = 1;
+                v.skey[d.init_state] = state_key_of(v.c->epoch, 0.0f, 0u);
+            }
+    int g0, g1;
+    balanced_slice(d, JG_CNT_EXIT, 0, sh_pref, g0, g1);
+    if (g0 >= g1) return;
+    const int L = d.n_lanes;
+    for (int lane = first_lane_of(sh_pref, L, g0); lane < L && sh_pref[lane] < g1; ++lane) {
+        const int i0 = max(g0, sh_pref[lane]) - sh_pref[lane];
+        const int i1 = min(g1, sh_pref[lane + 1]) - sh_pref[lane];
+        if (i1 <= i0) continue;
+        LaneView v = lane_view(d, lane);
+        LaneCtl* c = v.c;
+        const float be = o2f(c->best_int);
+        const float thr_end = (d.end_beam > 0.0f ? (be - d.end_beam) : JG_LZ);     // :349
+        const float thr_word = (d.word_beam > 0.0f ? (be - d.word_beam) : JG_LZ);  // :350
+        int proc = 0;
+        for (int e = i0 + threadIdx.x; e < i1; e += blockDim.x) {
+            const int arc = v.exit_arc[e];
+            const float4 t = v.exit_tok[e];
+            const int4 a = __ldg(&d.arcs[arc]);
+            const float thr = a.w == 0 ? thr_end : thr_word;                        // :952-962
+            if (t.x > thr) {
+                ++proc;
+                arrive(d, v, a.x, arc, t, 0, 0);
+            }
         }
+        __syncwarp();
+        for (int o = 16; o > 0; o >>= 1) proc += __shfl_xor_sync(0xffffffffu, proc, o);
+        if (lane_id() == 0 && proc) atomicAdd(&c->c_end_proc, proc);
     }
-    for (int o = 16; o > 0; o >>= 1) proc += __shfl_xor_sync(0xffffffffu, proc, o);
-    if (lane_id() == 0 && proc) atomicAdd(&c->c_end_proc, proc);
 }
 
-__device__ __forceinline__ void process_arc(const Dev& d, const LaneView& v, const float4 tok, unsigned r, int b,
-                                            float thr_end, float thr_word, int out_round)
+struct WalkCtx {
+    float thr_end, thr_word;
+    int out_round, out_base;
+    unsigned epoch;
+};
+
+template <int PASS>
+__device__ __forceinline__ void process_arc(const Dev& d, const LaneView& v, const WalkCtx& x, const float4 tok,
+                                            unsigned r, int b, float& best, int& n_entry)
 {
     const int4 a = __ldg(&d.arcs[b]);
     const float w = __int_as_float(a.y);
+    const float s = tok.x + w;
     if (a.z == 0) {                                           // epsilon input: :533-540
-        const float s = tok.x + w;
-        if (s > thr_end) arrive(d, v, a.x, b, make_float4(s, tok.y, tok.z + w, tok.w), out_round);
-    } else {                                                  // model arc: :542-601
-        const float s = tok.x + w;
-        if (s > JG_LZ) {
-            const u64 key = ((u64)f2o(s) << 32) | r;
-            const u64 old = atomicMax(&v.ekey[b], key);
-            if (old == 0) {
-                const int i = atomicAdd(&v.c->n_commit, 1);
-                if (i < d.cap) v.commit_arc[i] = b;
-                else { v.ekey[b] = 0; atomicOr(&v.c->error, JG_ERR_ACTIVE); }
-            }
-        }
-        if (d.arc_tee) {
-            const float tee = __ldg(d.arc_tee + b);
-            if (tee > JG_LZ) {                                // :584-600
-                const float s2 = s + tee;
-                const float thr = a.w != 0 ? thr_word : thr_end;
-                if (s2 > thr) arrive(d, v, a.x, b, make_float4(s2, tok.y + tee, tok.z + w, tok.w), out_round);
-            }
-        }
+        if (PASS == 0 && s > x.thr_end)
+            arrive(d, v, a.x, b, make_float4(s, tok.y, tok.z + w, tok.w), x.out_round, x.out_base);
+        return;
     }
-}
-
-__global__ void __launch_bounds__(JG_THREADS) k_expand(Dev d, int round)
-{
-    const int lane = blockIdx.y;
-    LaneView v = lane_view(d, lane);
-    LaneCtl* c = v.c;
-    const int mode = c->mode;
-    if (mode == JG_MODE_IDLE) return;
-    const int n = min(c->n_front[round], d.cap_arr);
-    if (n == 0) return;
-    float thr_end = JG_LZ, thr_word = JG_LZ;
-    if (mode == JG_MODE_FRAME) {
-        const float be = o2f(c->best_int);
-        thr_end = (d.end_beam > 0.0f ? (be - d.end_beam) : JG_LZ);
-        thr_word = (d.word_beam > 0.0f ? (be - d.word_beam) : JG_LZ);
-    }
-    const int2* list = v.front + (size_t)(round & 1) * d.cap_arr;
-    const int frame = c->frame;
-    int arcs_done = 0;
-    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const int e = base + threadIdx.x;
-        bool valid = e < n;
-        int q = 0, first = 0, deg = 0;
-        unsigned r = 0;
-        float4 tok = null_tok();
-        if (valid) {
-            const int2 qr = list[e];
-            q = qr.x; r = (unsigned)qr.y;
-            valid = ((unsigned)v.skey[q] == r);              // still the best arrival of q?
-        }
-        if (valid) {
-            tok = v.arr_tok[r];
-            const int via = v.arr_via[r];
-            if (via >= 0) {
-                const int olab = __ldg(&d.arcs[via]).w;
-                if (olab != 0) {                              // word boundary record: :497-509
-                    const int p = atomicAdd(&c->n_paths, 1);
-                    if (p < d.cap_paths) {
-                        PathRec pr;
-                        pr.prev = __float_as_int(tok.w); pr.frame = frame; pr.label = olab;
-                        pr.score = tok.x; pr.ac = tok.y; pr.lm = tok.z; pr.pad0 = pr.pad1 = 0;
-                        v.paths[p] = pr;
-                        tok.w = __int_as_float(p);
-                        v.arr_tok[r].w = tok.w;
+    // model arc: :542-601
+    if (s > JG_LZ) {
+        const u64 key = ((u64)f2o(s) << 32) | r;
+        if (PASS == 0) {
+            atomicMax(&v.ad[b].key, key);                     // recombination: best entry candidate of the arc
+        } else {
+            const uint4 dyn = *reinterpret_cast<const uint4*>(&v.ad[b]);
+            if (dyn.x == r && dyn.y == (unsigned)(key >> 32)) {             // this candidate won
+                const float4 t = make_float4(s, tok.y, tok.z + w, tok.w);   // :568-570
+                if (s > best) best = s;
+                ++n_entry;
+                if (dyn.w == x.epoch && dyn.z != 0) {         // the instance survived the internal phase
+                    v.tok_nxt[dyn.z - 1] = t;                 // plane 0 = entry token
+                    v.ad[b].key = 0;
+                } else {
+                    const int pos = agg_inc(&v.c->n_next);
+                    if (pos < d.cap) {
+                        v.meta_nxt[pos] = make_int2(b, (a.z - 1) | JG_FRESH);
+                        v.tok_nxt[pos] = t;
+                        *reinterpret_cast<uint4*>(&v.ad[b]) = make_uint4(0u, 0u, (unsigned)pos + 1u, x.epoch);
                     } else {
-                        valid = false;                        // flagged by k_boundary
+                        v.ad[b].key = 0;                      // overflow is flagged by k_boundary
                     }
                 }
-                const float fw = __ldg(d.state_final + q);
-                if (valid && fw > JG_LZ) {                    // :513-520
-                    const float cand = tok.x + fw;
-                    atomicMax(&c->best_final, ((u64)f2o(cand) << 32) | r);
+            }
+        }
+    }
+    if (PASS == 0 && d.arc_tee) {
+        const float tee = __ldg(d.arc_tee + b);
+        if (tee > JG_LZ) {                                    // :584-600
+            const float s2 = s + tee;
+            const float thr = a.w != 0 ? x.thr_word : x.thr_end;
+            if (s2 > thr)
+                arrive(d, v, a.x, b, make_float4(s2, tok.y + tee, tok.z + w, tok.w), x.out_round, x.out_base);
+        }
+    }
+}
+
+__device__ __forceinline__ WalkCtx walk_ctx(const Dev& d, const LaneCtl* c, int round)
+{
+    WalkCtx x;
+    x.thr_end = x.thr_word = JG_LZ;
+    if (c->mode == JG_MODE_FRAME) {
+        const float be = o2f(c->best_int);
+        x.thr_end = (d.end_beam > 0.0f ? (be - d.end_beam) : JG_LZ);
+        x.thr_word = (d.word_beam > 0.0f ? (be - d.word_beam) : JG_LZ);
+    }
+    x.out_round = round + 1;
+    x.out_base = arr_base(c, round + 1);
+    x.epoch = c->epoch;
+    return x;
+}
+
+// PASS 0: expansion round `round`.  PASS 1: commit over the records of all rounds.
+template <int PASS>
+__global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
+{
+    __shared__ int sh_pref[JG_MAX_LANES + 1];
+    int g0, g1;
+    balanced_slice(d, PASS == 0 ? JG_CNT_ROUND : JG_CNT_ALL, round, sh_pref, g0, g1);
+    if (g0 >= g1) return;
+    const int L = d.n_lanes;
+    for (int lane = first_lane_of(sh_pref, L, g0); lane < L && sh_pref[lane] < g1; ++lane) {
+        const int i0 = max(g0, sh_pref[lane]) - sh_pref[lane];
+        const int i1 = min(g1, sh_pref[lane + 1]) - sh_pref[lane];
+        if (i1 <= i0) continue;
+        LaneView v = lane_view(d, lane);
+        LaneCtl* c = v.c;
+        const WalkCtx x = walk_ctx(d, c, round);
+        const int rec0 = PASS == 0 ? arr_base(c, round) : 0;
+        const int frame = c->frame;
+        int arcs_done = 0, n_entry = 0;
+        float best = JG_LZ;
+        for (int base = i0; base < i1; base += blockDim.x) {
+            const int e = base + threadIdx.x;
+            bool valid = e < i1;
+            int q = 0, first = 0, deg = 0;
+            const unsigned r = (unsigned)(rec0 + e);
+            float4 tok = null_tok();
+            if (valid) {
+                const Arrival a = v.arr[r];
+                q = a.q;
+                tok = a.tok;
+                valid = a.via != -2 && v.skey[q] == state_key_of(x.epoch, tok.x, r);   // still the best arrival of q?
+                if (valid) {
+                    const int4 st = __ldg(&d.states[q]);
+                    first = st.x; deg = st.y;
+                    if (PASS == 0 && a.via >= 0) {
+                        const int olab = __ldg(&d.arcs[a.via]).w;
+                        if (olab != 0) {                      // word boundary record: :497-509
+                            const int p = agg_inc(&c->n_paths);
+                            if (p < d.cap_paths) {
+                                PathRec pr;
+                                pr.prev = __float_as_int(tok.w); pr.frame = frame; pr.label = olab;
+                                pr.score = tok.x; pr.ac = tok.y; pr.lm = tok.z; pr.pad0 = pr.pad1 = 0;
+                                v.paths[p] = pr;
+                                tok.w = __int_as_float(p);
+                                v.arr[r].tok.w = tok.w;
+                            } else {
+                                valid = false;                // flagged by k_boundary
+                                v.arr[r].via = -2;
+                            }
+                        }
+                        const float fw = __int_as_float(st.z);
+                        if (valid && fw > JG_LZ)              // :513-520
+                            atomicMax(&c->best_final, ((u64)f2o(tok.x + fw) << 32) | r);
+                    }
+                    if (!valid) deg = 0;
+                    if (PASS == 0) arcs_done += deg;
                 }
             }
-        }
-        if (valid) {
-            const int2 st = __ldg(&d.states[q]);
-            first = st.x; deg = st.y;
-            arcs_done += deg;
-        }
-        const bool small = valid && deg <= d.small_deg;
-        const bool is_huge = valid && deg >= d.huge_deg;
-        if (small) {
-            for (int b = first; b < first + deg; ++b) process_arc(d, v, tok, r, b, thr_end, thr_word, round + 1);
-        } else if (is_huge) {
-            const int h = atomicAdd(&c->n_huge[round], 1);
-            if (h < d.cap_huge) v.huge[(size_t)(round & 1) * d.cap_huge + h] = make_int2(q, (int)r);
-            else atomicOr(&c->error, JG_ERR_HUGE);
-        }
-        // medium out-degree: the warp walks the arc row together
-        unsigned mm = __ballot_sync(0xffffffffu, valid && !small && !is_huge);
-        while (mm) {
-            const int src = __ffs(mm) - 1;
-            mm &= mm - 1;
-            const int f_s = __shfl_sync(0xffffffffu, first, src);
-            const int n_s = __shfl_sync(0xffffffffu, deg, src);
-            const unsigned r_s = __shfl_sync(0xffffffffu, r, src);
-            float4 t_s;
-            t_s.x = __shfl_sync(0xffffffffu, tok.x, src);
-            t_s.y = __shfl_sync(0xffffffffu, tok.y, src);
-            t_s.z = __shfl_sync(0xffffffffu, tok.z, src);
-            t_s.w = __shfl_sync(0xffffffffu, tok.w, src);
-            for (int b = f_s + lane_id(); b < f_s + n_s; b += 32)
-                process_arc(d, v, t_s, r_s, b, thr_end, thr_word, round + 1);
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) arcs_done += __shfl_xor_sync(0xffffffffu, arcs_done, o);
-    if (lane_id() == 0 && arcs_done) atomicAdd(&c->c_arcs, arcs_done);
-}
-
-// hub-like states: every block of the lane strides over the arc row
-__global__ void __launch_bounds__(JG_THREADS) k_expand_huge(Dev d, int round)
-{
-    const int lane = blockIdx.y;
-    LaneView v = lane_view(d, lane);
-    LaneCtl* c = v.c;
-    const int mode = c->mode;
-    if (mode == JG_MODE_IDLE) return;
-    const int n = min(c->n_huge[round], d.cap_huge);
-    if (n == 0) return;
-    float thr_end = JG_LZ, thr_word = JG_LZ;
-    if (mode == JG_MODE_FRAME) {
-        const float be = o2f(c->best_int);
-        thr_end = (d.end_beam > 0.0f ? (be - d.end_beam) : JG_LZ);
-        thr_word = (d.word_beam > 0.0f ? (be - d.word_beam) : JG_LZ);
-    }
-    const int2* list = v.huge + (size_t)(round & 1) * d.cap_huge;
-    for (int h = 0; h < n; ++h) {
-        const int2 qr = list[h];
-        const float4 tok = v.arr_tok[qr.y];
-        const int2 st = __ldg(&d.states[qr.x]);
-        for (int b = st.x + blockIdx.x * blockDim.x + threadIdx.x; b < st.x + st.y; b += gridDim.x * blockDim.x)
-            process_arc(d, v, tok, (unsigned)qr.y, b, thr_end, thr_word, round + 1);
-    }
-}
-
-// =========================================================================================
-// k_commit: winners of the entry-token recombination write their token into the next
-// list, attaching a new instance when the arc had none (attachNetInst :751-774); the dense
-// tables are cleaned for the next frame.
-// =========================================================================================
-__global__ void __launch_bounds__(JG_THREADS) k_commit(Dev d)
-{
-    const int lane = blockIdx.y;
-    LaneView v = lane_view(d, lane);
-    LaneCtl* c = v.c;
-    if (c->mode == JG_MODE_IDLE) return;
-    const size_t cap = (size_t)d.cap;
-    const int n = min(c->n_commit, d.cap);
-    float best = JG_LZ;
-    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const int i = base + threadIdx.x;
-        const bool valid = i < n;
-        int b = 0, nst = 2;
-        unsigned slot = 0;
-        float4 t = null_tok();
-        if (valid) {
-            b = v.commit_arc[i];
-            const u64 key = v.ekey[b];
-            v.ekey[b] = 0;
-            const unsigned r = (unsigned)key;
-            const float4 src = v.arr_tok[r];
-            const int4 a = __ldg(&d.arcs[b]);
-            const float w = __int_as_float(a.y);
-            t = make_float4(src.x + w, src.y, src.z + w, src.w);               // :568-570
-            if (t.x > best) best = t.x;
-            slot = v.a2s[b];
-            nst = __ldg(d.hmm_info + (size_t)(a.z - 1) * 8) & 0xff;
-        }
-        const int pos = warp_alloc(&c->n_next, valid && slot == 0);
-        if (valid) {
-            if (slot) {
-                v.tok_nxt[slot - 1] = t;                      // plane 0 = entry token
-            } else if (pos < d.cap) {
-                v.arc_nxt[pos] = b;
-                v.tok_nxt[pos] = t;
-                for (int p = 1; p < nst - 1; ++p) v.tok_nxt[(size_t)p * cap + pos] = null_tok();
-                v.a2s[b] = (unsigned)pos + 1u;
+            const bool small = valid && deg <= d.small_deg;
+            const bool is_huge = valid && deg >= d.huge_deg;
+            if (small) {
+                for (int b = first; b < first + deg; ++b) process_arc<PASS>(d, v, x, tok, r, b, best, n_entry);
+            } else if (is_huge && PASS == 0) {
+                const int h = atomicAdd(&c->n_huge[round], 1);
+                if (h < d.cap_huge) v.huge[(size_t)round * d.cap_huge + h] = make_int2(q, (int)r);
+                else atomicOr(&c->error, JG_ERR_HUGE);
+            }
+            // medium out-degree: the warp walks the arc row together
+            unsigned mm = __ballot_sync(0xffffffffu, valid && !small && !is_huge);
+            while (mm) {
+                const int src = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const int f_s = __shfl_sync(0xffffffffu, first, src);
+                const int n_s = __shfl_sync(0xffffffffu, deg, src);
+                const unsigned r_s = __shfl_sync(0xffffffffu, r, src);
+                float4 t_s;
+                t_s.x = __shfl_sync(0xffffffffu, tok.x, src);
+                t_s.y = __shfl_sync(0xffffffffu, tok.y, src);
+                t_s.z = __shfl_sync(0xffffffffu, tok.z, src);
+                t_s.w = __shfl_sync(0xffffffffu, tok.w, src);
+                for (int b = f_s + lane_id(); b < f_s + n_s; b += 32)
+                    process_arc<PASS>(d, v, x, t_s, r_s, b, best, n_entry);
+                __syncwarp();
             }
         }
+        __syncwarp();
+        for (int o = 16; o > 0; o >>= 1) {
+            arcs_done += __shfl_xor_sync(0xffffffffu, arcs_done, o);
+            n_entry += __shfl_xor_sync(0xffffffffu, n_entry, o);
+            best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+        }
+        if (lane_id() == 0) {
+            if (arcs_done) atomicAdd(&c->c_arcs, arcs_done);
+            if (n_entry) atomicAdd(&c->c_entry, n_entry);
+            if (best > JG_LZ) atomicMax(&c->best_ext, f2o(best));               // :572-573
+        }
     }
-    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if (lane_id() == 0 && best > JG_LZ) atomicMax(&c->best_ext, f2o(best));   // :572-573
-    const int nt = min(c->n_touched, d.cap_arr);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += gridDim.x * blockDim.x)
-        v.skey[v.touched[i]] = 0;
+}
+
+// hub-like states: a group of CTAs per lane strides over the arc row.
+// PASS 0: the states met in round `round`; PASS 1: those of every round.
+template <int PASS>
+__global__ void __launch_bounds__(JG_THREADS) k_walk_huge(Dev d, int round)
+{
+    const int lane = blockIdx.y;
+    LaneCtl* c = d.ctl + lane;
+    if (c->mode == JG_MODE_IDLE) return;
+    const int r_lo = PASS == 0 ? round : 0, r_hi = PASS == 0 ? round + 1 : d.n_rounds;
+    bool any = false;
+    for (int k = r_lo; k < r_hi; ++k) any |= c->n_huge[k] > 0;
+    if (!any) return;
+    LaneView v = lane_view(d, lane);
+    int n_entry = 0;
+    float best = JG_LZ;
+    for (int k = r_lo; k < r_hi; ++k) {
+        const int n = min(c->n_huge[k], d.cap_huge);
+        if (n == 0) continue;
+        const WalkCtx x = walk_ctx(d, c, k);
+        const int2* list = v.huge + (size_t)k * d.cap_huge;
+        for (int h = 0; h < n; ++h) {
+            const int2 qr = list[h];
+            const float4 tok = v.arr[qr.y].tok;
+            if (PASS == 1 && v.skey[qr.x] != state_key_of(x.epoch, tok.x, (unsigned)qr.y)) continue;   // re-expanded later by a better token
+            const int4 st = __ldg(&d.states[qr.x]);
+            for (int b = st.x + blockIdx.x * blockDim.x + threadIdx.x; b < st.x + st.y; b += gridDim.x * blockDim.x)
+                process_arc<PASS>(d, v, x, tok, (unsigned)qr.y, b, best, n_entry);
+        }
+    }
+    if (PASS == 1) {
+        __syncwarp();
+        for (int o = 16; o > 0; o >>= 1) {
+            n_entry += __shfl_xor_sync(0xffffffffu, n_entry, o);
+            best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+        }
+        if (lane_id() == 0) {
+            if (n_entry) atomicAdd(&c->c_entry, n_entry);
+            if (best > JG_LZ) atomicMax(&c->best_ext, f2o(best));
+        }
+    }
 }
