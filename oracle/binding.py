@@ -19,6 +19,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "liboracle_ref.so")
 PORT_SO = os.path.join(HERE, "liboracle.so")
+DROPIN_BIN = os.path.join(HERE, "_ref", "dropin_test")
 LOG_ZERO = -np.finfo(np.float32).max
 
 
@@ -29,6 +30,8 @@ def build(ref: bool = True, port: bool = True) -> None:
         subprocess.check_call(["make", "-s", "-C", HERE, "port"])
     if ref and os.path.isdir(os.environ.get("JUICER_REF", "/root/reference")):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+        if os.path.exists(os.path.join(HERE, "..", "juicer_b200", "libjuicer_b200.so")):
+            subprocess.check_call(["make", "-s", "-C", HERE, "dropin"])      # C++ adapter behind Juicer::IDecoder
 
 
 class Word(C.Structure):
