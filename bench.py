@@ -203,6 +203,7 @@ def algorithmic_bytes(stats: Dict[str, int], dims: Dict[str, int], n_rows: int) 
         # arrival record + state key read per expanded record, arc rows, candidate keys, path records
         "k_expand": E * (32 + 8) + X * 16 + X * 8 + P * 32,
         "k_expand_huge": 0.0,                 # its arc rows are counted in k_expand's X
+        "k_expand_r1": 0.0, "k_expand_r2": 0.0,   # later rounds: their bytes are counted in k_expand (round 0 row)
         # second walk: arrival record + state key, arc rows, per-arc dynamic record; winners write
         # the dynamic record, the entry token and the instance meta
         "k_commit": E * (32 + 8) + X * 16 + X * 16 + W * (16 + 16 + 8),

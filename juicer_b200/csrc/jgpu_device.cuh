@@ -61,6 +61,7 @@ struct Arrival {          // 32 B: one sector
     int    pad[2];
 };
 
+#define JG_LR_CLASS 0x40000000   // hmm_info[0] flag: plain left-to-right topology (no skips), nStates <= 5
 #define JG_FRESH 0x40000000   // inst_meta.y flag: only the entry token of this instance is valid
 
 struct LaneCtl {
@@ -90,6 +91,7 @@ struct Dev {
     const int*   hmm_info;     // [n_hmms][8] : nst | class<<8, tee bits, gmm of states 1..6
     const float* trp;          // [n_class][S*S]
     const int2*  se;           // [n_class][S]
+    const float4* lr;          // [n_class][2]: left-to-right classes {a01,a11,a12,a22 | a23,a33,a34,-}
     int n_arcs, n_states, init_state, n_hmms, n_gmms, S;
     // settings
     float start_beam, main_beam, end_beam, word_beam;

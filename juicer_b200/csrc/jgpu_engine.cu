@@ -59,7 +59,9 @@ struct jgpu_handle {
     int bpl = 8;            // CTAs per lane for the search kernels
     bool has_huge = false;
     int max_deg = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // search kernels, copies
+    cudaStream_t stream_gmm = nullptr;   // acoustic scoring of the NEXT frame block overlaps the search
+    cudaEvent_t ev_inputs = nullptr, ev_gmm[2] = {nullptr, nullptr}, ev_search[2] = {nullptr, nullptr};
     std::vector<void*> allocs;
     size_t bytes = 0;
     // schedule
@@ -79,7 +81,11 @@ struct jgpu_handle {
     std::vector<LaneHost> lanes;
     int64_t launches = 0;
     JgpuStats batch_stats{};
+    char* static_base = nullptr;   // arcs | states | arc_tee | hmm tables: pinned in L2 by an access-policy window
+    size_t static_bytes = 0;
     bool own_stream = true;
+    bool overlap = false;   // JUICER_B200_OVERLAP=1: score the next frame block on a second stream (no gain measured on B200:
+                            // the search kernels hold every warp slot, so the two never co-reside)
     // optional per-kernel timing (CUDA events on the launching stream)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -88,9 +94,10 @@ struct jgpu_handle {
     double prof_ms[JGPU_N_KERNELS] = {0};
     int64_t prof_cnt[JGPU_N_KERNELS] = {0};
 
-    void prof_begin(int kind)
+    void prof_begin(int kind, cudaStream_t st = nullptr)
     {
         if (!prof_on) return;
+        if (!st) st = stream;
         if (prof_used + 2 > prof_ev.size()) {
             const size_t n = prof_ev.size() + 4096;
             while (prof_ev.size() < n) {
@@ -100,17 +107,18 @@ struct jgpu_handle {
             }
         }
         prof_kind.push_back(kind);
-        cudaEventRecord(prof_ev[prof_used++], stream);
+        cudaEventRecord(prof_ev[prof_used++], st);
     }
-    void prof_end()
+    void prof_end(cudaStream_t st = nullptr)
     {
         if (!prof_on) return;
-        cudaEventRecord(prof_ev[prof_used++], stream);
+        cudaEventRecord(prof_ev[prof_used++], st ? st : stream);
     }
     void prof_collect()
     {
         if (prof_used == 0) return;
         cudaStreamSynchronize(stream);
+        cudaStreamSynchronize(stream_gmm);
         for (size_t i = 0; i + 1 < prof_used; i += 2) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, prof_ev[i], prof_ev[i + 1]);
@@ -266,6 +274,7 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
     std::vector<float> trp;
     std::vector<int2> se;
     std::vector<int> info((size_t)H * 8, -1);
+    std::vector<float4> lrtab;
     for (int i = 0; i < H; ++i) {
         const int ns = m->n_states[i];
         std::vector<float> t((size_t)S * S, JG_LZ);
@@ -277,6 +286,10 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
         std::string key((const char*)&ns, 4);
         key.append((const char*)t.data(), t.size() * 4);
         key.append((const char*)e.data(), e.size() * 8);
+        // plain left-to-right class: SEIndex[j] = [j-1, j+1) for emitting j, [N-2, N-1) for the exit
+        bool is_lr = S == 5 && ns >= 3 && ns <= 5;
+        for (int j = 1; j < ns - 1 && is_lr; ++j) is_lr = e[j].x == j - 1 && e[j].y == j + 1;
+        if (is_lr) is_lr = e[ns - 1].x == ns - 2 && e[ns - 1].y == ns - 1;
         auto it = cls_of.find(key);
         int cls;
         if (it == cls_of.end()) {
@@ -284,25 +297,51 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
             cls_of.emplace(key, cls);
             trp.insert(trp.end(), t.begin(), t.end());
             se.insert(se.end(), e.begin(), e.end());
+            float c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (is_lr) {
+                for (int j = 1; j < ns - 1; ++j) { c[2 * (j - 1)] = t[(j - 1) * S + j]; c[2 * (j - 1) + 1] = t[j * S + j]; }
+                c[2 * (ns - 2)] = t[(ns - 2) * S + (ns - 1)];
+            }
+            lrtab.push_back(make_float4(c[0], c[1], c[2], c[3]));
+            lrtab.push_back(make_float4(c[4], c[5], c[6], c[7]));
         } else {
             cls = it->second;
         }
         int teebits;
         memcpy(&teebits, &m->tee[i], 4);
-        info[(size_t)i * 8 + 0] = ns | (cls << 8);
+        info[(size_t)i * 8 + 0] = ns | (cls << 8) | (is_lr ? JG_LR_CLASS : 0);
         info[(size_t)i * 8 + 1] = teebits;
         for (int s = 1; s < ns - 1; ++s) info[(size_t)i * 8 + 1 + s] = m->gmm[i * M + s];
     }
 
     int rc;
-    int4* d_arcs; int4* d_states; float* d_tee = nullptr; int* d_info; float* d_trp; int2* d_se;
-    if ((rc = upload(h, &d_arcs, arcs))) return rc;
-    if ((rc = upload(h, &d_states, states))) return rc;
-    if (any_tee && (rc = upload(h, &d_tee, arc_tee))) return rc;
-    if ((rc = upload(h, &d_info, info))) return rc;
-    if ((rc = upload(h, &d_trp, trp))) return rc;
-    if ((rc = upload(h, &d_se, se))) return rc;
-    d.arcs = d_arcs; d.states = d_states; d.arc_tee = d_tee;
+    // The static network + HMM tables live in ONE allocation so that a single L2 access-policy window can
+    // keep them resident: the per-lane dynamic tables stream gigabytes through L2 every frame and would
+    // otherwise evict the arc / state rows that every gather of the search kernels hits.
+    auto pad256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_arcs = pad256(arcs.size() * sizeof(int4)), b_states = pad256(states.size() * sizeof(int4));
+    const size_t b_tee = any_tee ? pad256(arc_tee.size() * sizeof(float)) : 0, b_info = pad256(info.size() * sizeof(int));
+    const size_t b_trp = pad256(trp.size() * sizeof(float)), b_se = pad256(se.size() * sizeof(int2));
+    const size_t b_lr = pad256(lrtab.size() * sizeof(float4));
+    h->static_bytes = b_arcs + b_states + b_tee + b_info + b_trp + b_se + b_lr;
+    char* base = nullptr;
+    if ((rc = h->alloc(&base, h->static_bytes, false))) return rc;
+    h->static_base = base;
+    size_t off = 0;
+    auto put = [&](const void* src, size_t bytes, size_t padded) -> char* {
+        char* p = base + off;
+        if (bytes) cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, h->stream);
+        off += padded;
+        return p;
+    };
+    d.arcs = (const int4*)put(arcs.data(), arcs.size() * sizeof(int4), b_arcs);
+    d.states = (const int4*)put(states.data(), states.size() * sizeof(int4), b_states);
+    d.arc_tee = any_tee ? (const float*)put(arc_tee.data(), arc_tee.size() * sizeof(float), b_tee) : nullptr;
+    int* d_info = (int*)put(info.data(), info.size() * sizeof(int), b_info);
+    float* d_trp = (float*)put(trp.data(), trp.size() * sizeof(float), b_trp);
+    int2* d_se = (int2*)put(se.data(), se.size() * sizeof(int2), b_se);
+    d.lr = (const float4*)put(lrtab.data(), lrtab.size() * sizeof(float4), b_lr);
+    CK(cudaGetLastError());
     d.hmm_info = d_info; d.trp = d_trp; d.se = d_se;
 
     // GMM parameters, transposed [d][c][g], zero padded
@@ -332,6 +371,12 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
     if ((rc = upload(h, &d_det, det))) return rc;
     if ((rc = upload(h, &d_nc, nc))) return rc;
     G.mu = d_mu; G.iv = d_iv; G.det = d_det; G.ncomp = d_nc;
+    {
+        std::vector<double> sp(&JG_SOFTPLUS_TABLE[0][0], &JG_SOFTPLUS_TABLE[0][0] + JG_SP_INTERVALS * (JG_SP_DEG + 1));
+        double* d_sp;
+        if ((rc = upload(h, &d_sp, sp))) return rc;
+        G.softplus = d_sp;
+    }
     return JGPU_OK;
 }
 
@@ -405,7 +450,7 @@ int build_state(jgpu_handle* h)
     // schedule + score ring + streaming feature staging
     if ((rc = h->alloc(&h->d_sched, (size_t)(h->sched_chunk + 1) * L, false))) return rc;
     if ((rc = h->alloc(&h->d_rows, (size_t)h->sched_chunk * L, false))) return rc;
-    if ((rc = h->alloc(&h->d_scores, (size_t)h->FB * L * d.n_gmms, false))) return rc;
+    if ((rc = h->alloc(&h->d_scores, (size_t)2 * h->FB * L * d.n_gmms, false))) return rc;   // two halves
     if ((rc = h->alloc(&h->d_stream_feats, L * h->stream_chunk * h->dim, false))) return rc;
     if ((rc = h->alloc(&h->d_gmm_out, (size_t)h->gmm_chunk * d.n_gmms, false))) return rc;
     d.scores = h->d_scores;
@@ -416,6 +461,27 @@ int build_state(jgpu_handle* h)
     if ((rc = h->alloc(&d.res_words, h->res_cap * d.max_words))) return rc;
     h->lanes.assign(L, LaneHost());
     return JGPU_OK;
+}
+
+// Pin the static network tables in L2 for the kernels of `st` (persisting hits, streaming misses).
+void apply_l2_window(jgpu_handle* h, cudaStream_t st)
+{
+    if (!h->static_base || !st) return;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+    if (max_persist <= 0 || max_window <= 0) return;
+    const size_t want = std::min<size_t>(h->static_bytes, (size_t)max_persist);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));
+    v.accessPolicyWindow.base_ptr = h->static_base;
+    v.accessPolicyWindow.num_bytes = std::min<size_t>(h->static_bytes, (size_t)max_window);
+    v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)v.accessPolicyWindow.num_bytes);
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+    cudaGetLastError();   // best effort: never fatal
 }
 
 int ensure_results(jgpu_handle* h, size_t n)
@@ -433,25 +499,27 @@ int ensure_results(jgpu_handle* h, size_t n)
     return JGPU_OK;
 }
 
-int launch_gmm(jgpu_handle* h, const float* d_x, const int* d_rows, int n_rows, float* d_out, long long out_base)
+int launch_gmm(jgpu_handle* h, const float* d_x, const int* d_rows, int n_rows, float* d_out, long long out_base,
+               cudaStream_t st = nullptr)
 {
     if (n_rows <= 0) return JGPU_OK;
+    if (!st) st = h->stream;
     const GmmDev& G = h->g;
     dim3 grid((G.n_gmms + G.gpb - 1) / G.gpb, (n_rows + JG_GMM_RT - 1) / JG_GMM_RT);
     const int cstride = JG_GMM_RT * G.gpb + (G.gpb & 31);
     const size_t smem = ((size_t)JG_GMM_RT * h->DP + (size_t)G.C * cstride) * sizeof(float);
-    h->prof_begin(JGPU_K_GMM);
+    h->prof_begin(JGPU_K_GMM, st);
     switch (h->DP) {
 #define GMM_CASE(DPV)                                                                                          \
     case DPV:                                                                                                  \
         CK(cudaFuncSetAttribute(k_gmm_scores<DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        k_gmm_scores<DPV><<<grid, 256, smem, h->stream>>>(G, d_x, d_rows, n_rows, d_out, out_base);            \
+        k_gmm_scores<DPV><<<grid, 256, smem, st>>>(G, d_x, d_rows, n_rows, d_out, out_base);                   \
         break;
         GMM_CASE(16) GMM_CASE(28) GMM_CASE(40) GMM_CASE(52) GMM_CASE(64)
 #undef GMM_CASE
     default: return fail(JGPU_E_ARG, "unsupported padded dim %d", h->DP);
     }
-    h->prof_end();
+    h->prof_end(st);
     ++h->launches;
     CK(cudaGetLastError());
     return JGPU_OK;
@@ -472,7 +540,7 @@ int launch_step(jgpu_handle* h, int rel_step)
     k_seed<<<d.grid_other, JG_THREADS, 0, h->stream>>>(d);
     h->prof_end();
     for (int r = 0; r < d.n_rounds; ++r) {
-        h->prof_begin(JGPU_K_EXPAND);
+        h->prof_begin(r == 0 ? JGPU_K_EXPAND : r == 1 ? JGPU_K_EXPAND_R1 : JGPU_K_EXPAND_R2);
         k_walk<0><<<d.grid_other, JG_THREADS, 0, h->stream>>>(d, r);
         h->prof_end();
         if (h->has_huge) {
@@ -509,17 +577,33 @@ int run_schedule(jgpu_handle* h, const std::vector<int4>& sched, int n_steps, co
         for (int i = 0; i < ns; ++i)
             for (int l = 0; l < L; ++l) {
                 int4& e = chunk[(size_t)i * L + l];
-                e.y = (i % FB) * L + l;                     // score-ring row of (step, lane)
+                e.y = (((i / FB) & 1) * FB + (i % FB)) * L + l;   // score-ring row of (step, lane): two halves
                 rows[(size_t)i * L + l] = ((e.z & 3) == JG_MODE_FRAME) ? e.x : -1;
             }
         CK(cudaMemcpyAsync(h->d_sched, chunk.data(), chunk.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
         if (ns) CK(cudaMemcpyAsync(h->d_rows, rows.data(), (size_t)ns * L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        for (int b0 = 0; b0 < ns; b0 += FB) {
-            const int nb = std::min(FB, ns - b0);
-            int rc = launch_gmm(h, d_x, h->d_rows + (size_t)b0 * L, nb * L, h->d_scores, 0);
+        CK(cudaEventRecord(h->ev_inputs, h->stream));            // features + row table are in place
+        CK(cudaStreamWaitEvent(h->stream_gmm, h->ev_inputs, 0));
+        // acoustic scores of frame block b+1 are computed on the second stream while the search runs block b
+        auto issue_gmm = [&](int b) -> int {
+            const int b0 = b * FB, nb = std::min(FB, ns - b0), half = b & 1;
+            CK(cudaStreamWaitEvent(h->stream_gmm, h->ev_search[half], 0));   // that half of the ring is free again
+            cudaStream_t st = (h->overlap && !h->prof_on) ? h->stream_gmm : h->stream;
+            int rc = launch_gmm(h, d_x, h->d_rows + (size_t)b0 * L, nb * L, h->d_scores, (long long)half * FB * L, st);
             if (rc) return rc;
+            CK(cudaEventRecord(h->ev_gmm[half], st));
+            return JGPU_OK;
+        };
+        const int n_blocks = (ns + FB - 1) / FB;
+        if (n_blocks > 0) { int rc = issue_gmm(0); if (rc) return rc; }
+        for (int b = 0; b < n_blocks; ++b) {
+            int rc;
+            if (b + 1 < n_blocks && (rc = issue_gmm(b + 1))) return rc;
+            CK(cudaStreamWaitEvent(h->stream, h->ev_gmm[b & 1], 0));
+            const int b0 = b * FB, nb = std::min(FB, ns - b0);
             for (int i = b0; i < b0 + nb; ++i)
                 if ((rc = launch_step(h, i))) return rc;
+            CK(cudaEventRecord(h->ev_search[b & 1], h->stream));
         }
         if (last) {
             h->prof_begin(JGPU_K_BOUNDARY);
@@ -672,10 +756,20 @@ int jgpu_create(const JgpuNet* net, const JgpuHmm* hmm, const JgpuGmm* gmm, cons
     jgpu_handle* h = new jgpu_handle;
     h->cfg = *cfg;
     h->device = cfg->device;
+    h->overlap = getenv("JUICER_B200_OVERLAP") && atoi(getenv("JUICER_B200_OVERLAP")) != 0;
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return fail(JGPU_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    e = cudaStreamCreateWithFlags(&h->stream_gmm, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_inputs, cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&h->ev_gmm[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_search[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) { jgpu_destroy(h); return fail(JGPU_E_CUDA, "stream/event setup: %s", cudaGetErrorString(e)); }
     rc = build_tables(h, net, hmm, gmm);
     if (!rc) rc = build_state(h);
+    // measured on B200/c3: pinning the static tables costs more L2 than it saves (177k vs 194k frames/s) -> opt-in
+    if (!rc && getenv("JUICER_B200_L2_WINDOW")) apply_l2_window(h, h->stream);
     if (!rc) {
         e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail(JGPU_E_CUDA, "create sync: %s", cudaGetErrorString(e));
@@ -690,6 +784,12 @@ int jgpu_destroy(jgpu_handle* h)
     if (!h) return JGPU_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream_gmm) { cudaStreamSynchronize(h->stream_gmm); cudaStreamDestroy(h->stream_gmm); }
+    if (h->ev_inputs) cudaEventDestroy(h->ev_inputs);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_gmm[i]) cudaEventDestroy(h->ev_gmm[i]);
+        if (h->ev_search[i]) cudaEventDestroy(h->ev_search[i]);
+    }
     for (void* p : h->allocs) cudaFree(p);
     if (h->d_feats) cudaFree(h->d_feats);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
@@ -848,6 +948,7 @@ int jgpu_set_stream(jgpu_handle* h, void* cuda_stream)
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     h->stream = (cudaStream_t)cuda_stream;
     h->own_stream = false;
+    if (getenv("JUICER_B200_L2_WINDOW")) apply_l2_window(h, h->stream);
     return JGPU_OK;
 }
 
@@ -874,8 +975,9 @@ int jgpu_profile_read(jgpu_handle* h, double* ms, int64_t* count)
 
 const char* jgpu_kernel_name(int32_t kind)
 {
+    // k_expand* = k_walk<0> by round (0, 1, >= 2), k_expand_huge = k_walk_huge<0>, k_commit = k_walk<1> + k_walk_huge<1>
     static const char* names[JGPU_N_KERNELS] = {"k_gmm_scores", "k_boundary", "k_internal", "k_seed", "k_expand",
-                                                "k_expand_huge", "k_commit"};   // expand = k_walk<0>, commit = k_walk<1>
+                                                "k_expand_huge", "k_commit", "k_expand_r1", "k_expand_r2"};
     return (kind >= 0 && kind < JGPU_N_KERNELS) ? names[kind] : "";
 }
 

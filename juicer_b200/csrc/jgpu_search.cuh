@@ -418,10 +418,8 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? 4 : 2)) k_internal(Dev d
                 const int4 h0 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2);
                 const int4 h1 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2 + 1);
                 nst = h0.x & 0xff;
-                const int cls = h0.x >> 8;
+                const int cls = (h0.x & ~JG_LR_CLASS) >> 8;
                 const int gm[6] = {h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                const float* __restrict__ trp = d.trp + (size_t)cls * S * S;
-                const int2* __restrict__ se = d.se + (size_t)cls * S;
                 float4 old[S];
                 old[0] = v.tok_cur[k];
 #pragma unroll
@@ -430,10 +428,34 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? 4 : 2)) k_internal(Dev d
                 old[S - 1] = null_tok();
                 if (old[0].x > JG_LZ && old[0].x < thr_start) old[0] = null_tok();   // :915-918
                 int nlive = 0;
+                const bool lr = S == 5 && (h0.x & JG_LR_CLASS);
+                float lrc[8];
+                const float* __restrict__ trp = d.trp + (size_t)cls * S * S;
+                const int2* __restrict__ se = d.se + (size_t)cls * S;
+                if (lr) {
+                    const float4 c0 = __ldg(d.lr + cls * 2), c1 = __ldg(d.lr + cls * 2 + 1);
+                    lrc[0] = c0.x; lrc[1] = c0.y; lrc[2] = c0.z; lrc[3] = c0.w;
+                    lrc[4] = c1.x; lrc[5] = c1.y; lrc[6] = c1.z; lrc[7] = c1.w;
+                }
 #pragma unroll
                 for (int j = 1; j < S - 1; ++j) {
                     if (j < nst - 1) {
-                        float4 res = viterbi_into<S>(old, trp, __ldg(se + j), j, nst);
+                        float4 res;
+                        if (lr) {
+                            // SEIndex[j] = [j-1, j+1): i = j-1 first, then i = j with strict '>' (:393-406)
+                            const float a = lrc[2 * (j - 1)], b = lrc[2 * (j - 1) + 1];
+                            res = old[j - 1];
+                            res.x = res.x + a;
+                            res.y = res.y + a;
+                            const float tmp = old[j].x + b;
+                            if (tmp > res.x) {
+                                res = old[j];
+                                res.x = tmp;
+                                res.y = res.y + b;
+                            }
+                        } else {
+                            res = viterbi_into<S>(old, trp, __ldg(se + j), j, nst);
+                        }
                         res.x = res.x - norm;                                          // :408
                         if (res.x > thr_emit) {
                             const float o = __ldg(scores + gm[j - 1]);                 // calcOutput :411
@@ -455,7 +477,15 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? 4 : 2)) k_internal(Dev d
                 survive = nlive > 0;
                 // exit state from the NEW emitting tokens (:443-483)
                 {
-                    float4 res = viterbi_into<S>(nt, trp, __ldg(se + (nst - 1)), nst - 1, nst);
+                    float4 res;
+                    if (lr) {                                 // SEIndex[N-1] = [N-2, N-1)
+                        const float a = nst == 5 ? lrc[6] : nst == 4 ? lrc[4] : lrc[2];
+                        res = nst == 5 ? nt[3] : nst == 4 ? nt[2] : nt[1];
+                        res.x = res.x + a;
+                        res.y = res.y + a;
+                    } else {
+                        res = viterbi_into<S>(nt, trp, __ldg(se + (nst - 1)), nst - 1, nst);
+                    }
                     if (res.x > JG_LZ) { ex = res; has_exit = true; ++cnt_end; }
                 }
             }
@@ -655,14 +685,25 @@ __device__ __forceinline__ WalkCtx walk_ctx(const Dev& d, const LaneCtl* c, int 
 }
 
 // PASS 0: expansion round `round`.  PASS 1: commit over the records of all rounds.
+// Per chunk of 256 records: (A) one thread per record decides whether the record still owns its
+// state and does the per-record work (word-boundary record, final-state candidate); (B) the arc
+// rows of all 256 records are walked as ONE flattened list — thread t takes arcs t, t+256, ... and
+// finds the owning record by binary search in the shared prefix of out-degrees — so every lane has
+// an independent arc in flight regardless of how the out-degrees are distributed.
 template <int PASS>
 __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
 {
     __shared__ int sh_pref[JG_MAX_LANES + 1];
+    __shared__ int s_off[JG_THREADS + 1];
+    __shared__ int s_first[JG_THREADS];
+    __shared__ unsigned s_r[JG_THREADS];
+    __shared__ float4 s_tok[JG_THREADS];
+    __shared__ int s_wsum[JG_THREADS / 32];
     int g0, g1;
     balanced_slice(d, PASS == 0 ? JG_CNT_ROUND : JG_CNT_ALL, round, sh_pref, g0, g1);
     if (g0 >= g1) return;
     const int L = d.n_lanes;
+    const int tid = threadIdx.x, wid = tid >> 5;
     for (int lane = first_lane_of(sh_pref, L, g0); lane < L && sh_pref[lane] < g1; ++lane) {
         const int i0 = max(g0, sh_pref[lane]) - sh_pref[lane];
         const int i1 = min(g1, sh_pref[lane + 1]) - sh_pref[lane];
@@ -675,7 +716,8 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
         int arcs_done = 0, n_entry = 0;
         float best = JG_LZ;
         for (int base = i0; base < i1; base += blockDim.x) {
-            const int e = base + threadIdx.x;
+            // ---- (A) one thread per record ----
+            const int e = base + tid;
             bool valid = e < i1;
             int q = 0, first = 0, deg = 0;
             const unsigned r = (unsigned)(rec0 + e);
@@ -710,34 +752,41 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
                     }
                     if (!valid) deg = 0;
                     if (PASS == 0) arcs_done += deg;
+                    if (deg >= d.huge_deg) {                  // hub-like state: left to k_walk_huge
+                        if (PASS == 0) {
+                            const int h = atomicAdd(&c->n_huge[round], 1);
+                            if (h < d.cap_huge) v.huge[(size_t)round * d.cap_huge + h] = make_int2(q, (int)r);
+                            else atomicOr(&c->error, JG_ERR_HUGE);
+                        }
+                        deg = 0;
+                    }
                 }
             }
-            const bool small = valid && deg <= d.small_deg;
-            const bool is_huge = valid && deg >= d.huge_deg;
-            if (small) {
-                for (int b = first; b < first + deg; ++b) process_arc<PASS>(d, v, x, tok, r, b, best, n_entry);
-            } else if (is_huge && PASS == 0) {
-                const int h = atomicAdd(&c->n_huge[round], 1);
-                if (h < d.cap_huge) v.huge[(size_t)round * d.cap_huge + h] = make_int2(q, (int)r);
-                else atomicOr(&c->error, JG_ERR_HUGE);
+            // ---- block-wide exclusive prefix of the out-degrees ----
+            int incl = deg;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane_id() >= o) incl += t;
             }
-            // medium out-degree: the warp walks the arc row together
-            unsigned mm = __ballot_sync(0xffffffffu, valid && !small && !is_huge);
-            while (mm) {
-                const int src = __ffs(mm) - 1;
-                mm &= mm - 1;
-                const int f_s = __shfl_sync(0xffffffffu, first, src);
-                const int n_s = __shfl_sync(0xffffffffu, deg, src);
-                const unsigned r_s = __shfl_sync(0xffffffffu, r, src);
-                float4 t_s;
-                t_s.x = __shfl_sync(0xffffffffu, tok.x, src);
-                t_s.y = __shfl_sync(0xffffffffu, tok.y, src);
-                t_s.z = __shfl_sync(0xffffffffu, tok.z, src);
-                t_s.w = __shfl_sync(0xffffffffu, tok.w, src);
-                for (int b = f_s + lane_id(); b < f_s + n_s; b += 32)
-                    process_arc<PASS>(d, v, x, t_s, r_s, b, best, n_entry);
-                __syncwarp();
+            if (lane_id() == 31) s_wsum[wid] = incl;
+            s_first[tid] = first; s_r[tid] = r; s_tok[tid] = tok;
+            __syncthreads();
+            int woff = 0;
+            for (int w = 0; w < wid; ++w) woff += s_wsum[w];
+            s_off[tid] = woff + incl - deg;
+            if (tid == blockDim.x - 1) s_off[blockDim.x] = woff + incl;
+            __syncthreads();
+            const int total = s_off[blockDim.x];
+            // ---- (B) flattened arc rows ----
+            for (int j = tid; j < total; j += blockDim.x) {
+                int lo = 0, hi = blockDim.x;                  // largest src with s_off[src] <= j
+                while (lo + 1 < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_off[mid] <= j) lo = mid; else hi = mid;
+                }
+                process_arc<PASS>(d, v, x, s_tok[lo], s_r[lo], s_first[lo] + (j - s_off[lo]), best, n_entry);
             }
+            __syncthreads();
         }
         __syncwarp();
         for (int o = 16; o > 0; o >>= 1) {

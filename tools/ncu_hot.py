@@ -1,7 +1,8 @@
-"""Top stall locations of an ncu report (SASS view):  python tools/ncu_hot.py report.ncu-rep [N]"""
+"""Top stall locations of an ncu report:  python tools/ncu_hot.py report.ncu-rep [N] [sass|cuda]"""
 import csv, subprocess, sys
 rep = sys.argv[1]; n = int(sys.argv[2]) if len(sys.argv) > 2 else 25
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+view = sys.argv[3] if len(sys.argv) > 3 else "sass"
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", view], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 blocks, cur = [], None
 for r in rows:
@@ -13,9 +14,11 @@ for r in rows:
         cur["rows"].append(r)
 b = blocks[0]
 h = b["hdr"]; k = h.index("Warp Stall Sampling (All Samples)"); ie = h.index("Instructions Executed")
-tot = sum(float(r[k] or 0) for r in b["rows"])
+src = h.index("Source")
+tot = sum(float(r[k] or 0) for r in b["rows"] if len(r) > k)
 print(b["name"], "total samples", tot)
-idx = sorted(range(len(b["rows"])), key=lambda i: -float(b["rows"][i][k] or 0))[:n]
+rows_ok = [r for r in b["rows"] if len(r) > k]
+idx = sorted(range(len(rows_ok)), key=lambda i: -float(rows_ok[i][k] or 0))[:n]
 for i in sorted(idx):
-    r = b["rows"][i]
-    print(f"{i:4d} {float(r[k]):8.0f} {100*float(r[k])/tot:5.1f}%  exec={r[ie]:>8}  {r[1].strip()}")
+    r = rows_ok[i]
+    print(f"{i:4d} {float(r[k] or 0):8.0f} {100*float(r[k] or 0)/tot:5.1f}%  exec={r[ie]:>9}  {r[src].strip()[:120]}")
