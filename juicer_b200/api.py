@@ -35,10 +35,11 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise JuicerError(f"{LIB_PATH} is missing: run `python -m juicer_b200.build` "
+    path = os.environ.get("JUICER_B200_LIB", LIB_PATH)      # instrumented build of the same sources (tools/)
+    if not os.path.exists(path):
+        raise JuicerError(f"{path} is missing: run `python -m juicer_b200.build` "
                           "(juicer_b200 has no fallback implementation)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     lib.jgpu_last_error.restype = C.c_char_p
     lib.jgpu_version.restype = C.c_char_p

@@ -23,15 +23,21 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """`defines` / `out` build an instrumented variant next to the product library (e.g.
+    defines=("JG_TRACE",), out=libjuicer_b200_trace.so, loaded through JUICER_B200_LIB)."""
+    if out == LIB and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines] + ["-o", out] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--trace" in sys.argv:
+        print(build(force=True, verbose="-v" in sys.argv, defines=("JG_TRACE",),
+                    out=os.path.join(HERE, "libjuicer_b200_trace.so")))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

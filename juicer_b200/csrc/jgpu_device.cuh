@@ -119,6 +119,35 @@ struct Dev {
     float*    fstat_best;      // [n_lanes][max_frames]
 };
 
+// ---- optional CTA timeline (compile with -DJG_TRACE; see tools/trace_report.py) -----------
+#ifdef JG_TRACE
+struct TraceRec { int kid, block, smid, aux; unsigned long long t0, t1; };
+__device__ TraceRec* g_trace;
+__device__ unsigned g_trace_n, g_trace_cap;
+__device__ int g_trace_on;
+struct TraceScope {
+    unsigned long long t0; int kid, aux;
+    __device__ __forceinline__ TraceScope(int k, int a) : kid(k), aux(a)
+    {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    }
+    __device__ __forceinline__ ~TraceScope()
+    {
+        __syncthreads();
+        if (threadIdx.x == 0 && g_trace_on) {
+            unsigned long long t1; unsigned smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const unsigned i = atomicAdd(&g_trace_n, 1u);
+            if (i < g_trace_cap) { TraceRec r; r.kid = kid; r.block = blockIdx.x + blockIdx.y * gridDim.x; r.smid = (int)smid; r.aux = aux; r.t0 = t0; r.t1 = t1; g_trace[i] = r; }
+        }
+    }
+};
+#define JG_TRACE_SCOPE(k, a) TraceScope _trace_scope(k, a)
+#else
+#define JG_TRACE_SCOPE(k, a)
+#endif
+
 // ---- small helpers ----------------------------------------------------------------------
 __device__ __forceinline__ unsigned f2o(float f)
 {

@@ -94,6 +94,13 @@ struct jgpu_handle {
     double prof_ms[JGPU_N_KERNELS] = {0};
     int64_t prof_cnt[JGPU_N_KERNELS] = {0};
 
+#ifdef JG_TRACE
+    TraceRec* d_trace = nullptr;
+    unsigned trace_cap = 0;
+    int trace_s0 = 0, trace_s1 = 0, abs_step = 0;
+    std::string trace_path;
+#endif
+
     void prof_begin(int kind, cudaStream_t st = nullptr)
     {
         if (!prof_on) return;
@@ -529,6 +536,14 @@ int launch_step(jgpu_handle* h, int rel_step)
 {
     const Dev& d = h->d;
     const dim3 grid_huge(h->bpl, d.n_lanes);
+#ifdef JG_TRACE
+    if (h->d_trace) {
+        static const int on = 1, off = 0;
+        if (h->abs_step == h->trace_s0) cudaMemcpyToSymbolAsync(g_trace_on, &on, sizeof(int), 0, cudaMemcpyHostToDevice, h->stream);
+        if (h->abs_step == h->trace_s1) cudaMemcpyToSymbolAsync(g_trace_on, &off, sizeof(int), 0, cudaMemcpyHostToDevice, h->stream);
+        ++h->abs_step;
+    }
+#endif
     h->prof_begin(JGPU_K_BOUNDARY);
     k_boundary<<<d.n_lanes, 32, 0, h->stream>>>(d, rel_step, 1);
     h->prof_end();
@@ -679,9 +694,31 @@ int decode_common(jgpu_handle* h, const float* d_feats, const int64_t* row_offse
     }
     k_reset_batch_stats<<<(L + 127) / 128, 128, 0, h->stream>>>(d);
     ++h->launches;
+#ifdef JG_TRACE
+    if (h->d_trace) {
+        static const unsigned zero = 0;
+        static const int off = 0;
+        h->abs_step = 0;
+        cudaMemcpyToSymbolAsync(g_trace_n, &zero, sizeof(unsigned), 0, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyToSymbolAsync(g_trace_on, &off, sizeof(int), 0, cudaMemcpyHostToDevice, h->stream);
+    }
+#endif
     rc = run_schedule(h, sched, (int)n_steps, d_feats);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
+#ifdef JG_TRACE
+    if (h->d_trace) {
+        unsigned n = 0;
+        cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(unsigned));
+        n = std::min(n, h->trace_cap);
+        std::vector<TraceRec> recs(n);
+        if (n) cudaMemcpy(recs.data(), h->d_trace, (size_t)n * sizeof(TraceRec), cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(h->trace_path.c_str(), "wb")) {
+            fwrite(recs.data(), sizeof(TraceRec), n, f);
+            fclose(f);
+        }
+    }
+#endif
     {
         std::vector<LaneCtl> ctl(L);
         CK(cudaMemcpy(ctl.data(), d.ctl, (size_t)L * sizeof(LaneCtl), cudaMemcpyDeviceToHost));
@@ -768,6 +805,19 @@ int jgpu_create(const JgpuNet* net, const JgpuHmm* hmm, const JgpuGmm* gmm, cons
     if (e != cudaSuccess) { jgpu_destroy(h); return fail(JGPU_E_CUDA, "stream/event setup: %s", cudaGetErrorString(e)); }
     rc = build_tables(h, net, hmm, gmm);
     if (!rc) rc = build_state(h);
+#ifdef JG_TRACE
+    if (!rc && getenv("JUICER_B200_TRACE")) {
+        h->trace_path = getenv("JUICER_B200_TRACE");
+        h->trace_cap = 1u << 21;
+        h->trace_s0 = 400; h->trace_s1 = 408;
+        if (const char* w = getenv("JUICER_B200_TRACE_STEPS")) sscanf(w, "%d:%d", &h->trace_s0, &h->trace_s1);
+        rc = h->alloc(&h->d_trace, (size_t)h->trace_cap);
+        if (!rc) {
+            cudaMemcpyToSymbol(g_trace, &h->d_trace, sizeof(TraceRec*));
+            cudaMemcpyToSymbol(g_trace_cap, &h->trace_cap, sizeof(unsigned));
+        }
+    }
+#endif
     // measured on B200/c3: pinning the static tables costs more L2 than it saves (177k vs 194k frames/s) -> opt-in
     if (!rc && getenv("JUICER_B200_L2_WINDOW")) apply_l2_window(h, h->stream);
     if (!rc) {

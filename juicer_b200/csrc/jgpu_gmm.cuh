@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(256, 2)
 k_gmm_scores(GmmDev g, const float* __restrict__ x, const int* __restrict__ rows, int n_rows,
              float* __restrict__ out, long long out_base)
 {
+    JG_TRACE_SCOPE(JGPU_K_GMM, 0);
     constexpr int RT = JG_GMM_RT;
     constexpr int D = DP;
     extern __shared__ float smem[];

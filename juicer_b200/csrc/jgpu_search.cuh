@@ -378,6 +378,7 @@ __device__ __forceinline__ float4 viterbi_into(const float4 (&src)[S], const flo
 template <int S>
 __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? 4 : 2)) k_internal(Dev d)
 {
+    JG_TRACE_SCOPE(JGPU_K_INTERNAL, 0);
     __shared__ int sh_pref[JG_MAX_LANES + 1];
     __shared__ float sh_best[JG_THREADS / 32];
     __shared__ int sh_cnt[3][JG_THREADS / 32];
@@ -570,6 +571,7 @@ __device__ __forceinline__ void arrive(const Dev& d, const LaneView& v, int q, i
 
 __global__ void __launch_bounds__(JG_THREADS, 6) k_seed(Dev d)
 {
+    JG_TRACE_SCOPE(JGPU_K_SEED, 0);
     __shared__ int sh_pref[JG_MAX_LANES + 1];
     // utterance seeds: propagateToken(&zeroToken, NULL) (:221-226) = an arrival at the initial state
     if (blockIdx.x == 0 && threadIdx.x < 32)
@@ -693,6 +695,7 @@ __device__ __forceinline__ WalkCtx walk_ctx(const Dev& d, const LaneCtl* c, int 
 template <int PASS>
 __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
 {
+    JG_TRACE_SCOPE(PASS ? JGPU_K_COMMIT : JGPU_K_EXPAND, round);
     __shared__ int sh_pref[JG_MAX_LANES + 1];
     __shared__ int s_off[JG_THREADS + 1];
     __shared__ int s_first[JG_THREADS];
@@ -807,6 +810,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
 template <int PASS>
 __global__ void __launch_bounds__(JG_THREADS) k_walk_huge(Dev d, int round)
 {
+    JG_TRACE_SCOPE(JGPU_K_EXPAND_HUGE, round + 100 * PASS);
     const int lane = blockIdx.y;
     LaneCtl* c = d.ctl + lane;
     if (c->mode == JG_MODE_IDLE) return;
