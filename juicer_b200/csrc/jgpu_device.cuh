@@ -8,17 +8,25 @@
 //   Histogram                               src/Histogram.cpp:64-158
 //
 // Layout in HBM (one decoder handle, L lanes = utterances decoded in lock-step):
-//   static, shared by all lanes : arcs int4{to,w,in,out} | states int2{first,n} | final f32
+//   static, shared by all lanes : arcs int4{to | MULTI, w, in, out}, every state's row ordered
+//                                 [epsilon arcs][tee-model arcs][other model arcs]
+//                                 | states int4{first, n arcs, final weight, n_eps | n_tee << 16}
 //                                 | hmm_info 8 x i32 per HMM | trP/SE per transition-matrix class
 //                                 | GMM parameters transposed [d][comp][gmm]
-//   per lane, double buffered   : active-instance list  inst_meta[2][cap] int2{arc, hmm | FRESH}
+//   per lane, double buffered   : active-instance list  inst_meta[2][cap] int4{arc, hmm | FRESH, to | MULTI, out label}
 //                                 token planes          tok[2][S-1][cap] float4{score,ac,lm,path}
-//   per lane, dense             : arcdyn[nArcs] 16 B {u64 entry key, u32 slot, u32 stamp}
-//                                   key  : atomicMax recombination of entry tokens, zeroed by k_commit
-//                                   slot : the GPU form of WFSTTransition::hook, valid iff stamp == epoch
-//                                 state_key[nStates] u64 (per-state max of arriving tokens, self-cleaning)
-//   per lane, per frame scratch : exit list, arrival records (32 B, stored round after round)
+//   per lane, dense             : slotmap[nArcs] u32 = epoch stamp << 20 | list position + 1 — the GPU form of
+//                                   WFSTTransition::hook, valid iff the stamp is the current epoch
+//                                 state_key[nStates] u64 (per-state max of arriving tokens, self-cleaning;
+//                                   only touched for states that can see more than one arrival per frame)
+//   per lane, per frame scratch : arrival records (32 B, stored round after round)
 //   per lane, per utterance     : word-boundary arena paths[cap_paths] (32 B records)
+//
+// Cost model behind the layout (measured on B200, tools/ubench/randmem.cu): random 32 B-sector
+// accesses to DRAM saturate at ~36 G/s (1.15 TB/s) and 64-bit atomics at ~20 G/s whatever the
+// footprint, L2-resident random accesses run at ~270 G/s, coalesced streams at ~200 G sectors/s.
+// So the search path keeps random tables small (4 B per arc), touches them row-contiguously, and
+// streams everything else with evict-first hints so that the tables stay in the 126 MB L2.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -48,27 +56,26 @@ struct ResHdr {           // 32 B per utterance
     int   error, pad1, pad2;
 };
 
-struct ArcDyn {           // 16 B per arc and lane
-    u64      key;         // (orderable score << 32) | arrival record of the best entry candidate, 0 = none
-    unsigned slot;        // slot + 1 of the arc's instance in the list being built
-    unsigned stamp;       // epoch in which `slot` was written
-};
-
 struct Arrival {          // 32 B: one sector
     float4 tok;
     int    via;           // arc through which the token arrived, -1 = utterance seed, -2 = dropped
-    int    q;             // state reached
-    int    pad[2];
+    int    q;             // state reached | JG_MULTI
+    int    olab;          // output label of `via` (word-boundary record needed when != 0)
+    int    pad;
 };
+
+#define JG_MULTI 0x80000000u      // arcs.x / Arrival.q / inst_meta.z flag: the destination state can receive more
+                                  // than one arrival per frame, so arrivals are max-reduced through state_key
+#define JG_SLOT_BITS 20           // slotmap entry = (epoch & 0x7ff) << 20 | position + 1
+#define JG_SLOT_MASK 0xfffffu
 
 #define JG_LR_CLASS 0x40000000   // hmm_info[0] flag: plain left-to-right topology (no skips), nStates <= 5
 #define JG_FRESH 0x40000000   // inst_meta.y flag: only the entry token of this instance is valid
 
 struct LaneCtl {
-    int n_cur, n_next, n_exit, n_clean, n_paths, flip;
+    int n_cur, n_next, n_huge, n_paths, flip;
     unsigned epoch;           // advances every non-idle step of this lane, never repeats
     int n_arr[JG_MAX_ROUNDS + 2];    // arrivals feeding expansion round k (records are stored back to back)
-    int n_huge[JG_MAX_ROUNDS + 1];   // hub-like states met in round k
     unsigned best_int;        // orderable max of emitting scores of this frame   (WFSTDecoderLite.cpp:417-418)
     unsigned best_ext;        // orderable max of entry scores of this frame      (:572-573)
     u64      best_final;      // key of the best arrival at a final state          (:513-520)
@@ -86,29 +93,29 @@ struct LaneCtl {
 struct Dev {
     // static tables
     const int4*  arcs;
-    const int4*  states;       // {first arc, n arcs, final weight bits, 0}
+    const int4*  states;       // {first arc, n arcs, final weight bits, n_eps | n_tee << 16}
     const float* arc_tee;      // per-arc tee weight of the arc's HMM, nullptr when no tee model exists
     const int*   hmm_info;     // [n_hmms][8] : nst | class<<8, tee bits, gmm of states 1..6
     const float* trp;          // [n_class][S*S]
     const int2*  se;           // [n_class][S]
     const float4* lr;          // [n_class][2]: left-to-right classes {a01,a11,a12,a22 | a23,a33,a34,-}
     int n_arcs, n_states, init_state, n_hmms, n_gmms, S;
+    unsigned init_multi;       // JG_MULTI when the initial state can receive more than one arrival per frame
     // settings
     float start_beam, main_beam, end_beam, word_beam;
     int max_hyps, hist_min, hist_max, hist_nbins;
     int n_lanes, cap, cap_arr, cap_paths, cap_huge, n_rounds, max_frames, frame_stats, max_words;
-    int small_deg, huge_deg;
-    int grid_internal, grid_other;   // CTAs of the lane-balanced kernels
+    int huge_deg;
+    int fuse_exits;                  // no end / word beam: exit tokens become arrivals inside k_internal
+    int grid_internal, grid_other;   // CTAs of the chunk-scheduled kernels
     // per-lane state
     LaneCtl*  ctl;
-    int2*     inst_meta;
+    int4*     inst_meta;
     float4*   tok;
-    ArcDyn*   arcdyn;
+    unsigned* slotmap;
     u64*      state_key;
-    int*      exit_arc;
-    float4*   exit_tok;
     Arrival*  arr;
-    int2*     huge;            // [n_lanes][JG_MAX_ROUNDS + 1][cap_huge] {state, arrival record}
+    int2*     huge;            // [n_lanes][cap_huge] {state, arrival record} of hub-like rows met by k_commit
     PathRec*  paths;
     int*      hist;
     const float* scores;       // [ring rows][n_gmms]

@@ -17,6 +17,7 @@
 #include "jgpu_device.cuh"
 #include "jgpu_err.h"
 #include "jgpu_gmm.cuh"
+#define JG_HUGE_DEG 1024   // rows with at least this many model arcs are walked by all CTAs of the lane
 #include "jgpu_search.cuh"
 
 namespace {
@@ -58,7 +59,8 @@ struct jgpu_handle {
     int FB = 16;            // frames per GMM scoring block
     int bpl = 8;            // CTAs per lane for the search kernels
     bool has_huge = false;
-    int max_deg = 0;
+    int max_deg = 0, n_huge_states = 0;
+    std::vector<unsigned> host_epoch;    // mirror of LaneCtl::epoch (advances on every non-idle step of the lane)
     cudaStream_t stream = nullptr;       // search kernels, copies
     cudaStream_t stream_gmm = nullptr;   // acoustic scoring of the NEXT frame block overlaps the search
     cudaEvent_t ev_inputs = nullptr, ev_gmm[2] = {nullptr, nullptr}, ev_search[2] = {nullptr, nullptr};
@@ -176,7 +178,7 @@ int upload(jgpu_handle* h, T** dst, const std::vector<T>& src)
 }
 
 // longest chain of pass-through arcs (epsilon input or tee model); -1 on a cycle.
-int passthrough_depth(const JgpuNet* n, const std::vector<char>& pass)
+int passthrough_depth(const JgpuNet* n, const std::vector<char>& pass, std::vector<int>* topo = nullptr)
 {
     const int S = n->n_states;
     std::vector<int> indeg(S, 0), depth(S, 0);
@@ -200,6 +202,7 @@ int passthrough_depth(const JgpuNet* n, const std::vector<char>& pass)
         }
     }
     if ((int)q.size() != S) return -1;
+    if (topo) *topo = q;
     return best;
 }
 
@@ -246,35 +249,66 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
     d.S = S;
     d.n_arcs = A; d.n_states = NS; d.init_state = n->init_state; d.n_hmms = H; d.n_gmms = g->n_gmms;
 
-    // network
-    std::vector<int4> arcs(A);
-    for (int a = 0; a < A; ++a) {
-        int wbits;
-        memcpy(&wbits, &n->arc_weight[a], 4);
-        arcs[a] = make_int4(n->arc_to[a], wbits, n->arc_in[a], n->arc_out[a]);
-    }
-    std::vector<int4> states(NS);
-    int max_deg = 0;
-    for (int s = 0; s < NS; ++s) {
-        int fbits;
-        memcpy(&fbits, &n->state_final[s], 4);
-        states[s] = make_int4(n->state_first[s], n->state_narcs[s], fbits, 0);
-        max_deg = std::max(max_deg, n->state_narcs[s]);
-    }
-    h->max_deg = max_deg;
+    // network.  pass-through arcs = epsilon input (:533-540) or tee model (:584-600)
     bool any_tee = false;
     for (int i = 0; i < H; ++i) any_tee |= m->tee[i] > JG_LZ;
     std::vector<char> pass(A);
-    std::vector<float> arc_tee(A, JG_LZ);
+    std::vector<float> tee_in(A, JG_LZ);                 // in the caller's arc order
     for (int a = 0; a < A; ++a) {
         const int in = n->arc_in[a];
-        if (in > 0) arc_tee[a] = m->tee[in - 1];
-        pass[a] = (in == 0) || (arc_tee[a] > JG_LZ);
+        if (in > 0) tee_in[a] = m->tee[in - 1];
+        pass[a] = (in == 0) || (tee_in[a] > JG_LZ);
     }
-    const int depth = passthrough_depth(n, pass);
+    std::vector<int> topo;
+    const int depth = passthrough_depth(n, pass, &topo);
     if (depth < 0) return fail(JGPU_E_ARG, "network has a cycle of epsilon/tee arcs (the reference would recurse forever)");
     if (depth + 1 > JG_MAX_ROUNDS) return fail(JGPU_E_ARG, "epsilon/tee chains of depth %d exceed %d rounds", depth, JG_MAX_ROUNDS);
     d.n_rounds = depth + 1;
+    // Which states can receive MORE THAN ONE arrival in a frame?  An arc delivers at most one token per frame
+    // (one instance per arc; a tee model's arc delivers its exit token and its pass-through token), unless it is
+    // a pass-through arc out of a state that is itself expanded more than once.  Only those states need the
+    // per-state max-reduction of arrivals; all others are expanded by their single arrival.
+    std::vector<int> n_in(NS, 0);
+    n_in[n->init_state] += 1;                            // the utterance seed (recognitionStart :221-226)
+    for (int a = 0; a < A; ++a) n_in[n->arc_to[a]] += (n->arc_in[a] > 0 && tee_in[a] > JG_LZ) ? 2 : 1;
+    std::vector<char> multi(NS, 0);
+    for (int s = 0; s < NS; ++s) multi[s] = n_in[s] > 1;
+    for (int s : topo)                                   // topological order of the pass-through sub-graph
+        if (multi[s])
+            for (int b = n->state_first[s]; b < n->state_first[s] + n->state_narcs[s]; ++b)
+                if (pass[b]) multi[n->arc_to[b]] = 1;
+    d.init_multi = multi[n->init_state] ? JG_MULTI : 0u;
+    // every row is re-ordered [epsilon | tee-model | other model arcs] (stable), so that the expansion rounds
+    // walk a prefix of the row and the commit walks the rest; arc ids are internal to the engine.
+    std::vector<int4> arcs(A);
+    std::vector<float> arc_tee(A, JG_LZ);
+    std::vector<int4> states(NS);
+    int max_deg = 0, n_huge_states = 0;
+    for (int s = 0; s < NS; ++s) {
+        const int f = n->state_first[s], k = n->state_narcs[s];
+        int pos = f, n_eps = 0, n_tee = 0;
+        for (int cls = 0; cls < 3; ++cls)
+            for (int b = f; b < f + k; ++b) {
+                const int in = n->arc_in[b];
+                const int c_b = in == 0 ? 0 : (tee_in[b] > JG_LZ ? 1 : 2);
+                if (c_b != cls) continue;
+                int wbits;
+                memcpy(&wbits, &n->arc_weight[b], 4);
+                arcs[pos] = make_int4(n->arc_to[b] | (multi[n->arc_to[b]] ? (int)JG_MULTI : 0), wbits, in, n->arc_out[b]);
+                arc_tee[pos] = tee_in[b];
+                ++pos;
+                n_eps += cls == 0; n_tee += cls == 1;
+            }
+        if (n_eps > 0xffff || n_tee > 0xffff)
+            return fail(JGPU_E_ARG, "state %d has %d epsilon / %d tee out-arcs (limit 65535 each)", s, n_eps, n_tee);
+        int fbits;
+        memcpy(&fbits, &n->state_final[s], 4);
+        states[s] = make_int4(f, k, fbits, n_eps | (n_tee << 16));
+        max_deg = std::max(max_deg, k - n_eps);
+        n_huge_states += (k - n_eps) >= JG_HUGE_DEG;
+    }
+    h->max_deg = max_deg;
+    h->n_huge_states = n_huge_states;
 
     // HMM classes: deduplicate (nst, trP, SEIndex)
     std::map<std::string, int> cls_of;
@@ -404,17 +438,17 @@ int build_state(jgpu_handle* h)
     d.n_lanes = c.n_lanes;
     d.cap = c.max_active > 0 ? c.max_active : std::min(d.n_arcs + 1, 1 << 18);
     d.cap = std::max(d.cap, 64);
-    d.cap = std::min(d.cap, 1000000);                    // arrival records are addressed with 21 bits
+    d.cap = std::min(d.cap, 1000000);                    // arrival records: 21 bits, slotmap positions: 20 bits
     d.cap_arr = 2 * d.cap + 1024;
     d.cap_paths = c.max_paths > 0 ? c.max_paths : (1 << 21);   // re-sized from free memory below when 0
-    d.cap_huge = 256;
+    d.cap_huge = std::max(h->n_huge_states, 1);          // a state is committed at most once per frame
     d.max_frames = c.max_frames > 0 ? c.max_frames : 4096;
     d.frame_stats = c.frame_stats;
     d.max_words = 256;
-    d.small_deg = 4;
-    d.huge_deg = 1024;
-    h->has_huge = h->max_deg >= d.huge_deg;
-    h->bpl = std::max(2, std::min(64, (1184 + c.n_lanes - 1) / c.n_lanes));   // k_expand_huge only
+    d.huge_deg = JG_HUGE_DEG;
+    d.fuse_exits = !(c.end_beam > 0.0f) && !(c.word_beam > 0.0f);
+    h->has_huge = h->n_huge_states > 0;
+    h->bpl = std::max(2, std::min(64, (1184 + c.n_lanes - 1) / c.n_lanes));   // k_commit_huge only
     {
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
@@ -423,7 +457,7 @@ int build_state(jgpu_handle* h)
     }
 
     const size_t cap = d.cap, P = d.S - 1;
-    size_t need = L * (2 * cap * 8 + 2 * P * cap * 16 + (size_t)d.n_arcs * 16 + (size_t)d.n_states * 8 + cap * 20 +
+    size_t need = L * (2 * cap * 16 + 2 * P * cap * 16 + (size_t)d.n_arcs * 4 + (size_t)d.n_states * 8 +
                        (size_t)d.cap_arr * 32 + (size_t)d.cap_paths * 32);
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
@@ -444,12 +478,10 @@ int build_state(jgpu_handle* h)
     if ((rc = h->alloc(&d.ctl, L))) return rc;
     if ((rc = h->alloc(&d.inst_meta, L * 2 * cap, false))) return rc;
     if ((rc = h->alloc(&d.tok, L * 2 * P * cap, false))) return rc;
-    if ((rc = h->alloc(&d.arcdyn, L * d.n_arcs))) return rc;
+    if ((rc = h->alloc(&d.slotmap, L * d.n_arcs))) return rc;
     if ((rc = h->alloc(&d.state_key, L * d.n_states))) return rc;
-    if ((rc = h->alloc(&d.exit_arc, L * cap, false))) return rc;
-    if ((rc = h->alloc(&d.exit_tok, L * cap, false))) return rc;
     if ((rc = h->alloc(&d.arr, L * d.cap_arr, false))) return rc;
-    if ((rc = h->alloc(&d.huge, L * (JG_MAX_ROUNDS + 1) * d.cap_huge, false))) return rc;
+    if ((rc = h->alloc(&d.huge, L * d.cap_huge, false))) return rc;
     if ((rc = h->alloc(&d.paths, L * d.cap_paths, false))) return rc;
     if ((rc = h->alloc(&d.hist, L * d.hist_nbins))) return rc;
     if ((rc = h->alloc(&d.fstat_cnt, d.frame_stats ? L * d.max_frames * 4 : 1))) return rc;
@@ -467,6 +499,7 @@ int build_state(jgpu_handle* h)
     if ((rc = h->alloc(&d.res_hdr, h->res_cap))) return rc;
     if ((rc = h->alloc(&d.res_words, h->res_cap * d.max_words))) return rc;
     h->lanes.assign(L, LaneHost());
+    h->host_epoch.assign(L, 0u);
     return JGPU_OK;
 }
 
@@ -548,28 +581,35 @@ int launch_step(jgpu_handle* h, int rel_step)
     k_boundary<<<d.n_lanes, 32, 0, h->stream>>>(d, rel_step, 1);
     h->prof_end();
     h->prof_begin(JGPU_K_INTERNAL);
-    if (h->S == 5) k_internal<5><<<d.grid_internal, JG_THREADS, 0, h->stream>>>(d);
-    else k_internal<8><<<d.grid_internal, JG_THREADS, 0, h->stream>>>(d);
+    if (h->S == 5) {
+        if (d.fuse_exits) k_internal<5, true><<<d.grid_internal, JG_THREADS, 0, h->stream>>>(d);
+        else k_internal<5, false><<<d.grid_internal, JG_THREADS, 0, h->stream>>>(d);
+    } else {
+        if (d.fuse_exits) k_internal<8, true><<<d.grid_internal, JG_THREADS, 0, h->stream>>>(d);
+        else k_internal<8, false><<<d.grid_internal, JG_THREADS, 0, h->stream>>>(d);
+    }
     h->prof_end();
-    h->prof_begin(JGPU_K_SEED);
-    k_seed<<<d.grid_other, JG_THREADS, 0, h->stream>>>(d);
-    h->prof_end();
+    if (!d.fuse_exits) {
+        h->prof_begin(JGPU_K_SEED);
+        k_filter<<<d.grid_other, JG_THREADS, 0, h->stream>>>(d);
+        h->prof_end();
+        ++h->launches;
+    }
     for (int r = 0; r < d.n_rounds; ++r) {
         h->prof_begin(r == 0 ? JGPU_K_EXPAND : r == 1 ? JGPU_K_EXPAND_R1 : JGPU_K_EXPAND_R2);
         k_walk<0><<<d.grid_other, JG_THREADS, 0, h->stream>>>(d, r);
         h->prof_end();
-        if (h->has_huge) {
-            h->prof_begin(JGPU_K_EXPAND_HUGE);
-            k_walk_huge<0><<<grid_huge, JG_THREADS, 0, h->stream>>>(d, r);
-            h->prof_end();
-            ++h->launches;
-        }
     }
     h->prof_begin(JGPU_K_COMMIT);
     k_walk<1><<<d.grid_other, JG_THREADS, 0, h->stream>>>(d, 0);
-    if (h->has_huge) { k_walk_huge<1><<<grid_huge, JG_THREADS, 0, h->stream>>>(d, 0); ++h->launches; }
     h->prof_end();
-    h->launches += 4 + d.n_rounds;
+    if (h->has_huge) {
+        h->prof_begin(JGPU_K_EXPAND_HUGE);
+        k_commit_huge<<<grid_huge, JG_THREADS, 0, h->stream>>>(d);
+        h->prof_end();
+        ++h->launches;
+    }
+    h->launches += 3 + d.n_rounds;
     CK(cudaGetLastError());
     return JGPU_OK;
 }
@@ -616,8 +656,17 @@ int run_schedule(jgpu_handle* h, const std::vector<int4>& sched, int n_steps, co
             if (b + 1 < n_blocks && (rc = issue_gmm(b + 1))) return rc;
             CK(cudaStreamWaitEvent(h->stream, h->ev_gmm[b & 1], 0));
             const int b0 = b * FB, nb = std::min(FB, ns - b0);
-            for (int i = b0; i < b0 + nb; ++i)
+            for (int i = b0; i < b0 + nb; ++i) {
+                // a lane's 11-bit epoch stamp is about to wrap: wipe its stamped tables (once per 2048 steps)
+                for (int l = 0; l < L; ++l) {
+                    if ((chunk[(size_t)i * L + l].z & 3) == JG_MODE_IDLE) continue;
+                    if (((++h->host_epoch[l]) & 0x7ffu) == 0u) {
+                        CK(cudaMemsetAsync(h->d.state_key + (size_t)l * d.n_states, 0, (size_t)d.n_states * sizeof(u64), h->stream));
+                        CK(cudaMemsetAsync(h->d.slotmap + (size_t)l * d.n_arcs, 0, (size_t)d.n_arcs * sizeof(unsigned), h->stream));
+                    }
+                }
                 if ((rc = launch_step(h, i))) return rc;
+            }
             CK(cudaEventRecord(h->ev_search[b & 1], h->stream));
         }
         if (last) {

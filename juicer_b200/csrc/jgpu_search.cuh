@@ -1,32 +1,33 @@
 // jgpu_search.cuh — the per-frame token-passing kernels (sm_100a).
 //
 // One frame step of every lane is the launch sequence
-//   k_boundary -> k_internal -> k_seed -> { k_walk<0> [-> k_walk_huge<0>] } x n_rounds
-//              -> k_walk<1> [-> k_walk_huge<1>]
+//   k_boundary -> k_internal [-> k_filter] -> k_walk<0> x n_rounds -> k_walk<1> [-> k_commit_huge]
 // which restates WFSTDecoderLite::processFrame (src/WFSTDecoderLite.cpp:311-372) as
 // data-parallel passes.  All float arithmetic on scores is plain fp32 add/sub in the
 // reference's per-token order (compiled with -fmad=false; there are no multiplies), so
 // every token carries bit-identical scores to the CPU decoder.
 //
-// Work distribution: the per-lane work lists (active instances, exit tokens, frontier,
-// commit list) have very different lengths (a lane whose hub state was just expanded holds
-// 20k fresh instances, its neighbour 2k), so every kernel runs a fixed grid (a multiple of
-// the 148 SMs) and each CTA takes an equal, contiguous slice of the CONCATENATION of all
-// lanes' lists (prefix of the per-lane counts in shared memory).
+// Work distribution: the per-lane work lists (active instances, arrival records) have very
+// different lengths, and the work per item is uneven (a fresh instance reads one token, a
+// word-end record walks 44 arcs).  Every kernel therefore runs a fixed grid (a multiple of the
+// 148 SMs) over CHUNKS of 256 items of one lane; chunk c of the concatenation of all lanes'
+// chunk lists goes to CTA c mod grid, so neighbouring chunks — similar work — spread over CTAs.
+// The per-lane parameters a chunk needs (thresholds, epoch, list bases) are read once per CTA
+// into shared memory: no dependent global load sits in front of a chunk.
 #pragma once
 
 #include "jgpu_device.cuh"
 
-#define JG_MAX_LANES 1024
+#define JG_MAX_LANES 512
+#define JG_CH JG_THREADS          // items per chunk
 
 // Per-lane views -------------------------------------------------------------------------
 struct LaneView {
     LaneCtl* c;
-    int2* meta_cur; int2* meta_nxt;
+    int4* meta_cur; int4* meta_nxt;
     float4* tok_cur; float4* tok_nxt;
-    ArcDyn* ad;
+    unsigned* slotmap;
     u64* skey;
-    int* exit_arc; float4* exit_tok;
     Arrival* arr;
     int2* huge;
     PathRec* paths;
@@ -43,19 +44,17 @@ __device__ __forceinline__ LaneView lane_view(const Dev& d, int lane)
     v.meta_nxt = d.inst_meta + ((size_t)lane * 2 + (flip ^ 1)) * cap;
     v.tok_cur = d.tok + ((size_t)lane * 2 + flip) * P * cap;
     v.tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * P * cap;
-    v.ad = d.arcdyn + (size_t)lane * d.n_arcs;
+    v.slotmap = d.slotmap + (size_t)lane * d.n_arcs;
     v.skey = d.state_key + (size_t)lane * d.n_states;
-    v.exit_arc = d.exit_arc + (size_t)lane * cap;
-    v.exit_tok = d.exit_tok + (size_t)lane * cap;
     v.arr = d.arr + (size_t)lane * d.cap_arr;
-    v.huge = d.huge + (size_t)lane * (JG_MAX_ROUNDS + 1) * d.cap_huge;
+    v.huge = d.huge + (size_t)lane * d.cap_huge;
     v.paths = d.paths + (size_t)lane * d.cap_paths;
     v.hist = d.hist + (size_t)lane * d.hist_nbins;
     return v;
 }
 
 // aggregated counter bump: the threads of the warp that are here together share one
-// atomicAdd.  All of them must target the SAME counter (one lane per CTA segment).
+// atomicAdd.  All of them must target the SAME counter (one lane per chunk).
 __device__ __forceinline__ int agg_inc(int* counter)
 {
     const unsigned peers = __activemask();
@@ -66,8 +65,11 @@ __device__ __forceinline__ int agg_inc(int* counter)
     return base + __popc(peers & ((1u << lane_id()) - 1u));
 }
 
-// ---- lane-balanced slicing ---------------------------------------------------------------
-enum { JG_CNT_CUR = 0, JG_CNT_EXIT, JG_CNT_ROUND, JG_CNT_ALL };
+// streaming (evict-first) accessors for data that is written once and read once per step
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ int4 ld_stream(const int4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(int4* p, int4 v) { __stcs(p, v); }
 
 // first arrival record of expansion round k (arrivals of earlier rounds are final by then)
 __device__ __forceinline__ int arr_base(const LaneCtl* c, int round)
@@ -77,60 +79,65 @@ __device__ __forceinline__ int arr_base(const LaneCtl* c, int round)
     return b;
 }
 
-__device__ __forceinline__ int lane_count(const Dev& d, int lane, int which, int round)
-{
-    const LaneCtl* c = d.ctl + lane;
-    const int mode = c->mode;
-    if (mode == JG_MODE_IDLE) return 0;
-    switch (which) {
-    case JG_CNT_CUR: return mode == JG_MODE_FRAME ? c->n_cur : 0;
-    case JG_CNT_EXIT: return mode == JG_MODE_FRAME ? c->n_exit : 0;
-    case JG_CNT_ROUND: {
-        const int b = arr_base(c, round);
-        return max(0, min(c->n_arr[round], d.cap_arr - b));
-    }
-    default: return min(arr_base(c, d.n_rounds + 1), d.cap_arr);
-    }
-}
+// ---- chunk scheduling --------------------------------------------------------------------
+struct LaneSh {                   // per-CTA shared copy of what a chunk needs to know about its lane
+    int pref[JG_MAX_LANES + 1];   // exclusive prefix of the per-lane chunk counts
+    int cnt[JG_MAX_LANES];        // items in the lane's list
+    unsigned epoch[JG_MAX_LANES];
+    float f0[JG_MAX_LANES], f1[JG_MAX_LANES], f2[JG_MAX_LANES];   // kernel-specific
+    int i0[JG_MAX_LANES], i1[JG_MAX_LANES], i2[JG_MAX_LANES];
+};
 
-// sh_pref[0..L] = exclusive prefix of the lane counts; returns this CTA's global slice [g0, g1)
-__device__ __forceinline__ void balanced_slice(const Dev& d, int which, int round, int* sh_pref, int& g0, int& g1)
+// sh.cnt[] must be filled (and __syncthreads() NOT yet called); returns the number of chunks
+__device__ __forceinline__ int chunk_scan(LaneSh& sh, int L)
 {
-    const int L = d.n_lanes;
-    for (int l = threadIdx.x; l < L; l += blockDim.x) sh_pref[l + 1] = lane_count(d, l, which, round);
-    if (threadIdx.x == 0) sh_pref[0] = 0;
     __syncthreads();
     if (threadIdx.x < 32) {                                  // warp 0: scan L values, L/32 per thread
         const int per = (L + 31) / 32;
         const int b = threadIdx.x * per;
         int sum = 0;
         for (int i = 0; i < per; ++i)
-            if (b + i < L) sum += sh_pref[b + i + 1];
+            if (b + i < L) sum += (sh.cnt[b + i] + JG_CH - 1) / JG_CH;
         int incl = sum;
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, o);
             if ((int)threadIdx.x >= o) incl += t;
         }
         int run = incl - sum;
+        if (threadIdx.x == 0) sh.pref[0] = 0;
         for (int i = 0; i < per; ++i)
-            if (b + i < L) { run += sh_pref[b + i + 1]; sh_pref[b + i + 1] = run; }
+            if (b + i < L) { run += (sh.cnt[b + i] + JG_CH - 1) / JG_CH; sh.pref[b + i + 1] = run; }
     }
     __syncthreads();
-    const int total = sh_pref[L];
-    int per = (total + gridDim.x - 1) / gridDim.x;
-    per = (per + 31) & ~31;
-    g0 = min(blockIdx.x * per, total);
-    g1 = min(g0 + per, total);
+    return sh.pref[L];
 }
 
-__device__ __forceinline__ int first_lane_of(const int* sh_pref, int L, int g)
+__device__ __forceinline__ int lane_of_chunk(const int* pref, int L, int c)
 {
-    int lo = 0, hi = L;                                      // largest l with sh_pref[l] <= g
+    int lo = 0, hi = L;                                      // largest l with pref[l] <= c
     while (lo + 1 < hi) {
         const int mid = (lo + hi) >> 1;
-        if (sh_pref[mid] <= g) lo = mid; else hi = mid;
+        if (pref[mid] <= c) lo = mid; else hi = mid;
     }
     return lo;
+}
+
+__device__ __forceinline__ u64 warp_max_u64(u64 v)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        const u64 t = __shfl_xor_sync(0xffffffffu, v, o);
+        if (t > v) v = t;
+    }
+    return v;
+}
+
+// state key = epoch (11 bits) | orderable score (32 bits) | arrival record (21 bits): keys of older
+// steps always lose the atomicMax and never compare equal, so state_key needs no per-frame cleaning
+// (the host wipes a lane's table when its 11-bit epoch wraps, once every 2048 steps).
+#define JG_R_BITS 21
+__device__ __forceinline__ u64 state_key_of(unsigned epoch, float score, unsigned r)
+{
+    return ((u64)(epoch & 0x7ffu) << 53) | ((u64)f2o(score) << JG_R_BITS) | (u64)r;
 }
 
 // =========================================================================================
@@ -246,7 +253,7 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d, int step, int open)
         if (key) {
             const Arrival a = v.arr[(unsigned)key];
             float4 t = a.tok;
-            const float fw = __int_as_float(d.states[a.q].z);
+            const float fw = __int_as_float(d.states[a.q & 0x7fffffff].z);
             t.x += fw;                                        // :517-518
             t.z += fw;
             c->final_tok = t;
@@ -281,10 +288,7 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d, int step, int open)
     __syncwarp();
 
     // ---- (B) open this step -------------------------------------------------------------
-    if (mode != JG_MODE_IDLE && ((c->epoch + 1u) & 0x7ffu) == 0u) {      // 11-bit epoch of the state keys wraps
-        for (int i = l; i < d.n_states; i += 32) v.skey[i] = 0;
-    }
-    __syncwarp();
+    // (the host wipes a lane's state_key / slotmap tables when its 11-bit epoch stamp wraps, run_schedule)
     float thr_emit = JG_LZ;
     if (mode == JG_MODE_FRAME && d.max_hyps > 0) {
         thr_emit = hist_thresh_warp(d, v);                   // whole warp
@@ -296,9 +300,8 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d, int step, int open)
             c->flip ^= 1;
             c->n_cur = min(c->n_next, d.cap);
         }
-        c->n_next = 0; c->n_exit = 0;
-        for (int i = 0; i <= JG_MAX_ROUNDS; ++i) { c->n_arr[i] = 0; c->n_huge[i] = 0; }
-        c->n_arr[JG_MAX_ROUNDS + 1] = 0;
+        c->n_next = 0; c->n_huge = 0;
+        for (int i = 0; i <= JG_MAX_ROUNDS + 1; ++i) c->n_arr[i] = 0;
         c->best_final = 0;
         c->c_active_emit = c->c_active_end = c->c_end_proc = c->c_arcs = c->c_entry = 0;
         c->mode = mode;
@@ -316,6 +319,14 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d, int step, int open)
             c->final_valid = 0;
             c->s_active_models = c->s_active_emit = c->s_active_end = c->s_proc_emit = c->s_proc_end = 0;
             c->s_arcs = c->s_entry = c->s_paths = c->s_frames = c->s_gmm = 0;
+            // propagateToken(&zeroToken, NULL) (:221-226) = an arrival at the initial state, walked by the
+            // expansion rounds of this step with every threshold at LOG_ZERO
+            Arrival a;
+            a.tok = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
+            a.via = -1; a.q = d.init_state | (int)d.init_multi; a.olab = 0; a.pad = 0;
+            v.arr[0] = a;
+            c->n_arr[0] = 1;
+            if (d.init_multi) v.skey[d.init_state] = state_key_of(c->epoch, 0.0f, 0u);
         } else if (mode == JG_MODE_FRAME) {                  // processFrame :318-339
             const float bi = o2f(c->best_int), bx = o2f(c->best_ext);
             const float be = bi > bx ? bi : bx;              // bestEmitScore at the end of the last frame
@@ -344,7 +355,11 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d, int step, int open)
 // =========================================================================================
 // k_internal: one thread per active instance.  HMMInternalPropagation
 // (src/WFSTDecoderLite.cpp:376-484) + the list walk of doHMMInternalPropagation (:899-935),
-// with survivors compacted by warp ballot into the next list.
+// with survivors compacted by warp ballot into the next list.  A live exit token becomes an
+// arrival record {token, arc, destination state, output label} straight away — the instance
+// record carries the arc's destination and label, so nothing is gathered for it.  With no
+// end / word beam (FUSE) the record is final here (doHMMExternalPropagation :946-962 passes
+// every live exit token); otherwise k_filter applies the two beams once bestEmit is known.
 // =========================================================================================
 template <int S>
 __device__ __forceinline__ float4 viterbi_into(const float4 (&src)[S], const float* __restrict__ trp,
@@ -375,159 +390,216 @@ __device__ __forceinline__ float4 viterbi_into(const float4 (&src)[S], const flo
     return res;
 }
 
-template <int S>
+template <int S, bool FUSE>
 __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? 4 : 2)) k_internal(Dev d)
 {
     JG_TRACE_SCOPE(JGPU_K_INTERNAL, 0);
-    __shared__ int sh_pref[JG_MAX_LANES + 1];
-    __shared__ float sh_best[JG_THREADS / 32];
-    __shared__ int sh_cnt[3][JG_THREADS / 32];
-    int g0, g1;
-    balanced_slice(d, JG_CNT_CUR, 0, sh_pref, g0, g1);
-    if (g0 >= g1) return;
+    __shared__ LaneSh sh;
+    __shared__ float sh_best[2][JG_THREADS / 32];
+    __shared__ int sh_red[2][3][JG_THREADS / 32];
+    const int L = d.n_lanes;
+    const int tid = threadIdx.x;
+    for (int l = tid; l < L; l += blockDim.x) {
+        const LaneCtl* c = d.ctl + l;
+        sh.cnt[l] = c->mode == JG_MODE_FRAME ? c->n_cur : 0;
+        sh.f0[l] = c->norm; sh.f1[l] = c->thr_emit; sh.f2[l] = c->thr_start;
+        sh.i0[l] = c->srow; sh.i1[l] = c->flip;
+        sh.epoch[l] = c->epoch;
+    }
+    const int total = chunk_scan(sh, L);
     const size_t cap = (size_t)d.cap;
     constexpr int P = S - 1;
     const bool hist_on = d.max_hyps > 0;
-    const int L = d.n_lanes;
+    int par = 0;
 
-    for (int lane = first_lane_of(sh_pref, L, g0); lane < L && sh_pref[lane] < g1; ++lane) {
-        const int i0 = max(g0, sh_pref[lane]) - sh_pref[lane];
-        const int i1 = min(g1, sh_pref[lane + 1]) - sh_pref[lane];
-        if (i1 <= i0) continue;
-        LaneView v = lane_view(d, lane);
-        LaneCtl* c = v.c;
-        const float norm = c->norm, thr_emit = c->thr_emit, thr_start = c->thr_start;
-        const unsigned epoch = c->epoch;
-        const float* __restrict__ scores = d.scores + (size_t)c->srow * d.n_gmms;
+    for (int ch = blockIdx.x; ch < total; ch += gridDim.x, par ^= 1) {
+        const int lane = lane_of_chunk(sh.pref, L, ch);
+        const int k = (ch - sh.pref[lane]) * JG_CH + tid;
+        const bool valid = k < sh.cnt[lane];
+        const float norm = sh.f0[lane], thr_emit = sh.f1[lane], thr_start = sh.f2[lane];
+        const unsigned epoch = sh.epoch[lane];
+        const int flip = sh.i1[lane];
+        LaneCtl* c = d.ctl + lane;
+        const int4* meta_cur = d.inst_meta + ((size_t)lane * 2 + flip) * cap;
+        int4* meta_nxt = d.inst_meta + ((size_t)lane * 2 + (flip ^ 1)) * cap;
+        const float4* tok_cur = d.tok + ((size_t)lane * 2 + flip) * P * cap;
+        float4* tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * P * cap;
+        const float* __restrict__ scores = d.scores + (size_t)sh.i0[lane] * d.n_gmms;
         float best = JG_LZ;
         int cnt_emit = 0, cnt_end = 0, cnt_hist = 0;
 
-        for (int base = i0; base < i1; base += blockDim.x) {
-            const int k = base + threadIdx.x;
-            const bool valid = k < i1;
-            bool survive = false, has_exit = false;
-            int arc = 0, nst = 2, hmm = 0;
-            float4 nt[S];
-            float4 ex = null_tok();
+        bool survive = false, has_exit = false;
+        int nst = 2;
+        int4 meta = make_int4(0, 0, 0, 0);
+        float4 nt[S];
+        float4 ex = null_tok();
 #pragma unroll
-            for (int i = 0; i < S; ++i) nt[i] = null_tok();
-            if (valid) {
-                const int2 meta = v.meta_cur[k];
-                arc = meta.x;
-                hmm = meta.y & ~JG_FRESH;
-                const bool fresh = (meta.y & JG_FRESH) != 0;
-                const int4 h0 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2);
-                const int4 h1 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2 + 1);
-                nst = h0.x & 0xff;
-                const int cls = (h0.x & ~JG_LR_CLASS) >> 8;
-                const int gm[6] = {h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                float4 old[S];
-                old[0] = v.tok_cur[k];
+        for (int i = 0; i < S; ++i) nt[i] = null_tok();
+        if (valid) {
+            // every load of the instance is issued before anything depends on one of them
+            meta = ld_stream(meta_cur + k);
+            float4 old[S];
+            old[0] = ld_stream(tok_cur + k);
+            const bool fresh = (meta.y & JG_FRESH) != 0;
 #pragma unroll
-                for (int i = 1; i < P; ++i)
-                    old[i] = (!fresh && i < nst - 1) ? v.tok_cur[(size_t)i * cap + k] : null_tok();
-                old[S - 1] = null_tok();
-                if (old[0].x > JG_LZ && old[0].x < thr_start) old[0] = null_tok();   // :915-918
-                int nlive = 0;
-                const bool lr = S == 5 && (h0.x & JG_LR_CLASS);
-                float lrc[8];
-                const float* __restrict__ trp = d.trp + (size_t)cls * S * S;
-                const int2* __restrict__ se = d.se + (size_t)cls * S;
-                if (lr) {
-                    const float4 c0 = __ldg(d.lr + cls * 2), c1 = __ldg(d.lr + cls * 2 + 1);
-                    lrc[0] = c0.x; lrc[1] = c0.y; lrc[2] = c0.z; lrc[3] = c0.w;
-                    lrc[4] = c1.x; lrc[5] = c1.y; lrc[6] = c1.z; lrc[7] = c1.w;
-                }
+            for (int i = 1; i < P; ++i) old[i] = fresh ? null_tok() : ld_stream(tok_cur + (size_t)i * cap + k);
+            old[S - 1] = null_tok();
+            const int hmm = meta.y & ~JG_FRESH;
+            const int4 h0 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2);
+            const int4 h1 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2 + 1);
+            nst = h0.x & 0xff;
+            const int cls = (h0.x & ~JG_LR_CLASS) >> 8;
+            const int gm[6] = {h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-                for (int j = 1; j < S - 1; ++j) {
-                    if (j < nst - 1) {
-                        float4 res;
-                        if (lr) {
-                            // SEIndex[j] = [j-1, j+1): i = j-1 first, then i = j with strict '>' (:393-406)
-                            const float a = lrc[2 * (j - 1)], b = lrc[2 * (j - 1) + 1];
-                            res = old[j - 1];
-                            res.x = res.x + a;
-                            res.y = res.y + a;
-                            const float tmp = old[j].x + b;
-                            if (tmp > res.x) {
-                                res = old[j];
-                                res.x = tmp;
-                                res.y = res.y + b;
-                            }
-                        } else {
-                            res = viterbi_into<S>(old, trp, __ldg(se + j), j, nst);
-                        }
-                        res.x = res.x - norm;                                          // :408
-                        if (res.x > thr_emit) {
-                            const float o = __ldg(scores + gm[j - 1]);                 // calcOutput :411
-                            res.x = res.x + o;
-                            res.y = res.y + o;
-                            if (hist_on) {                                             // Histogram::addScore
-                                int sc;
-                                if (res.x < 0.0f) sc = (int)((double)res.x - 0.5);
-                                else sc = (int)((double)res.x + 0.5);
-                                if (sc > d.hist_max) atomicOr(&c->error, JG_ERR_HIST);
-                                else if (sc >= d.hist_min) { atomicAdd(&v.hist[sc - d.hist_min], 1); ++cnt_hist; }
-                            }
-                            if (res.x > best) best = res.x;
-                            if (res.x > JG_LZ) { ++nlive; nt[j] = res; }
-                        }
-                    }
-                }
-                cnt_emit += nlive;
-                survive = nlive > 0;
-                // exit state from the NEW emitting tokens (:443-483)
-                {
+            for (int i = 1; i < P; ++i)
+                if (i >= nst - 1) old[i] = null_tok();        // planes beyond this HMM's states hold stale data
+            if (old[0].x > JG_LZ && old[0].x < thr_start) old[0] = null_tok();   // :915-918
+            int nlive = 0;
+            const bool lr = S == 5 && (h0.x & JG_LR_CLASS);
+            float lrc[8];
+            const float* __restrict__ trp = d.trp + (size_t)cls * S * S;
+            const int2* __restrict__ se = d.se + (size_t)cls * S;
+            if (lr) {
+                const float4 c0 = __ldg(d.lr + cls * 2), c1 = __ldg(d.lr + cls * 2 + 1);
+                lrc[0] = c0.x; lrc[1] = c0.y; lrc[2] = c0.z; lrc[3] = c0.w;
+                lrc[4] = c1.x; lrc[5] = c1.y; lrc[6] = c1.z; lrc[7] = c1.w;
+            }
+#pragma unroll
+            for (int j = 1; j < S - 1; ++j) {
+                if (j < nst - 1) {
                     float4 res;
-                    if (lr) {                                 // SEIndex[N-1] = [N-2, N-1)
-                        const float a = nst == 5 ? lrc[6] : nst == 4 ? lrc[4] : lrc[2];
-                        res = nst == 5 ? nt[3] : nst == 4 ? nt[2] : nt[1];
+                    if (lr) {
+                        // SEIndex[j] = [j-1, j+1): i = j-1 first, then i = j with strict '>' (:393-406)
+                        const float a = lrc[2 * (j - 1)], b = lrc[2 * (j - 1) + 1];
+                        res = old[j - 1];
                         res.x = res.x + a;
                         res.y = res.y + a;
+                        const float tmp = old[j].x + b;
+                        if (tmp > res.x) {
+                            res = old[j];
+                            res.x = tmp;
+                            res.y = res.y + b;
+                        }
                     } else {
-                        res = viterbi_into<S>(nt, trp, __ldg(se + (nst - 1)), nst - 1, nst);
+                        res = viterbi_into<S>(old, trp, __ldg(se + j), j, nst);
                     }
-                    if (res.x > JG_LZ) { ex = res; has_exit = true; ++cnt_end; }
+                    res.x = res.x - norm;                                          // :408
+                    if (res.x > thr_emit) {
+                        const float o = __ldg(scores + gm[j - 1]);                 // calcOutput :411
+                        res.x = res.x + o;
+                        res.y = res.y + o;
+                        if (hist_on) {                                             // Histogram::addScore
+                            int sc;
+                            if (res.x < 0.0f) sc = (int)((double)res.x - 0.5);
+                            else sc = (int)((double)res.x + 0.5);
+                            if (sc > d.hist_max) atomicOr(&c->error, JG_ERR_HIST);
+                            else if (sc >= d.hist_min) { atomicAdd(d.hist + (size_t)lane * d.hist_nbins + (sc - d.hist_min), 1); ++cnt_hist; }
+                        }
+                        if (res.x > best) best = res.x;
+                        if (res.x > JG_LZ) { ++nlive; nt[j] = res; }
+                    }
                 }
             }
-            // survivors -> next list (warp-ballot compaction); instances that die simply stop
-            // being listed: their arcdyn.slot goes stale with the epoch (:924-925)
-            int pos, e;
-            warp_alloc2(&c->n_next, survive, &c->n_exit, has_exit, pos, e);
-            if (survive && pos < d.cap) {
-                v.meta_nxt[pos] = make_int2(arc, hmm);
-                v.tok_nxt[pos] = null_tok();                  // entry token consumed (:426-435)
-#pragma unroll
-                for (int i = 1; i < P; ++i)
-                    if (i < nst - 1) v.tok_nxt[(size_t)i * cap + pos] = nt[i];
-                *reinterpret_cast<uint2*>(&v.ad[arc].slot) = make_uint2((unsigned)pos + 1u, epoch);
-            }
-            if (has_exit) {                                   // n_exit <= n_cur <= cap
-                v.exit_arc[e] = arc;
-                v.exit_tok[e] = ex;
+            cnt_emit += nlive;
+            survive = nlive > 0;
+            // exit state from the NEW emitting tokens (:443-483)
+            {
+                float4 res;
+                if (lr) {                                 // SEIndex[N-1] = [N-2, N-1)
+                    const float a = nst == 5 ? lrc[6] : nst == 4 ? lrc[4] : lrc[2];
+                    res = nst == 5 ? nt[3] : nst == 4 ? nt[2] : nt[1];
+                    res.x = res.x + a;
+                    res.y = res.y + a;
+                } else {
+                    res = viterbi_into<S>(nt, trp, __ldg(se + (nst - 1)), nst - 1, nst);
+                }
+                if (res.x > JG_LZ) { ex = res; has_exit = true; ++cnt_end; }
             }
         }
-        // per-lane block reductions
+        // survivors -> next list (warp-ballot compaction); instances that die simply stop
+        // being listed: their slotmap entry goes stale with the epoch (:924-925).
+        // exit tokens -> arrival records of expansion round 0.
+        int pos, e;
+        warp_alloc2(&c->n_next, survive, &c->n_arr[0], has_exit, pos, e);
+        if (survive && pos < d.cap) {
+            st_stream(meta_nxt + pos, make_int4(meta.x, meta.y & ~JG_FRESH, meta.z, meta.w));
+            tok_nxt[pos] = null_tok();                    // entry token consumed (:426-435); k_walk<1> may overwrite it
+#pragma unroll
+            for (int i = 1; i < P; ++i)
+                if (i < nst - 1) st_stream(tok_nxt + (size_t)i * cap + pos, nt[i]);
+            d.slotmap[(size_t)lane * d.n_arcs + meta.x] = ((epoch & 0x7ffu) << JG_SLOT_BITS) | ((unsigned)pos + 1u);
+        }
+        if (has_exit && e < d.cap_arr) {
+            Arrival* a = d.arr + (size_t)lane * d.cap_arr + e;
+            *reinterpret_cast<float4*>(a) = ex;
+            *(reinterpret_cast<int4*>(a) + 1) = make_int4(meta.x, meta.z, meta.w, 0);
+            if (FUSE && meta.z < 0)                       // destination can see several arrivals this frame
+                atomicMax(d.state_key + (size_t)lane * d.n_states + (meta.z & 0x7fffffff),
+                          state_key_of(epoch, ex.x, (unsigned)e));
+        }
+        // per-chunk block reductions
         for (int o = 16; o > 0; o >>= 1) {
             best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
             cnt_emit += __shfl_xor_sync(0xffffffffu, cnt_emit, o);
             cnt_end += __shfl_xor_sync(0xffffffffu, cnt_end, o);
             cnt_hist += __shfl_xor_sync(0xffffffffu, cnt_hist, o);
         }
-        const int w = threadIdx.x >> 5;
+        const int w = tid >> 5;
+        if (lane_id() == 0) { sh_best[par][w] = best; sh_red[par][0][w] = cnt_emit; sh_red[par][1][w] = cnt_end; sh_red[par][2][w] = cnt_hist; }
         __syncthreads();
-        if (lane_id() == 0) { sh_best[w] = best; sh_cnt[0][w] = cnt_emit; sh_cnt[1][w] = cnt_end; sh_cnt[2][w] = cnt_hist; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             for (int i = 1; i < JG_THREADS / 32; ++i) {
-                best = fmaxf(best, sh_best[i]);
-                cnt_emit += sh_cnt[0][i]; cnt_end += sh_cnt[1][i]; cnt_hist += sh_cnt[2][i];
+                best = fmaxf(best, sh_best[par][i]);
+                cnt_emit += sh_red[par][0][i]; cnt_end += sh_red[par][1][i]; cnt_hist += sh_red[par][2][i];
             }
             if (best > JG_LZ) atomicMax(&c->best_int, f2o(best));
             if (cnt_emit) atomicAdd(&c->c_active_emit, cnt_emit);
             if (cnt_end) atomicAdd(&c->c_active_end, cnt_end);
+            if (FUSE && cnt_end) atomicAdd(&c->c_end_proc, cnt_end);
             if (cnt_hist) atomicAdd(&c->hist_count, cnt_hist);
         }
+    }
+}
+
+// =========================================================================================
+// k_filter (only with an end or word beam): the exit-token test of doHMMExternalPropagation
+// (:946-962) once bestEmit of the frame is complete.  Records that fail are marked dropped;
+// the others are max-reduced per destination state where that is needed.
+// =========================================================================================
+__global__ void __launch_bounds__(JG_THREADS, 6) k_filter(Dev d)
+{
+    JG_TRACE_SCOPE(JGPU_K_SEED, 0);
+    __shared__ LaneSh sh;
+    const int L = d.n_lanes, tid = threadIdx.x;
+    for (int l = tid; l < L; l += blockDim.x) {
+        const LaneCtl* c = d.ctl + l;
+        sh.cnt[l] = c->mode == JG_MODE_FRAME ? min(c->n_arr[0], d.cap_arr) : 0;
+        const float be = o2f(c->best_int);
+        sh.f0[l] = (d.end_beam > 0.0f ? (be - d.end_beam) : JG_LZ);     // :349
+        sh.f1[l] = (d.word_beam > 0.0f ? (be - d.word_beam) : JG_LZ);   // :350
+        sh.epoch[l] = c->epoch;
+    }
+    const int total = chunk_scan(sh, L);
+    for (int ch = blockIdx.x; ch < total; ch += gridDim.x) {
+        const int lane = lane_of_chunk(sh.pref, L, ch);
+        const int e = (ch - sh.pref[lane]) * JG_CH + tid;
+        int proc = 0;
+        if (e < sh.cnt[lane]) {
+            Arrival* a = d.arr + (size_t)lane * d.cap_arr + e;
+            const float score = a->tok.x;
+            const int4 m = *(reinterpret_cast<const int4*>(a) + 1);
+            const float thr = m.z == 0 ? sh.f0[lane] : sh.f1[lane];                 // :952-962
+            if (score > thr) {
+                proc = 1;
+                if (m.y < 0)
+                    atomicMax(d.state_key + (size_t)lane * d.n_states + (m.y & 0x7fffffff),
+                              state_key_of(sh.epoch[lane], score, (unsigned)e));
+            } else {
+                a->via = -2;
+            }
+        }
+        proc = __reduce_add_sync(0xffffffffu, proc);
+        if (lane_id() == 0 && proc) atomicAdd(&d.ctl[lane].c_end_proc, proc);
     }
 }
 
@@ -535,315 +607,261 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? 4 : 2)) k_internal(Dev d
 // External propagation (doHMMExternalPropagation :937-982 + propagateToken :491-605) as
 // level-synchronous rounds over WFST states.
 //   arrival  = a token reaching state q through arc `via` (exit of an instance, epsilon arc,
-//              or tee pass-through).  Arrivals are max-reduced per state by a fire-and-forget
-//              64-bit atomicMax on state_key (score bits | record index); the records of one
-//              round are stored back to back, so round k simply walks its slice of records and
-//              expands those that still own their state — once per round instead of the
-//              reference's re-expansion per token.
-//   pass 0   = expansion, per out-arc of q: epsilon arc -> arrival for the next round
-//              (:533-540); model arc -> entry-token candidate, atomicMax on arcdyn.key
-//              (:542-582); tee model -> additional pass-through arrival (:584-600).
-//   pass 1   = commit: every record that owns its state walks its arc row again; the candidate
-//              that owns arcdyn.key writes the entry token into the next list, attaching a new
-//              instance when the arc had none (attachNetInst :751-774), and clears the key.
-// No atomic in pass 0 returns a value the thread has to wait for, except the per-round record
-// counter (one aggregated atomicAdd per warp).
+//              or tee pass-through).  A state that can receive more than one arrival per
+//              frame (JG_MULTI, decided on the static network) max-reduces them through a
+//              fire-and-forget 64-bit atomicMax on state_key (score bits | record index) and
+//              only the record that owns the key expands the state; every other state has at
+//              most one arrival per frame and needs no key at all.
+//   k_walk<0>(k) = expansion round k over the records created in round k-1: word-boundary
+//              record (:497-509), final-state candidate (:513-520), and the state's
+//              PASS-THROUGH arcs only — epsilon arcs (:533-540) and tee models (:584-600) —
+//              which create the arrivals of round k+1.  Rows are stored
+//              [epsilon | tee-model | other model arcs], so this is a prefix of the row.
+//   k_walk<1>  = commit over the records of all rounds: the record that owns its state at the
+//              END of the closure walks the model arcs of the row once and writes the entry
+//              tokens (:542-582).  An arc only ever receives candidates from the owners of its
+//              source state, and a later owner beats an earlier one on every arc (fl(s+w) is
+//              monotone in s), so the final owner's token IS the recombination result: no
+//              per-arc atomic is needed.  The arc's instance is found through slotmap[arc]
+//              (existing slot if the instance survived the internal phase this step, else a
+//              new FRESH instance, attachNetInst :751-774); a row's slotmap entries are
+//              contiguous, so the lookup costs one sequential read per state.
 // =========================================================================================
-// state key = epoch (11 bits) | orderable score (32 bits) | arrival record (21 bits): keys of older
-// steps always lose the atomicMax and never compare equal, so state_key needs no per-frame cleaning
-// (k_boundary wipes a lane's table when its 11-bit epoch wraps, once every 2048 steps).
-#define JG_R_BITS 21
-__device__ __forceinline__ u64 state_key_of(unsigned epoch, float score, unsigned r)
-{
-    return ((u64)(epoch & 0x7ffu) << 53) | ((u64)f2o(score) << JG_R_BITS) | (u64)r;
-}
-
-__device__ __forceinline__ void arrive(const Dev& d, const LaneView& v, int q, int via, float4 tok, int out_round,
-                                       int out_base)
-{
-    const int r = out_base + agg_inc(&v.c->n_arr[out_round]);
-    if (r >= d.cap_arr) return;                              // flagged by k_boundary
-    Arrival a;
-    a.tok = tok; a.via = via; a.q = q; a.pad[0] = a.pad[1] = 0;
-    v.arr[r] = a;
-    atomicMax(&v.skey[q], state_key_of(v.c->epoch, tok.x, (unsigned)r));
-}
-
-__global__ void __launch_bounds__(JG_THREADS, 6) k_seed(Dev d)
-{
-    JG_TRACE_SCOPE(JGPU_K_SEED, 0);
-    __shared__ int sh_pref[JG_MAX_LANES + 1];
-    // utterance seeds: propagateToken(&zeroToken, NULL) (:221-226) = an arrival at the initial state
-    if (blockIdx.x == 0 && threadIdx.x < 32)
-        for (int lane = threadIdx.x; lane < d.n_lanes; lane += 32)
-            if (d.ctl[lane].mode == JG_MODE_SEED) {
-                LaneView v = lane_view(d, lane);
-                Arrival a;
-                a.tok = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
-                a.via = -1; a.q = d.init_state; a.pad[0] = a.pad[1] = 0;
-                v.arr[0] = a;                                 // seed lanes have no exit tokens: record 0 is free
-                v.c->n_arr[0] = 1;
-                v.skey[d.init_state] = state_key_of(v.c->epoch, 0.0f, 0u);
-            }
-    int g0, g1;
-    balanced_slice(d, JG_CNT_EXIT, 0, sh_pref, g0, g1);
-    if (g0 >= g1) return;
-    const int L = d.n_lanes;
-    for (int lane = first_lane_of(sh_pref, L, g0); lane < L && sh_pref[lane] < g1; ++lane) {
-        const int i0 = max(g0, sh_pref[lane]) - sh_pref[lane];
-        const int i1 = min(g1, sh_pref[lane + 1]) - sh_pref[lane];
-        if (i1 <= i0) continue;
-        LaneView v = lane_view(d, lane);
-        LaneCtl* c = v.c;
-        const float be = o2f(c->best_int);
-        const float thr_end = (d.end_beam > 0.0f ? (be - d.end_beam) : JG_LZ);     // :349
-        const float thr_word = (d.word_beam > 0.0f ? (be - d.word_beam) : JG_LZ);  // :350
-        int proc = 0;
-        for (int e = i0 + threadIdx.x; e < i1; e += blockDim.x) {
-            const int arc = v.exit_arc[e];
-            const float4 t = v.exit_tok[e];
-            const int4 a = __ldg(&d.arcs[arc]);
-            const float thr = a.w == 0 ? thr_end : thr_word;                        // :952-962
-            if (t.x > thr) {
-                ++proc;
-                arrive(d, v, a.x, arc, t, 0, 0);
-            }
-        }
-        __syncwarp();
-        for (int o = 16; o > 0; o >>= 1) proc += __shfl_xor_sync(0xffffffffu, proc, o);
-        if (lane_id() == 0 && proc) atomicAdd(&c->c_end_proc, proc);
-    }
-}
-
-struct WalkCtx {
-    float thr_end, thr_word;
-    int out_round, out_base;
-    unsigned epoch;
-};
-
 template <int PASS>
-__device__ __forceinline__ void process_arc(const Dev& d, const LaneView& v, const WalkCtx& x, const float4 tok,
-                                            unsigned r, int b, float& best, int& n_entry)
+__device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, unsigned epoch, float thr_end, float thr_word,
+                                            int out_round, int out_base, int flip, const float4 tok, int b, const int4 a,
+                                            unsigned sm, float& best, int& n_entry)
 {
-    const int4 a = __ldg(&d.arcs[b]);
     const float w = __int_as_float(a.y);
     const float s = tok.x + w;
-    if (a.z == 0) {                                           // epsilon input: :533-540
-        if (PASS == 0 && s > x.thr_end)
-            arrive(d, v, a.x, b, make_float4(s, tok.y, tok.z + w, tok.w), x.out_round, x.out_base);
-        return;
-    }
-    // model arc: :542-601
-    if (s > JG_LZ) {
-        const u64 key = ((u64)f2o(s) << 32) | r;
-        if (PASS == 0) {
-            atomicMax(&v.ad[b].key, key);                     // recombination: best entry candidate of the arc
-        } else {
-            const uint4 dyn = *reinterpret_cast<const uint4*>(&v.ad[b]);
-            if (dyn.x == r && dyn.y == (unsigned)(key >> 32)) {             // this candidate won
-                const float4 t = make_float4(s, tok.y, tok.z + w, tok.w);   // :568-570
-                if (s > best) best = s;
-                ++n_entry;
-                if (dyn.w == x.epoch && dyn.z != 0) {         // the instance survived the internal phase
-                    v.tok_nxt[dyn.z - 1] = t;                 // plane 0 = entry token
-                    v.ad[b].key = 0;
-                } else {
-                    const int pos = agg_inc(&v.c->n_next);
-                    if (pos < d.cap) {
-                        v.meta_nxt[pos] = make_int2(b, (a.z - 1) | JG_FRESH);
-                        v.tok_nxt[pos] = t;
-                        *reinterpret_cast<uint4*>(&v.ad[b]) = make_uint4(0u, 0u, (unsigned)pos + 1u, x.epoch);
-                    } else {
-                        v.ad[b].key = 0;                      // overflow is flagged by k_boundary
-                    }
+    if (PASS == 0) {
+        float4 t;
+        bool go;
+        if (a.z == 0) {                                       // epsilon input: :533-540
+            t = make_float4(s, tok.y, tok.z + w, tok.w);
+            go = s > thr_end;
+        } else {                                              // tee model: :584-600
+            const float tee = __ldg(d.arc_tee + b);
+            const float s2 = s + tee;
+            t = make_float4(s2, tok.y + tee, tok.z + w, tok.w);
+            go = s2 > (a.w != 0 ? thr_word : thr_end);
+        }
+        if (go) {
+            const int r = out_base + agg_inc(&c->n_arr[out_round]);
+            if (r < d.cap_arr) {                              // overflow is flagged by k_boundary
+                Arrival* o = d.arr + (size_t)lane * d.cap_arr + r;
+                *reinterpret_cast<float4*>(o) = t;
+                *(reinterpret_cast<int4*>(o) + 1) = make_int4(b, a.x, a.w, 0);
+                if (a.x < 0)
+                    atomicMax(d.state_key + (size_t)lane * d.n_states + (a.x & 0x7fffffff), state_key_of(epoch, t.x, (unsigned)r));
+            }
+        }
+    } else {
+        if (s > JG_LZ) {                                      // model arc: :542-582
+            const float4 t = make_float4(s, tok.y, tok.z + w, tok.w);   // :568-570
+            if (s > best) best = s;
+            ++n_entry;
+            const size_t cap = (size_t)d.cap;
+            float4* tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * (size_t)(d.S - 1) * cap;
+            if ((sm >> JG_SLOT_BITS) == (epoch & 0x7ffu) && (sm & JG_SLOT_MASK) != 0) {
+                tok_nxt[(sm & JG_SLOT_MASK) - 1] = t;         // the instance survived the internal phase: plane 0 = entry token
+            } else {
+                const int pos = agg_inc(&c->n_next);
+                if (pos < d.cap) {                            // overflow is flagged by k_boundary
+                    int4* meta_nxt = d.inst_meta + ((size_t)lane * 2 + (flip ^ 1)) * cap;
+                    st_stream(meta_nxt + pos, make_int4(b, (a.z - 1) | JG_FRESH, a.x, a.w));
+                    tok_nxt[pos] = t;
+                    d.slotmap[(size_t)lane * d.n_arcs + b] = ((epoch & 0x7ffu) << JG_SLOT_BITS) | ((unsigned)pos + 1u);
                 }
             }
         }
     }
-    if (PASS == 0 && d.arc_tee) {
-        const float tee = __ldg(d.arc_tee + b);
-        if (tee > JG_LZ) {                                    // :584-600
-            const float s2 = s + tee;
-            const float thr = a.w != 0 ? x.thr_word : x.thr_end;
-            if (s2 > thr)
-                arrive(d, v, a.x, b, make_float4(s2, tok.y + tee, tok.z + w, tok.w), x.out_round, x.out_base);
-        }
-    }
 }
 
-__device__ __forceinline__ WalkCtx walk_ctx(const Dev& d, const LaneCtl* c, int round)
-{
-    WalkCtx x;
-    x.thr_end = x.thr_word = JG_LZ;
-    if (c->mode == JG_MODE_FRAME) {
-        const float be = o2f(c->best_int);
-        x.thr_end = (d.end_beam > 0.0f ? (be - d.end_beam) : JG_LZ);
-        x.thr_word = (d.word_beam > 0.0f ? (be - d.word_beam) : JG_LZ);
-    }
-    x.out_round = round + 1;
-    x.out_base = arr_base(c, round + 1);
-    x.epoch = c->epoch;
-    return x;
-}
-
-// PASS 0: expansion round `round`.  PASS 1: commit over the records of all rounds.
-// Per chunk of 256 records: (A) one thread per record decides whether the record still owns its
-// state and does the per-record work (word-boundary record, final-state candidate); (B) the arc
-// rows of all 256 records are walked as ONE flattened list — thread t takes arcs t, t+256, ... and
-// finds the owning record by binary search in the shared prefix of out-degrees — so every lane has
-// an independent arc in flight regardless of how the out-degrees are distributed.
 template <int PASS>
 __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
 {
     JG_TRACE_SCOPE(PASS ? JGPU_K_COMMIT : JGPU_K_EXPAND, round);
-    __shared__ int sh_pref[JG_MAX_LANES + 1];
+    __shared__ LaneSh sh;
     __shared__ int s_off[JG_THREADS + 1];
     __shared__ int s_first[JG_THREADS];
-    __shared__ unsigned s_r[JG_THREADS];
     __shared__ float4 s_tok[JG_THREADS];
     __shared__ int s_wsum[JG_THREADS / 32];
-    int g0, g1;
-    balanced_slice(d, PASS == 0 ? JG_CNT_ROUND : JG_CNT_ALL, round, sh_pref, g0, g1);
-    if (g0 >= g1) return;
     const int L = d.n_lanes;
     const int tid = threadIdx.x, wid = tid >> 5;
-    for (int lane = first_lane_of(sh_pref, L, g0); lane < L && sh_pref[lane] < g1; ++lane) {
-        const int i0 = max(g0, sh_pref[lane]) - sh_pref[lane];
-        const int i1 = min(g1, sh_pref[lane + 1]) - sh_pref[lane];
-        if (i1 <= i0) continue;
-        LaneView v = lane_view(d, lane);
-        LaneCtl* c = v.c;
-        const WalkCtx x = walk_ctx(d, c, round);
-        const int rec0 = PASS == 0 ? arr_base(c, round) : 0;
-        const int frame = c->frame;
-        int arcs_done = 0, n_entry = 0;
-        float best = JG_LZ;
-        for (int base = i0; base < i1; base += blockDim.x) {
-            // ---- (A) one thread per record ----
-            const int e = base + tid;
-            bool valid = e < i1;
-            int q = 0, first = 0, deg = 0;
-            const unsigned r = (unsigned)(rec0 + e);
-            float4 tok = null_tok();
+    for (int l = tid; l < L; l += blockDim.x) {
+        const LaneCtl* c = d.ctl + l;
+        const int mode = c->mode;
+        int n = 0, rec0 = 0, out_base = 0;
+        if (mode != JG_MODE_IDLE) {
+            if (PASS == 0) {
+                rec0 = arr_base(c, round);
+                n = max(0, min(c->n_arr[round], d.cap_arr - rec0));
+                out_base = rec0 + c->n_arr[round];
+            } else {
+                n = min(arr_base(c, d.n_rounds + 1), d.cap_arr);
+            }
+        }
+        sh.cnt[l] = n;
+        sh.i0[l] = rec0; sh.i1[l] = out_base; sh.i2[l] = PASS == 0 ? c->frame : c->flip;
+        float te = JG_LZ, tw = JG_LZ;
+        if (mode == JG_MODE_FRAME) {
+            const float be = o2f(c->best_int);
+            te = (d.end_beam > 0.0f ? (be - d.end_beam) : JG_LZ);
+            tw = (d.word_beam > 0.0f ? (be - d.word_beam) : JG_LZ);
+        }
+        sh.f0[l] = te; sh.f1[l] = tw;
+        sh.epoch[l] = c->epoch;
+    }
+    const int total_chunks = chunk_scan(sh, L);
+
+    for (int ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
+        const int lane = lane_of_chunk(sh.pref, L, ch);
+        LaneCtl* c = d.ctl + lane;
+        const unsigned epoch = sh.epoch[lane];
+        const float thr_end = sh.f0[lane], thr_word = sh.f1[lane];
+        const int out_base = sh.i1[lane];
+        Arrival* arr = d.arr + (size_t)lane * d.cap_arr;
+        // ---- (A) one thread per record ----
+        const int e = (ch - sh.pref[lane]) * JG_CH + tid;
+        bool valid = e < sh.cnt[lane];
+        const unsigned r = (unsigned)(sh.i0[lane] + e);
+        int first = 0, deg = 0, arcs_done = 0;
+        float4 tok = null_tok();
+        u64 fin = 0;
+        if (valid) {
+            tok = *reinterpret_cast<const float4*>(arr + r);
+            const int4 m = *(reinterpret_cast<const int4*>(arr + r) + 1);     // {via, q | MULTI, olab, -}
+            const int q = m.y & 0x7fffffff;
+            const int4 st = __ldg(&d.states[q]);
+            valid = m.x != -2;
+            if (valid && m.y < 0)                             // still the best arrival of q?
+                valid = d.state_key[(size_t)lane * d.n_states + q] == state_key_of(epoch, tok.x, r);
             if (valid) {
-                const Arrival a = v.arr[r];
-                q = a.q;
-                tok = a.tok;
-                valid = a.via != -2 && v.skey[q] == state_key_of(x.epoch, tok.x, r);   // still the best arrival of q?
-                if (valid) {
-                    const int4 st = __ldg(&d.states[q]);
-                    first = st.x; deg = st.y;
-                    if (PASS == 0 && a.via >= 0) {
-                        const int olab = __ldg(&d.arcs[a.via]).w;
-                        if (olab != 0) {                      // word boundary record: :497-509
-                            const int p = agg_inc(&c->n_paths);
-                            if (p < d.cap_paths) {
-                                PathRec pr;
-                                pr.prev = __float_as_int(tok.w); pr.frame = frame; pr.label = olab;
-                                pr.score = tok.x; pr.ac = tok.y; pr.lm = tok.z; pr.pad0 = pr.pad1 = 0;
-                                v.paths[p] = pr;
-                                tok.w = __int_as_float(p);
-                                v.arr[r].tok.w = tok.w;
-                            } else {
-                                valid = false;                // flagged by k_boundary
-                                v.arr[r].via = -2;
-                            }
+                const int n_eps = st.w & 0xffff, n_tee = (unsigned)st.w >> 16;
+                if (PASS == 0) {
+                    if (m.z != 0) {                           // word boundary record: :497-509
+                        const int p = agg_inc(&c->n_paths);
+                        if (p < d.cap_paths) {
+                            PathRec* pr = d.paths + (size_t)lane * d.cap_paths + p;
+                            st_stream(reinterpret_cast<int4*>(pr), make_int4(__float_as_int(tok.w), sh.i2[lane], m.z, __float_as_int(tok.x)));
+                            st_stream(reinterpret_cast<int4*>(pr) + 1, make_int4(__float_as_int(tok.y), __float_as_int(tok.z), 0, 0));
+                            tok.w = __int_as_float(p);
+                            arr[r].tok.w = tok.w;
+                        } else {
+                            valid = false;                    // flagged by k_boundary
+                            arr[r].via = -2;
                         }
-                        const float fw = __int_as_float(st.z);
-                        if (valid && fw > JG_LZ)              // :513-520
-                            atomicMax(&c->best_final, ((u64)f2o(tok.x + fw) << 32) | r);
                     }
-                    if (!valid) deg = 0;
-                    if (PASS == 0) arcs_done += deg;
-                    if (deg >= d.huge_deg) {                  // hub-like state: left to k_walk_huge
-                        if (PASS == 0) {
-                            const int h = atomicAdd(&c->n_huge[round], 1);
-                            if (h < d.cap_huge) v.huge[(size_t)round * d.cap_huge + h] = make_int2(q, (int)r);
-                            else atomicOr(&c->error, JG_ERR_HUGE);
-                        }
+                    const float fw = __int_as_float(st.z);
+                    if (valid && fw > JG_LZ && m.x >= 0) fin = ((u64)f2o(tok.x + fw) << 32) | r;   // :513-520 (not for the seed: trans == NULL)
+                    if (valid) { first = st.x; deg = n_eps + n_tee; }
+                } else {
+                    first = st.x + n_eps;
+                    deg = st.y - n_eps;
+                    arcs_done = st.y;
+                    if (deg >= d.huge_deg) {                  // hub-like row: left to k_commit_huge
+                        const int h = atomicAdd(&c->n_huge, 1);
+                        if (h < d.cap_huge) d.huge[(size_t)lane * d.cap_huge + h] = make_int2(q, (int)r);
+                        else atomicOr(&c->error, JG_ERR_HUGE);
                         deg = 0;
                     }
                 }
             }
-            // ---- block-wide exclusive prefix of the out-degrees ----
-            int incl = deg;
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane_id() >= o) incl += t;
+        }
+        if (PASS == 0) {
+            if (__any_sync(0xffffffffu, fin != 0)) {
+                fin = warp_max_u64(fin);
+                if (lane_id() == 0) atomicMax(&c->best_final, fin);
             }
-            if (lane_id() == 31) s_wsum[wid] = incl;
-            s_first[tid] = first; s_r[tid] = r; s_tok[tid] = tok;
-            __syncthreads();
-            int woff = 0;
-            for (int w = 0; w < wid; ++w) woff += s_wsum[w];
-            s_off[tid] = woff + incl - deg;
-            if (tid == blockDim.x - 1) s_off[blockDim.x] = woff + incl;
-            __syncthreads();
-            const int total = s_off[blockDim.x];
-            // ---- (B) flattened arc rows ----
-            for (int j = tid; j < total; j += blockDim.x) {
-                int lo = 0, hi = blockDim.x;                  // largest src with s_off[src] <= j
-                while (lo + 1 < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (s_off[mid] <= j) lo = mid; else hi = mid;
+        }
+        // ---- block-wide exclusive prefix of the row lengths ----
+        int incl = deg;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane_id() >= o) incl += t;
+        }
+        if (lane_id() == 31) s_wsum[wid] = incl;
+        s_first[tid] = first; s_tok[tid] = tok;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < wid; ++w) woff += s_wsum[w];
+        s_off[tid] = woff + incl - deg;
+        if (tid == JG_THREADS - 1) s_off[JG_THREADS] = woff + incl;
+        __syncthreads();
+        const int total = s_off[JG_THREADS];
+        // ---- (B) the rows of the chunk as ONE flattened arc list, two arcs in flight per thread ----
+        int n_entry = 0;
+        float best = JG_LZ;
+        for (int jb = 0; jb < total; jb += 2 * JG_THREADS) {
+            int b[2], src[2];
+            int4 a[2];
+            unsigned sm[2] = {0u, 0u};
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int j = jb + u * JG_THREADS + tid;
+                b[u] = -1; src[u] = 0;
+                if (j < total) {
+                    int lo = 0, hi = JG_THREADS;              // largest src with s_off[src] <= j
+                    while (lo + 1 < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_off[mid] <= j) lo = mid; else hi = mid;
+                    }
+                    src[u] = lo;
+                    b[u] = s_first[lo] + (j - s_off[lo]);
+                    a[u] = __ldg(&d.arcs[b[u]]);
+                    if (PASS == 1) sm[u] = d.slotmap[(size_t)lane * d.n_arcs + b[u]];
                 }
-                process_arc<PASS>(d, v, x, s_tok[lo], s_r[lo], s_first[lo] + (j - s_off[lo]), best, n_entry);
             }
-            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (b[u] >= 0)
+                    process_arc<PASS>(d, lane, c, epoch, thr_end, thr_word, round + 1, out_base, sh.i2[lane], s_tok[src[u]], b[u],
+                                      a[u], sm[u], best, n_entry);
         }
-        __syncwarp();
-        for (int o = 16; o > 0; o >>= 1) {
-            arcs_done += __shfl_xor_sync(0xffffffffu, arcs_done, o);
-            n_entry += __shfl_xor_sync(0xffffffffu, n_entry, o);
-            best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if (PASS == 1) {
+            arcs_done = __reduce_add_sync(0xffffffffu, arcs_done);
+            n_entry = __reduce_add_sync(0xffffffffu, n_entry);
+            for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+            if (lane_id() == 0) {
+                if (arcs_done) atomicAdd(&c->c_arcs, arcs_done);
+                if (n_entry) atomicAdd(&c->c_entry, n_entry);
+                if (best > JG_LZ) atomicMax(&c->best_ext, f2o(best));           // :572-573
+            }
         }
-        if (lane_id() == 0) {
-            if (arcs_done) atomicAdd(&c->c_arcs, arcs_done);
-            if (n_entry) atomicAdd(&c->c_entry, n_entry);
-            if (best > JG_LZ) atomicMax(&c->best_ext, f2o(best));               // :572-573
-        }
+        __syncthreads();                                      // s_off / s_tok are rewritten by the next chunk
     }
 }
 
-// hub-like states: a group of CTAs per lane strides over the arc row.
-// PASS 0: the states met in round `round`; PASS 1: those of every round.
-template <int PASS>
-__global__ void __launch_bounds__(JG_THREADS) k_walk_huge(Dev d, int round)
+// hub-like rows met by the commit: all CTAs of the lane stride over the row.
+__global__ void __launch_bounds__(JG_THREADS) k_commit_huge(Dev d)
 {
-    JG_TRACE_SCOPE(JGPU_K_EXPAND_HUGE, round + 100 * PASS);
+    JG_TRACE_SCOPE(JGPU_K_EXPAND_HUGE, 0);
     const int lane = blockIdx.y;
     LaneCtl* c = d.ctl + lane;
     if (c->mode == JG_MODE_IDLE) return;
-    const int r_lo = PASS == 0 ? round : 0, r_hi = PASS == 0 ? round + 1 : d.n_rounds;
-    bool any = false;
-    for (int k = r_lo; k < r_hi; ++k) any |= c->n_huge[k] > 0;
-    if (!any) return;
-    LaneView v = lane_view(d, lane);
+    const int n = min(c->n_huge, d.cap_huge);
+    if (n == 0) return;
+    const unsigned epoch = c->epoch;
+    const int flip = c->flip;
     int n_entry = 0;
     float best = JG_LZ;
-    for (int k = r_lo; k < r_hi; ++k) {
-        const int n = min(c->n_huge[k], d.cap_huge);
-        if (n == 0) continue;
-        const WalkCtx x = walk_ctx(d, c, k);
-        const int2* list = v.huge + (size_t)k * d.cap_huge;
-        for (int h = 0; h < n; ++h) {
-            const int2 qr = list[h];
-            const float4 tok = v.arr[qr.y].tok;
-            if (PASS == 1 && v.skey[qr.x] != state_key_of(x.epoch, tok.x, (unsigned)qr.y)) continue;   // re-expanded later by a better token
-            const int4 st = __ldg(&d.states[qr.x]);
-            for (int b = st.x + blockIdx.x * blockDim.x + threadIdx.x; b < st.x + st.y; b += gridDim.x * blockDim.x)
-                process_arc<PASS>(d, v, x, tok, (unsigned)qr.y, b, best, n_entry);
+    for (int h = 0; h < n; ++h) {
+        const int2 qr = d.huge[(size_t)lane * d.cap_huge + h];
+        const float4 tok = d.arr[(size_t)lane * d.cap_arr + qr.y].tok;
+        const int4 st = __ldg(&d.states[qr.x]);
+        const int n_eps = st.w & 0xffff;
+        for (int b = st.x + n_eps + blockIdx.x * blockDim.x + threadIdx.x; b < st.x + st.y; b += gridDim.x * blockDim.x) {
+            const int4 a = __ldg(&d.arcs[b]);
+            const unsigned sm = d.slotmap[(size_t)lane * d.n_arcs + b];
+            process_arc<1>(d, lane, c, epoch, JG_LZ, JG_LZ, 0, 0, flip, tok, b, a, sm, best, n_entry);
         }
     }
-    if (PASS == 1) {
-        __syncwarp();
-        for (int o = 16; o > 0; o >>= 1) {
-            n_entry += __shfl_xor_sync(0xffffffffu, n_entry, o);
-            best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
-        }
-        if (lane_id() == 0) {
-            if (n_entry) atomicAdd(&c->c_entry, n_entry);
-            if (best > JG_LZ) atomicMax(&c->best_ext, f2o(best));
-        }
+    __syncwarp();
+    n_entry = __reduce_add_sync(0xffffffffu, n_entry);
+    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane_id() == 0) {
+        if (n_entry) atomicAdd(&c->c_entry, n_entry);
+        if (best > JG_LZ) atomicMax(&c->best_ext, f2o(best));
     }
 }
