@@ -120,6 +120,7 @@ struct Dev {
     int*      hist;
     const float* scores;       // [ring rows][n_gmms]
     const int4*  sched;        // [n_steps + 1][n_lanes] {feature row, score row, flags, utt}
+    int*      lane_step;       // [n_lanes] next schedule row of the lane (k_boundary)
     ResHdr*   res_hdr;
     JgpuWord* res_words;
     int*      fstat_cnt;       // [n_lanes][max_frames][4]

@@ -20,6 +20,12 @@
 #define JG_HUGE_DEG 1024   // rows with at least this many model arcs are walked by all CTAs of the lane
 #include "jgpu_search.cuh"
 
+#ifdef JG_TRACE
+#define JG_TRACING(h) ((h)->d_trace != nullptr)
+#else
+#define JG_TRACING(h) false
+#endif
+
 namespace {
 
 int fail(int code, const char* fmt, ...)
@@ -60,6 +66,8 @@ struct jgpu_handle {
     int bpl = 8;            // CTAs per lane for the search kernels
     bool has_huge = false;
     int max_deg = 0, n_huge_states = 0;
+    cudaGraphExec_t graph_step = nullptr, graph_block = nullptr;   // one frame step / FB frame steps of all lanes
+    bool use_graphs = true;
     std::vector<unsigned> host_epoch;    // mirror of LaneCtl::epoch (advances on every non-idle step of the lane)
     cudaStream_t stream = nullptr;       // search kernels, copies
     cudaStream_t stream_gmm = nullptr;   // acoustic scoring of the NEXT frame block overlaps the search
@@ -452,7 +460,7 @@ int build_state(jgpu_handle* h)
     {
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
-        d.grid_internal = n_sm * (h->S <= 5 ? 4 : 2);   // __launch_bounds__ of k_internal
+        d.grid_internal = n_sm * (h->S <= 5 ? JG_INT_CTAS : 2);   // __launch_bounds__ of k_internal
         d.grid_other = n_sm * 6;                       // __launch_bounds__(256, 6)
     }
 
@@ -489,6 +497,7 @@ int build_state(jgpu_handle* h)
     // schedule + score ring + streaming feature staging
     if ((rc = h->alloc(&h->d_sched, (size_t)(h->sched_chunk + 1) * L, false))) return rc;
     if ((rc = h->alloc(&h->d_rows, (size_t)h->sched_chunk * L, false))) return rc;
+    if ((rc = h->alloc(&d.lane_step, L))) return rc;
     if ((rc = h->alloc(&h->d_scores, (size_t)2 * h->FB * L * d.n_gmms, false))) return rc;   // two halves
     if ((rc = h->alloc(&h->d_stream_feats, L * h->stream_chunk * h->dim, false))) return rc;
     if ((rc = h->alloc(&h->d_gmm_out, (size_t)h->gmm_chunk * d.n_gmms, false))) return rc;
@@ -498,6 +507,18 @@ int build_state(jgpu_handle* h)
     h->res_cap = std::max<size_t>(L, 64);
     if ((rc = h->alloc(&d.res_hdr, h->res_cap))) return rc;
     if ((rc = h->alloc(&d.res_words, h->res_cap * d.max_words))) return rc;
+    {
+        const int smem = 2 * h->S * JG_THREADS * (int)sizeof(float4);
+        cudaError_t e = cudaSuccess;
+        if (h->S == 5) {
+            e = cudaFuncSetAttribute(k_internal<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_internal<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        } else {
+            e = cudaFuncSetAttribute(k_internal<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_internal<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        }
+        if (e != cudaSuccess) return fail(JGPU_E_CUDA, "k_internal shared memory opt-in: %s", cudaGetErrorString(e));
+    }
     h->lanes.assign(L, LaneHost());
     h->host_epoch.assign(L, 0u);
     return JGPU_OK;
@@ -524,11 +545,19 @@ void apply_l2_window(jgpu_handle* h, cudaStream_t st)
     cudaGetLastError();   // best effort: never fatal
 }
 
+void drop_graphs(jgpu_handle* h)
+{
+    if (h->graph_step) cudaGraphExecDestroy(h->graph_step);
+    if (h->graph_block) cudaGraphExecDestroy(h->graph_block);
+    h->graph_step = h->graph_block = nullptr;
+}
+
 int ensure_results(jgpu_handle* h, size_t n)
 {
     if (n <= h->res_cap) return JGPU_OK;
     Dev& d = h->d;
     CK(cudaStreamSynchronize(h->stream));
+    drop_graphs(h);                                       // Dev (kernel argument) changes
     h->release(d.res_hdr);
     h->release(d.res_words);
     d.res_hdr = nullptr; d.res_words = nullptr;
@@ -565,7 +594,7 @@ int launch_gmm(jgpu_handle* h, const float* d_x, const int* d_rows, int n_rows, 
     return JGPU_OK;
 }
 
-int launch_step(jgpu_handle* h, int rel_step)
+int launch_step(jgpu_handle* h)
 {
     const Dev& d = h->d;
     const dim3 grid_huge(h->bpl, d.n_lanes);
@@ -578,15 +607,18 @@ int launch_step(jgpu_handle* h, int rel_step)
     }
 #endif
     h->prof_begin(JGPU_K_BOUNDARY);
-    k_boundary<<<d.n_lanes, 32, 0, h->stream>>>(d, rel_step, 1);
+    k_boundary<<<d.n_lanes, 32, 0, h->stream>>>(d);
     h->prof_end();
     h->prof_begin(JGPU_K_INTERNAL);
-    if (h->S == 5) {
-        if (d.fuse_exits) k_internal<5, true><<<d.grid_internal, JG_THREADS, 0, h->stream>>>(d);
-        else k_internal<5, false><<<d.grid_internal, JG_THREADS, 0, h->stream>>>(d);
-    } else {
-        if (d.fuse_exits) k_internal<8, true><<<d.grid_internal, JG_THREADS, 0, h->stream>>>(d);
-        else k_internal<8, false><<<d.grid_internal, JG_THREADS, 0, h->stream>>>(d);
+    {
+        const size_t smem = (size_t)2 * h->S * JG_THREADS * sizeof(float4);   // two chunk buffers: record + S-1 token planes
+        if (h->S == 5) {
+            if (d.fuse_exits) k_internal<5, true><<<d.grid_internal, JG_THREADS, smem, h->stream>>>(d);
+            else k_internal<5, false><<<d.grid_internal, JG_THREADS, smem, h->stream>>>(d);
+        } else {
+            if (d.fuse_exits) k_internal<8, true><<<d.grid_internal, JG_THREADS, smem, h->stream>>>(d);
+            else k_internal<8, false><<<d.grid_internal, JG_THREADS, smem, h->stream>>>(d);
+        }
     }
     h->prof_end();
     if (!d.fuse_exits) {
@@ -614,6 +646,31 @@ int launch_step(jgpu_handle* h, int rel_step)
     return JGPU_OK;
 }
 
+// The kernel sequence of `n` frame steps has no per-step argument (schedule rows, thresholds, list
+// sizes and round counts all live in device memory), so it is captured once and replayed as a CUDA
+// graph: the launch gaps between the 6-8 small kernels of a step shrink to the graph's node-to-node latency.
+int launch_steps_graph(jgpu_handle* h, int n)
+{
+    cudaGraphExec_t& exec = n == 1 ? h->graph_step : h->graph_block;
+    if (!exec) {
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        const int64_t before = h->launches;
+        int rc = JGPU_OK;
+        for (int i = 0; i < n && !rc; ++i) rc = launch_step(h);
+        h->launches = before;
+        cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(JGPU_E_CUDA, "graph capture: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { exec = nullptr; return fail(JGPU_E_CUDA, "graph instantiate: %s", cudaGetErrorString(e)); }
+    }
+    CK(cudaGraphLaunch(exec, h->stream));
+    h->launches += (int64_t)n * (3 + h->d.n_rounds + (h->d.fuse_exits ? 0 : 1) + (h->has_huge ? 1 : 0));
+    return JGPU_OK;
+}
+
 // Runs `n_steps` schedule rows (plus the trailing close-only row n_steps).
 // sched: (n_steps + 1) * n_lanes entries {feature row, -, flags, utt}; d_x: feature base.
 int run_schedule(jgpu_handle* h, const std::vector<int4>& sched, int n_steps, const float* d_x)
@@ -636,6 +693,7 @@ int run_schedule(jgpu_handle* h, const std::vector<int4>& sched, int n_steps, co
                 rows[(size_t)i * L + l] = ((e.z & 3) == JG_MODE_FRAME) ? e.x : -1;
             }
         CK(cudaMemcpyAsync(h->d_sched, chunk.data(), chunk.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemsetAsync(h->d.lane_step, 0, (size_t)L * sizeof(int), h->stream));
         if (ns) CK(cudaMemcpyAsync(h->d_rows, rows.data(), (size_t)ns * L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         CK(cudaEventRecord(h->ev_inputs, h->stream));            // features + row table are in place
         CK(cudaStreamWaitEvent(h->stream_gmm, h->ev_inputs, 0));
@@ -656,22 +714,38 @@ int run_schedule(jgpu_handle* h, const std::vector<int4>& sched, int n_steps, co
             if (b + 1 < n_blocks && (rc = issue_gmm(b + 1))) return rc;
             CK(cudaStreamWaitEvent(h->stream, h->ev_gmm[b & 1], 0));
             const int b0 = b * FB, nb = std::min(FB, ns - b0);
-            for (int i = b0; i < b0 + nb; ++i) {
-                // a lane's 11-bit epoch stamp is about to wrap: wipe its stamped tables (once per 2048 steps)
-                for (int l = 0; l < L; ++l) {
-                    if ((chunk[(size_t)i * L + l].z & 3) == JG_MODE_IDLE) continue;
-                    if (((++h->host_epoch[l]) & 0x7ffu) == 0u) {
-                        CK(cudaMemsetAsync(h->d.state_key + (size_t)l * d.n_states, 0, (size_t)d.n_states * sizeof(u64), h->stream));
-                        CK(cudaMemsetAsync(h->d.slotmap + (size_t)l * d.n_arcs, 0, (size_t)d.n_arcs * sizeof(unsigned), h->stream));
+            // a lane whose 11-bit epoch stamp wraps inside this block gets its stamped tables wiped right before
+            // that step (once per 2048 steps); such a block is launched step by step
+            bool wipe_in_block = false;
+            {
+                std::vector<unsigned> ep(h->host_epoch);
+                for (int i = b0; i < b0 + nb && !wipe_in_block; ++i)
+                    for (int l = 0; l < L; ++l)
+                        if ((chunk[(size_t)i * L + l].z & 3) != JG_MODE_IDLE && ((++ep[l]) & 0x7ffu) == 0u) { wipe_in_block = true; break; }
+            }
+            const bool graphs = h->use_graphs && !h->prof_on && !JG_TRACING(h);
+            if (graphs && nb == FB && !wipe_in_block) {
+                for (int i = b0; i < b0 + nb; ++i)
+                    for (int l = 0; l < L; ++l)
+                        if ((chunk[(size_t)i * L + l].z & 3) != JG_MODE_IDLE) ++h->host_epoch[l];
+                if ((rc = launch_steps_graph(h, nb))) return rc;
+            } else {
+                for (int i = b0; i < b0 + nb; ++i) {
+                    for (int l = 0; l < L; ++l) {
+                        if ((chunk[(size_t)i * L + l].z & 3) == JG_MODE_IDLE) continue;
+                        if (((++h->host_epoch[l]) & 0x7ffu) == 0u) {
+                            CK(cudaMemsetAsync(h->d.state_key + (size_t)l * d.n_states, 0, (size_t)d.n_states * sizeof(u64), h->stream));
+                            CK(cudaMemsetAsync(h->d.slotmap + (size_t)l * d.n_arcs, 0, (size_t)d.n_arcs * sizeof(unsigned), h->stream));
+                        }
                     }
+                    if ((rc = graphs ? launch_steps_graph(h, 1) : launch_step(h))) return rc;
                 }
-                if ((rc = launch_step(h, i))) return rc;
             }
             CK(cudaEventRecord(h->ev_search[b & 1], h->stream));
         }
         if (last) {
             h->prof_begin(JGPU_K_BOUNDARY);
-            k_boundary<<<L, 32, 0, h->stream>>>(d, ns, 1);   // close the last step, run pending finishes
+            k_boundary<<<L, 32, 0, h->stream>>>(d);          // close the last step, run pending finishes
             h->prof_end();
             ++h->launches;
             CK(cudaGetLastError());
@@ -756,7 +830,7 @@ int decode_common(jgpu_handle* h, const float* d_feats, const int64_t* row_offse
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
 #ifdef JG_TRACE
-    if (h->d_trace) {
+    if (h->d_trace && !h->prof_on) {                   // (the per-kernel event timing widens the launch gaps)
         unsigned n = 0;
         cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(unsigned));
         n = std::min(n, h->trace_cap);
@@ -843,6 +917,7 @@ int jgpu_create(const JgpuNet* net, const JgpuHmm* hmm, const JgpuGmm* gmm, cons
     h->cfg = *cfg;
     h->device = cfg->device;
     h->overlap = getenv("JUICER_B200_OVERLAP") && atoi(getenv("JUICER_B200_OVERLAP")) != 0;
+    if (const char* g = getenv("JUICER_B200_GRAPHS")) h->use_graphs = atoi(g) != 0;
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return fail(JGPU_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     e = cudaStreamCreateWithFlags(&h->stream_gmm, cudaStreamNonBlocking);
@@ -884,6 +959,7 @@ int jgpu_destroy(jgpu_handle* h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->stream_gmm) { cudaStreamSynchronize(h->stream_gmm); cudaStreamDestroy(h->stream_gmm); }
+    drop_graphs(h);
     if (h->ev_inputs) cudaEventDestroy(h->ev_inputs);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_gmm[i]) cudaEventDestroy(h->ev_gmm[i]);

@@ -21,7 +21,14 @@
 #include "jgpu_device.cuh"
 #include "jgpu_softplus_table.h"
 
-#define JG_GMM_RT 32          // feature rows per CTA tile
+#ifndef JG_GMM_RT
+#define JG_GMM_RT 64          // feature rows per CTA tile
+#endif
+#ifndef JG_GMM_UNROLL
+#define JG_GMM_UNROLL 4       // feature rows in flight per thread (independent accumulation chains)
+#endif
+#define JG_PRAGMA_(x) _Pragma(#x)
+#define JG_PRAGMA_UNROLL(n) JG_PRAGMA_(unroll n)
 #define JG_GMM_DMAX 64        // max feature dimension held in registers
 
 struct GmmDev {
@@ -121,7 +128,7 @@ k_gmm_scores(GmmDev g, const float* __restrict__ x, const int* __restrict__ rows
     __syncthreads();
     if (active) {
         const double ddet = (double)det;
-#pragma unroll 2
+JG_PRAGMA_UNROLL(JG_GMM_UNROLL)
         for (int r = 0; r < RT; ++r) {
             const float4* xr = reinterpret_cast<const float4*>(xs + r * DP);
             float s = 0.0f;

@@ -19,6 +19,9 @@
 #include "jgpu_device.cuh"
 
 #define JG_MAX_LANES 512
+#ifndef JG_INT_CTAS
+#define JG_INT_CTAS 3             // resident CTAs per SM of k_internal<5> (register budget 64 K / (256 * CTAs))
+#endif
 #define JG_CH JG_THREADS          // items per chunk
 
 // Per-lane views -------------------------------------------------------------------------
@@ -110,16 +113,6 @@ __device__ __forceinline__ int chunk_scan(LaneSh& sh, int L)
     }
     __syncthreads();
     return sh.pref[L];
-}
-
-__device__ __forceinline__ int lane_of_chunk(const int* pref, int L, int c)
-{
-    int lo = 0, hi = L;                                      // largest l with pref[l] <= c
-    while (lo + 1 < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (pref[mid] <= c) lo = mid; else hi = mid;
-    }
-    return lo;
 }
 
 __device__ __forceinline__ u64 warp_max_u64(u64 v)
@@ -232,14 +225,19 @@ __device__ float hist_thresh_warp(const Dev& d, const LaneView& v)
     return thr;
 }
 
-__global__ void __launch_bounds__(32) k_boundary(Dev d, int step, int open)
+// The schedule row is addressed by a per-lane device counter (reset by the host with every schedule
+// chunk), so that the launch has no per-step argument and a whole block of steps replays as one CUDA graph.
+__global__ void __launch_bounds__(32) k_boundary(Dev d)
 {
     const int lane = blockIdx.x;
+    int step = 0;
+    if (lane_id() == 0) step = d.lane_step[lane]++;
+    step = __shfl_sync(0xffffffffu, step, 0);
     LaneView v = lane_view(d, lane);
     LaneCtl* c = v.c;
     const int l = lane_id();
     const int prev_mode = c->mode;
-    const int4 s = open ? d.sched[(size_t)step * d.n_lanes + lane] : make_int4(-1, 0, 0, -1);
+    const int4 s = d.sched[(size_t)step * d.n_lanes + lane];
     const int mode = s.z & 3;
 
     // ---- (A) close the previous step ----------------------------------------------------
@@ -390,15 +388,37 @@ __device__ __forceinline__ float4 viterbi_into(const float4 (&src)[S], const flo
     return res;
 }
 
+// cp.async helpers: 16-byte global -> shared copies that bypass L1 and the register file; a thread
+// only ever reads back what it copied itself, so cp.async.wait_group is the only synchronisation.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Software pipeline over the CTA's chunks (chunk i = the i-th chunk this CTA owns):
+//   iteration i:  registers <- shared buffer (i & 1)          [chunk i: instance record + token planes]
+//                 cp.async chunk i+2 -> shared buffer (i & 1)  [one chunk of HBM latency ahead]
+//                 wait for chunk i+1's copies, read its HMM ids, issue its hmm_info gathers
+//                 Viterbi + pruning of chunk i
+//                 issue chunk i+1's acoustic-score gathers (its hmm_info has landed by now)
+//                 block-wide slot allocation (2 atomics per chunk) + counters, stores of chunk i
+// so the only memory latency a chunk still waits for is that of its own two allocation atomics.
 template <int S, bool FUSE>
-__global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? 4 : 2)) k_internal(Dev d)
+__global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_internal(Dev d)
 {
     JG_TRACE_SCOPE(JGPU_K_INTERNAL, 0);
+    constexpr int P = S - 1;
+    constexpr int NW = JG_THREADS / 32;
     __shared__ LaneSh sh;
-    __shared__ float sh_best[2][JG_THREADS / 32];
-    __shared__ int sh_red[2][3][JG_THREADS / 32];
+    __shared__ int sh_w[NW][4];                               // per warp: survivors, exits, packed counters, best
+    __shared__ int sh_base[2];
+    extern __shared__ float4 stage[];                         // [2][P + 1][JG_THREADS]; plane 0 = instance record
     const int L = d.n_lanes;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, wid = tid >> 5;
     for (int l = tid; l < L; l += blockDim.x) {
         const LaneCtl* c = d.ctl + l;
         sh.cnt[l] = c->mode == JG_MODE_FRAME ? c->n_cur : 0;
@@ -408,48 +428,98 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? 4 : 2)) k_internal(Dev d
     }
     const int total = chunk_scan(sh, L);
     const size_t cap = (size_t)d.cap;
-    constexpr int P = S - 1;
     const bool hist_on = d.max_hyps > 0;
-    int par = 0;
+    const int G = gridDim.x;
 
-    for (int ch = blockIdx.x; ch < total; ch += gridDim.x, par ^= 1) {
-        const int lane = lane_of_chunk(sh.pref, L, ch);
-        const int k = (ch - sh.pref[lane]) * JG_CH + tid;
-        const bool valid = k < sh.cnt[lane];
+    // copies of chunk `ch` (lane `ln`) into buffer `buf`; returns whether this thread has an instance there
+    auto issue = [&](int ch, int ln, int buf) -> bool {
+        bool v = false;
+        if (ch < total) {
+            const int k = (ch - sh.pref[ln]) * JG_CH + tid;
+            if (k < sh.cnt[ln]) {
+                v = true;
+                const int flip = sh.i1[ln];
+                const int4* meta_cur = d.inst_meta + ((size_t)ln * 2 + flip) * cap;
+                const float4* tok_cur = d.tok + ((size_t)ln * 2 + flip) * P * cap;
+                float4* dst = stage + (size_t)buf * (P + 1) * JG_THREADS + tid;
+                cp_async16(dst, meta_cur + k);
+#pragma unroll
+                for (int i = 0; i < P; ++i) cp_async16(dst + (i + 1) * JG_THREADS, tok_cur + (size_t)i * cap + k);
+            }
+        }
+        cp_async_commit();
+        return v;
+    };
+    auto lane_of = [&](int ch, int ln) -> int {               // chunks come in increasing order; pref[L] = total
+        if (ch < total)
+            while (sh.pref[ln + 1] <= ch) ++ln;
+        return ln;
+    };
+
+    int ch = blockIdx.x;
+    int lane = lane_of(ch, 0);
+    int lane1 = lane_of(ch + G, lane), lane2 = lane1;
+    bool valid = issue(ch, lane, 0);
+    bool valid1 = issue(ch + G, lane1, 1);
+    // hmm_info + scores of the first chunk (exposed once per CTA)
+    int4 h0 = make_int4(2, 0, 0, 0), h1 = make_int4(0, 0, 0, 0);
+    float outp[S - 2];
+#pragma unroll
+    for (int j = 0; j < S - 2; ++j) outp[j] = 0.0f;
+    cp_async_wait<1>();
+    if (valid) {
+        const int hmm = reinterpret_cast<const int4*>(stage)[tid].y & ~JG_FRESH;
+        h0 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2);
+        h1 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2 + 1);
+        const float* __restrict__ scores = d.scores + (size_t)sh.i0[lane] * d.n_gmms;
+        const int gm[6] = {h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const int nst0 = h0.x & 0xff;
+#pragma unroll
+        for (int j = 1; j < S - 1; ++j) outp[j - 1] = j < nst0 - 1 ? __ldg(scores + gm[j - 1]) : 0.0f;
+    }
+
+    for (int it = 0; ch < total; ++it, ch += G) {
+        const int buf = it & 1;
         const float norm = sh.f0[lane], thr_emit = sh.f1[lane], thr_start = sh.f2[lane];
         const unsigned epoch = sh.epoch[lane];
         const int flip = sh.i1[lane];
         LaneCtl* c = d.ctl + lane;
-        const int4* meta_cur = d.inst_meta + ((size_t)lane * 2 + flip) * cap;
-        int4* meta_nxt = d.inst_meta + ((size_t)lane * 2 + (flip ^ 1)) * cap;
-        const float4* tok_cur = d.tok + ((size_t)lane * 2 + flip) * P * cap;
-        float4* tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * P * cap;
-        const float* __restrict__ scores = d.scores + (size_t)sh.i0[lane] * d.n_gmms;
+        // ---- registers <- buffer (chunk i) ----
+        int4 meta = make_int4(0, 0, 0, 0);
+        float4 old[S];
+#pragma unroll
+        for (int i = 0; i < S; ++i) old[i] = null_tok();
+        if (valid) {
+            const float4* src = stage + (size_t)buf * (P + 1) * JG_THREADS + tid;
+            meta = *reinterpret_cast<const int4*>(src);
+            old[0] = src[JG_THREADS];
+            if (!(meta.y & JG_FRESH)) {                        // a FRESH instance only has its entry token
+#pragma unroll
+                for (int i = 1; i < P; ++i) old[i] = src[(i + 1) * JG_THREADS];
+            }
+        }
+        // ---- chunk i+2 -> the buffer just read; chunk i+1 has landed: start its hmm_info gathers ----
+        lane2 = lane_of(ch + 2 * G, lane1);
+        const bool valid2 = issue(ch + 2 * G, lane2, buf);
+        cp_async_wait<1>();
+        int4 n0 = make_int4(2, 0, 0, 0), n1 = make_int4(0, 0, 0, 0);
+        if (valid1) {
+            const int hmm = reinterpret_cast<const int4*>(stage + (size_t)(buf ^ 1) * (P + 1) * JG_THREADS)[tid].y & ~JG_FRESH;
+            n0 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2);
+            n1 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2 + 1);
+        }
+
+        // ---- HMMInternalPropagation of chunk i ----
         float best = JG_LZ;
         int cnt_emit = 0, cnt_end = 0, cnt_hist = 0;
-
         bool survive = false, has_exit = false;
-        int nst = 2;
-        int4 meta = make_int4(0, 0, 0, 0);
+        const int nst = h0.x & 0xff;
         float4 nt[S];
         float4 ex = null_tok();
 #pragma unroll
         for (int i = 0; i < S; ++i) nt[i] = null_tok();
         if (valid) {
-            // every load of the instance is issued before anything depends on one of them
-            meta = ld_stream(meta_cur + k);
-            float4 old[S];
-            old[0] = ld_stream(tok_cur + k);
-            const bool fresh = (meta.y & JG_FRESH) != 0;
-#pragma unroll
-            for (int i = 1; i < P; ++i) old[i] = fresh ? null_tok() : ld_stream(tok_cur + (size_t)i * cap + k);
-            old[S - 1] = null_tok();
-            const int hmm = meta.y & ~JG_FRESH;
-            const int4 h0 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2);
-            const int4 h1 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2 + 1);
-            nst = h0.x & 0xff;
             const int cls = (h0.x & ~JG_LR_CLASS) >> 8;
-            const int gm[6] = {h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
             for (int i = 1; i < P; ++i)
                 if (i >= nst - 1) old[i] = null_tok();        // planes beyond this HMM's states hold stale data
@@ -485,7 +555,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? 4 : 2)) k_internal(Dev d
                     }
                     res.x = res.x - norm;                                          // :408
                     if (res.x > thr_emit) {
-                        const float o = __ldg(scores + gm[j - 1]);                 // calcOutput :411
+                        const float o = outp[j - 1];                               // calcOutput :411
                         res.x = res.x + o;
                         res.y = res.y + o;
                         if (hist_on) {                                             // Histogram::addScore
@@ -516,12 +586,47 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? 4 : 2)) k_internal(Dev d
                 if (res.x > JG_LZ) { ex = res; has_exit = true; ++cnt_end; }
             }
         }
-        // survivors -> next list (warp-ballot compaction); instances that die simply stop
-        // being listed: their slotmap entry goes stale with the epoch (:924-925).
-        // exit tokens -> arrival records of expansion round 0.
-        int pos, e;
-        warp_alloc2(&c->n_next, survive, &c->n_arr[0], has_exit, pos, e);
+        // ---- chunk i+1: its hmm_info has landed, start its acoustic-score gathers ----
+        h0 = n0; h1 = n1;
+        if (valid1) {
+            const float* __restrict__ scores = d.scores + (size_t)sh.i0[lane1] * d.n_gmms;
+            const int gm[6] = {h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            const int nstn = h0.x & 0xff;
+#pragma unroll
+            for (int j = 1; j < S - 1; ++j) outp[j - 1] = j < nstn - 1 ? __ldg(scores + gm[j - 1]) : 0.0f;
+        }
+        // ---- block-wide allocation: survivors -> next list, exit tokens -> arrival records of round 0;
+        //      instances that die simply stop being listed, their slotmap entry goes stale with the epoch (:924-925)
+        const unsigned m_s = __ballot_sync(0xffffffffu, survive), m_e = __ballot_sync(0xffffffffu, has_exit);
+        const unsigned best_o = __reduce_max_sync(0xffffffffu, f2o(best));
+        const unsigned packed = __reduce_add_sync(0xffffffffu, (unsigned)cnt_emit | ((unsigned)cnt_hist << 16));
+        if (lane_id() == 0) { sh_w[wid][0] = __popc(m_s); sh_w[wid][1] = __popc(m_e); sh_w[wid][2] = (int)packed; sh_w[wid][3] = (int)best_o; }
+        __syncthreads();
+        if (tid == 0) {
+            int ns = 0, ne = 0, n_emit = 0, n_hist = 0;
+            unsigned bo = 0;
+            for (int w = 0; w < NW; ++w) {
+                const int a = sh_w[w][0], b = sh_w[w][1];
+                sh_w[w][0] = ns; sh_w[w][1] = ne;             // exclusive offsets of the warp
+                ns += a; ne += b;
+                n_emit += sh_w[w][2] & 0xffff; n_hist += (unsigned)sh_w[w][2] >> 16;
+                bo = max(bo, (unsigned)sh_w[w][3]);
+            }
+            sh_base[0] = ns ? atomicAdd(&c->n_next, ns) : 0;
+            sh_base[1] = ne ? atomicAdd(&c->n_arr[0], ne) : 0;
+            if (bo > f2o(JG_LZ)) atomicMax(&c->best_int, bo);
+            if (n_emit) atomicAdd(&c->c_active_emit, n_emit);
+            if (ne) atomicAdd(&c->c_active_end, ne);
+            if (FUSE && ne) atomicAdd(&c->c_end_proc, ne);
+            if (n_hist) atomicAdd(&c->hist_count, n_hist);
+        }
+        __syncthreads();
+        const unsigned lt = (1u << lane_id()) - 1u;
+        const int pos = sh_base[0] + sh_w[wid][0] + __popc(m_s & lt);
+        const int e = sh_base[1] + sh_w[wid][1] + __popc(m_e & lt);
         if (survive && pos < d.cap) {
+            int4* meta_nxt = d.inst_meta + ((size_t)lane * 2 + (flip ^ 1)) * cap;
+            float4* tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * P * cap;
             st_stream(meta_nxt + pos, make_int4(meta.x, meta.y & ~JG_FRESH, meta.z, meta.w));
             tok_nxt[pos] = null_tok();                    // entry token consumed (:426-435); k_walk<1> may overwrite it
 #pragma unroll
@@ -537,28 +642,12 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? 4 : 2)) k_internal(Dev d
                 atomicMax(d.state_key + (size_t)lane * d.n_states + (meta.z & 0x7fffffff),
                           state_key_of(epoch, ex.x, (unsigned)e));
         }
-        // per-chunk block reductions
-        for (int o = 16; o > 0; o >>= 1) {
-            best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
-            cnt_emit += __shfl_xor_sync(0xffffffffu, cnt_emit, o);
-            cnt_end += __shfl_xor_sync(0xffffffffu, cnt_end, o);
-            cnt_hist += __shfl_xor_sync(0xffffffffu, cnt_hist, o);
-        }
-        const int w = tid >> 5;
-        if (lane_id() == 0) { sh_best[par][w] = best; sh_red[par][0][w] = cnt_emit; sh_red[par][1][w] = cnt_end; sh_red[par][2][w] = cnt_hist; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int i = 1; i < JG_THREADS / 32; ++i) {
-                best = fmaxf(best, sh_best[par][i]);
-                cnt_emit += sh_red[par][0][i]; cnt_end += sh_red[par][1][i]; cnt_hist += sh_red[par][2][i];
-            }
-            if (best > JG_LZ) atomicMax(&c->best_int, f2o(best));
-            if (cnt_emit) atomicAdd(&c->c_active_emit, cnt_emit);
-            if (cnt_end) atomicAdd(&c->c_active_end, cnt_end);
-            if (FUSE && cnt_end) atomicAdd(&c->c_end_proc, cnt_end);
-            if (cnt_hist) atomicAdd(&c->hist_count, cnt_hist);
-        }
+        // (no barrier needed here: a warp only rewrites its own sh_w row, and thread 0 rewrites the offsets and
+        //  sh_base after the next chunk's first barrier, which every warp reaches after reading its positions)
+        lane = lane1; lane1 = lane2;
+        valid = valid1; valid1 = valid2;
     }
+    cp_async_wait<0>();
 }
 
 // =========================================================================================
@@ -580,8 +669,9 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_filter(Dev d)
         sh.epoch[l] = c->epoch;
     }
     const int total = chunk_scan(sh, L);
+    int lane = 0;
     for (int ch = blockIdx.x; ch < total; ch += gridDim.x) {
-        const int lane = lane_of_chunk(sh.pref, L, ch);
+        while (sh.pref[lane + 1] <= ch) ++lane;
         const int e = (ch - sh.pref[lane]) * JG_CH + tid;
         int proc = 0;
         if (e < sh.cnt[lane]) {
@@ -715,8 +805,9 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
     }
     const int total_chunks = chunk_scan(sh, L);
 
+    int lane = 0;
     for (int ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
-        const int lane = lane_of_chunk(sh.pref, L, ch);
+        while (sh.pref[lane + 1] <= ch) ++lane;
         LaneCtl* c = d.ctl + lane;
         const unsigned epoch = sh.epoch[lane];
         const float thr_end = sh.f0[lane], thr_word = sh.f1[lane];
