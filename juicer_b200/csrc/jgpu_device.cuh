@@ -73,8 +73,10 @@ struct Arrival {          // 32 B: one sector
 #define JG_FRESH 0x40000000   // inst_meta.y flag: only the entry token of this instance is valid
 
 struct LaneCtl {
-    int n_cur, n_next, n_huge, n_paths, flip;
+    int n_cur, n_huge, n_paths, flip;
     unsigned epoch;           // advances every non-idle step of this lane, never repeats
+    int pad0_;
+    int n_next;               // (n_next, n_arr[0]) sit in one aligned 64-bit word: k_internal bumps both with one atomic
     int n_arr[JG_MAX_ROUNDS + 2];    // arrivals feeding expansion round k (records are stored back to back)
     unsigned best_int;        // orderable max of emitting scores of this frame   (WFSTDecoderLite.cpp:417-418)
     unsigned best_ext;        // orderable max of entry scores of this frame      (:572-573)
@@ -95,7 +97,7 @@ struct Dev {
     const int4*  arcs;
     const int4*  states;       // {first arc, n arcs, final weight bits, n_eps | n_tee << 16}
     const float* arc_tee;      // per-arc tee weight of the arc's HMM, nullptr when no tee model exists
-    const int*   hmm_info;     // [n_hmms][8] : nst | class<<8, tee bits, gmm of states 1..6
+    const int*   hmm_info;     // [n_hmms][8] : nst | class<<8, gmm of states 1..3 | tee bits, gmm of states 4..6
     const float* trp;          // [n_class][S*S]
     const int2*  se;           // [n_class][S]
     const float4* lr;          // [n_class][2]: left-to-right classes {a01,a11,a12,a22 | a23,a33,a34,-}
@@ -107,7 +109,7 @@ struct Dev {
     int n_lanes, cap, cap_arr, cap_paths, cap_huge, n_rounds, max_frames, frame_stats, max_words;
     int huge_deg;
     int fuse_exits;                  // no end / word beam: exit tokens become arrivals inside k_internal
-    int grid_internal, grid_other;   // CTAs of the chunk-scheduled kernels
+    int grid_internal, grid_other, grid_walk;   // CTAs of the chunk-scheduled kernels
     // per-lane state
     LaneCtl*  ctl;
     int4*     inst_meta;

@@ -359,8 +359,8 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
         int teebits;
         memcpy(&teebits, &m->tee[i], 4);
         info[(size_t)i * 8 + 0] = ns | (cls << 8) | (is_lr ? JG_LR_CLASS : 0);
-        info[(size_t)i * 8 + 1] = teebits;
-        for (int s = 1; s < ns - 1; ++s) info[(size_t)i * 8 + 1 + s] = m->gmm[i * M + s];
+        info[(size_t)i * 8 + 4] = teebits;                // {nst | class, gmm 1..3 | tee, gmm 4..6}: <= 5-state HMMs need one int4
+        for (int s = 1; s < ns - 1; ++s) info[(size_t)i * 8 + (s <= 3 ? s : s + 1)] = m->gmm[i * M + s];
     }
 
     int rc;
@@ -461,7 +461,8 @@ int build_state(jgpu_handle* h)
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
         d.grid_internal = n_sm * (h->S <= 5 ? JG_INT_CTAS : 2);   // __launch_bounds__ of k_internal
-        d.grid_other = n_sm * 6;                       // __launch_bounds__(256, 6)
+        d.grid_other = n_sm * 6;                       // __launch_bounds__(256, 6): k_filter
+        d.grid_walk = n_sm * 6;                        // __launch_bounds__(256, 6): k_walk
     }
 
     const size_t cap = d.cap, P = d.S - 1;
@@ -629,11 +630,11 @@ int launch_step(jgpu_handle* h)
     }
     for (int r = 0; r < d.n_rounds; ++r) {
         h->prof_begin(r == 0 ? JGPU_K_EXPAND : r == 1 ? JGPU_K_EXPAND_R1 : JGPU_K_EXPAND_R2);
-        k_walk<0><<<d.grid_other, JG_THREADS, 0, h->stream>>>(d, r);
+        k_walk<0><<<d.grid_walk, JG_THREADS, 0, h->stream>>>(d, r);
         h->prof_end();
     }
     h->prof_begin(JGPU_K_COMMIT);
-    k_walk<1><<<d.grid_other, JG_THREADS, 0, h->stream>>>(d, 0);
+    k_walk<1><<<d.grid_walk, JG_THREADS, 0, h->stream>>>(d, 0);
     h->prof_end();
     if (h->has_huge) {
         h->prof_begin(JGPU_K_EXPAND_HUGE);

@@ -6,7 +6,8 @@
 // Exactness rules:
 //   * the d-sum is a sequential fp32 accumulation with separate sub, mul, mul, add — written
 //     with __fsub_rn/__fmul_rn/__fadd_rn so ptxas can never contract it into an FMA;
-//   * "-0.5*sumxmu + det" is evaluated in double and narrowed once (:254);
+//   * "-0.5*sumxmu + det" (double, narrowed once, :254) is evaluated as fadd(fmul(-0.5f, s), det), which is
+//     bit-identical for every pair of floats (see the comment at the store);
 //   * components are folded in order 0..n-1 by logAdd: float diff, double threshold -18.42,
 //     double log(1.0 + exp(diff)), narrowed once (:289).  No tree reduction anywhere.
 // Parallelism comes from (Gaussians) x (feature rows), never from inside one Gaussian.
@@ -127,7 +128,6 @@ k_gmm_scores(GmmDev g, const float* __restrict__ x, const int* __restrict__ rows
     }
     __syncthreads();
     if (active) {
-        const double ddet = (double)det;
 JG_PRAGMA_UNROLL(JG_GMM_UNROLL)
         for (int r = 0; r < RT; ++r) {
             const float4* xr = reinterpret_cast<const float4*>(xs + r * DP);
@@ -143,7 +143,11 @@ JG_PRAGMA_UNROLL(JG_GMM_UNROLL)
                     s = __fadd_rn(s, __fmul_rn(__fmul_rn(xmu, xmu), iv[d]));
                 }
             }
-            vals[c * cstride + r * gpb + gl] = (float)(-0.5 * (double)s + ddet);
+            // the reference evaluates -0.5*s + det in double and narrows (:254).  The fp32 form below is the same
+            // value bit for bit: -0.5f*s is exact, and the sum of two floats rounded to double and then to float
+            // equals the sum rounded to float directly — exact in double when the exponents differ by <= 29, and
+            // beyond that both roundings return the larger operand.
+            vals[c * cstride + r * gpb + gl] = __fadd_rn(__fmul_rn(-0.5f, s), det);
         }
     }
     __syncthreads();

@@ -37,10 +37,10 @@ struct LaneView {
     int* hist;
 };
 
-__device__ __forceinline__ LaneView lane_view(const Dev& d, int lane)
+__device__ __forceinline__ LaneView lane_view(const Dev& d, int lane, LaneCtl* ctl = nullptr)
 {
     LaneView v;
-    v.c = d.ctl + lane;
+    v.c = ctl ? ctl : d.ctl + lane;
     const int flip = v.c->flip;
     const size_t cap = (size_t)d.cap, P = (size_t)(d.S - 1);
     v.meta_cur = d.inst_meta + ((size_t)lane * 2 + flip) * cap;
@@ -92,7 +92,7 @@ struct LaneSh {                   // per-CTA shared copy of what a chunk needs t
 };
 
 // sh.cnt[] must be filled (and __syncthreads() NOT yet called); returns the number of chunks
-__device__ __forceinline__ int chunk_scan(LaneSh& sh, int L)
+__device__ __forceinline__ int chunk_scan(LaneSh& sh, int L, int items = JG_CH)
 {
     __syncthreads();
     if (threadIdx.x < 32) {                                  // warp 0: scan L values, L/32 per thread
@@ -100,7 +100,7 @@ __device__ __forceinline__ int chunk_scan(LaneSh& sh, int L)
         const int b = threadIdx.x * per;
         int sum = 0;
         for (int i = 0; i < per; ++i)
-            if (b + i < L) sum += (sh.cnt[b + i] + JG_CH - 1) / JG_CH;
+            if (b + i < L) sum += (sh.cnt[b + i] + items - 1) / items;
         int incl = sum;
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -109,7 +109,7 @@ __device__ __forceinline__ int chunk_scan(LaneSh& sh, int L)
         int run = incl - sum;
         if (threadIdx.x == 0) sh.pref[0] = 0;
         for (int i = 0; i < per; ++i)
-            if (b + i < L) { run += (sh.cnt[b + i] + JG_CH - 1) / JG_CH; sh.pref[b + i + 1] = run; }
+            if (b + i < L) { run += (sh.cnt[b + i] + items - 1) / items; sh.pref[b + i + 1] = run; }
     }
     __syncthreads();
     return sh.pref[L];
@@ -230,12 +230,22 @@ __device__ float hist_thresh_warp(const Dev& d, const LaneView& v)
 __global__ void __launch_bounds__(32) k_boundary(Dev d)
 {
     const int lane = blockIdx.x;
-    int step = 0;
-    if (lane_id() == 0) step = d.lane_step[lane]++;
-    step = __shfl_sync(0xffffffffu, step, 0);
-    LaneView v = lane_view(d, lane);
-    LaneCtl* c = v.c;
     const int l = lane_id();
+    int step = 0;
+    if (l == 0) step = d.lane_step[lane]++;
+    // the lane's control block is worked on in shared memory (one coalesced read, one coalesced write back):
+    // this kernel is a long chain of dependent scalar accesses to it
+    __shared__ LaneCtl sc;
+    static_assert(sizeof(LaneCtl) % 4 == 0, "LaneCtl is copied word by word");
+    {
+        const int* src = reinterpret_cast<const int*>(d.ctl + lane);
+        int* dst = reinterpret_cast<int*>(&sc);
+        for (int i = l; i < (int)(sizeof(LaneCtl) / 4); i += 32) dst[i] = src[i];
+    }
+    step = __shfl_sync(0xffffffffu, step, 0);
+    __syncwarp();
+    LaneView v = lane_view(d, lane, &sc);
+    LaneCtl* c = v.c;
     const int prev_mode = c->mode;
     const int4 s = d.sched[(size_t)step * d.n_lanes + lane];
     const int mode = s.z & 3;
@@ -348,6 +358,12 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
     }
     if (mode == JG_MODE_SEED && d.max_hyps > 0)
         for (int b = l; b < d.hist_nbins; b += 32) v.hist[b] = 0;
+    __syncwarp();
+    {
+        const int* src = reinterpret_cast<const int*>(&sc);
+        int* dst = reinterpret_cast<int*>(d.ctl + lane);
+        for (int i = l; i < (int)(sizeof(LaneCtl) / 4); i += 32) dst[i] = src[i];
+    }
 }
 
 // =========================================================================================
@@ -450,15 +466,29 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         cp_async_commit();
         return v;
     };
-    auto lane_of = [&](int ch, int ln) -> int {               // chunks come in increasing order; pref[L] = total
+    // lane of this CTA's i-th chunk (chunk blockIdx.x + i * G), looked up once
+    __shared__ unsigned short my_lane[JG_THREADS];
+    {
+        const int c_t = blockIdx.x + tid * G;
+        int lo = 0, hi = L;                                   // largest l with pref[l] <= c_t
+        if (c_t < total)
+            while (lo + 1 < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (sh.pref[mid] <= c_t) lo = mid; else hi = mid;
+            }
+        my_lane[tid] = (unsigned short)lo;
+    }
+    __syncthreads();
+    auto lane_of = [&](int i, int ch, int ln) -> int {
+        if (i < JG_THREADS) return my_lane[i];
         if (ch < total)
-            while (sh.pref[ln + 1] <= ch) ++ln;
+            while (sh.pref[ln + 1] <= ch) ++ln;               // (more than 256 chunks per CTA: walk on)
         return ln;
     };
 
     int ch = blockIdx.x;
-    int lane = lane_of(ch, 0);
-    int lane1 = lane_of(ch + G, lane), lane2 = lane1;
+    int lane = lane_of(0, ch, 0);
+    int lane1 = lane_of(1, ch + G, lane), lane2 = lane1;
     bool valid = issue(ch, lane, 0);
     bool valid1 = issue(ch + G, lane1, 1);
     // hmm_info + scores of the first chunk (exposed once per CTA)
@@ -470,9 +500,9 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
     if (valid) {
         const int hmm = reinterpret_cast<const int4*>(stage)[tid].y & ~JG_FRESH;
         h0 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2);
-        h1 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2 + 1);
+        if (S > 5) h1 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2 + 1);
         const float* __restrict__ scores = d.scores + (size_t)sh.i0[lane] * d.n_gmms;
-        const int gm[6] = {h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const int gm[6] = {h0.y, h0.z, h0.w, h1.y, h1.z, h1.w};
         const int nst0 = h0.x & 0xff;
 #pragma unroll
         for (int j = 1; j < S - 1; ++j) outp[j - 1] = j < nst0 - 1 ? __ldg(scores + gm[j - 1]) : 0.0f;
@@ -499,14 +529,14 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
             }
         }
         // ---- chunk i+2 -> the buffer just read; chunk i+1 has landed: start its hmm_info gathers ----
-        lane2 = lane_of(ch + 2 * G, lane1);
+        lane2 = lane_of(it + 2, ch + 2 * G, lane1);
         const bool valid2 = issue(ch + 2 * G, lane2, buf);
         cp_async_wait<1>();
         int4 n0 = make_int4(2, 0, 0, 0), n1 = make_int4(0, 0, 0, 0);
         if (valid1) {
             const int hmm = reinterpret_cast<const int4*>(stage + (size_t)(buf ^ 1) * (P + 1) * JG_THREADS)[tid].y & ~JG_FRESH;
             n0 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2);
-            n1 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2 + 1);
+            if (S > 5) n1 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2 + 1);
         }
 
         // ---- HMMInternalPropagation of chunk i ----
@@ -590,7 +620,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         h0 = n0; h1 = n1;
         if (valid1) {
             const float* __restrict__ scores = d.scores + (size_t)sh.i0[lane1] * d.n_gmms;
-            const int gm[6] = {h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            const int gm[6] = {h0.y, h0.z, h0.w, h1.y, h1.z, h1.w};
             const int nstn = h0.x & 0xff;
 #pragma unroll
             for (int j = 1; j < S - 1; ++j) outp[j - 1] = j < nstn - 1 ? __ldg(scores + gm[j - 1]) : 0.0f;
