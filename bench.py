@@ -183,30 +183,31 @@ def run_reference(args) -> None:
 # ---------------------------------------------------------------------------------------
 def algorithmic_bytes(stats: Dict[str, int], dims: Dict[str, int], n_rows: int) -> Dict[str, float]:
     """Algorithmic bytes moved by each kernel over one whole step, from the decoder's own work
-    counters and the device record sizes of DESIGN.md ("Kernels"): instance meta 8 B, token 16 B,
-    exit record 20 B, arrival record 32 B, state key 8 B, arc row entry 16 B, per-arc dynamic
-    record 16 B, word-boundary record 32 B.  Minimal traffic: every record counted once."""
+    counters and the device record sizes of DESIGN.md ("Kernels"): instance record 16 B, token 16 B,
+    arrival record 32 B, state row 16 B, arc 16 B, slotmap entry 4 B, word-boundary record 32 B.
+    Minimal traffic: every record counted once."""
     A = stats["total_active_models"]          # instances walked by the internal phase (sum over frames)
     H = stats["total_active_emit_hyps"]       # live emitting tokens after the internal phase
-    Ea = stats["total_active_end_hyps"]       # live exit tokens
+    Ea = stats["total_active_end_hyps"]       # live exit tokens = arrival records written by k_internal
     E = stats["total_proc_end_hyps"]          # exit tokens passing the end/word beam = first-round arrivals
-    X = stats["total_arcs_expanded"]          # out-arcs of the distinct states expanded
+    X = stats["total_arcs_expanded"]          # out-arcs of the states committed (hub rows included)
     W = stats["total_entry_writes"]           # distinct destination arcs whose entry token was written
     P = stats["total_paths"]                  # word-boundary records appended
     D, G, M = dims["D"], dims["n_gmm"], dims["C"]
     return {
-        # read meta + entry token per instance, emitting tokens read + written, GMM score per live token,
-        # exit records written
-        "k_internal": A * (8 + 16) + H * (16 + 16 + 4) + Ea * 20,
-        # exit records read, arc record, arrival record + state key written
-        "k_seed": Ea * 20 + E * (16 + 32 + 8),
-        # arrival record + state key read per expanded record, arc rows, candidate keys, path records
-        "k_expand": E * (32 + 8) + X * 16 + X * 8 + P * 32,
-        "k_expand_huge": 0.0,                 # its arc rows are counted in k_expand's X
-        "k_expand_r1": 0.0, "k_expand_r2": 0.0,   # later rounds: their bytes are counted in k_expand (round 0 row)
-        # second walk: arrival record + state key, arc rows, per-arc dynamic record; winners write
-        # the dynamic record, the entry token and the instance meta
-        "k_commit": E * (32 + 8) + X * 16 + X * 16 + W * (16 + 16 + 8),
+        # instance record + entry token read per instance; emitting tokens read + written, one acoustic score
+        # per live token; one arrival record per live exit token
+        "k_internal": A * (16 + 16) + H * (16 + 16 + 4) + Ea * 32,
+        # (only with an end / word beam) arrival records re-read and filtered
+        "k_seed": Ea * 16,
+        # expansion round 0: arrival record + state row per record, word-boundary records
+        "k_expand": E * (32 + 16) + P * 32,
+        "k_expand_r1": 0.0, "k_expand_r2": 0.0,   # later rounds: a few hundred records per step
+        # commit: arrival record + state row per record, arc + slotmap entry per arc walked, entry token +
+        # instance record + slotmap entry per entry written (rows of hub-like states are walked by
+        # k_commit_huge, timed as k_expand_huge; their bytes are counted here)
+        "k_commit": E * (32 + 16) + X * (16 + 4) + W * (16 + 16 + 4),
+        "k_expand_huge": 0.0,
         "k_boundary": 0.0,
         # one parameter pass per launch (frames x lanes rows share it) + features in, scores out
         "k_gmm_scores": dims["gmm_launches"] * G * M * (2 * D + 1) * 4 + n_rows * (D * 4 + G * 4),

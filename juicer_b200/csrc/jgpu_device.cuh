@@ -131,31 +131,48 @@ struct Dev {
 
 // ---- optional CTA timeline (compile with -DJG_TRACE; see tools/trace_report.py) -----------
 #ifdef JG_TRACE
-struct TraceRec { int kid, block, smid, aux; unsigned long long t0, t1; };
+#define JG_TRACE_MARKS 8
+struct TraceRec { int kid, block, smid, aux; unsigned long long t0, t1; unsigned mark[JG_TRACE_MARKS]; };   // marks: SM cycles after CTA start
 __device__ TraceRec* g_trace;
 __device__ unsigned g_trace_n, g_trace_cap;
 __device__ int g_trace_on;
+__device__ __forceinline__ unsigned long long jg_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 struct TraceScope {
-    unsigned long long t0; int kid, aux;
+    unsigned long long t0; long long c0; int kid, aux; unsigned mark[JG_TRACE_MARKS];
     __device__ __forceinline__ TraceScope(int k, int a) : kid(k), aux(a)
     {
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        t0 = jg_now();
+        c0 = clock64();
+        for (int i = 0; i < JG_TRACE_MARKS; ++i) mark[i] = 0;
     }
+    // stamp `i` of thread 0 in SM cycles since CTA start (kept the first time it is reached; globaltimer ticks too coarsely)
+    __device__ __forceinline__ void at(int i) { if (threadIdx.x == 0 && mark[i] == 0) mark[i] = (unsigned)(clock64() - c0); }
     __device__ __forceinline__ ~TraceScope()
     {
         __syncthreads();
         if (threadIdx.x == 0 && g_trace_on) {
-            unsigned long long t1; unsigned smid;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            const unsigned long long t1 = jg_now();
+            unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
             const unsigned i = atomicAdd(&g_trace_n, 1u);
-            if (i < g_trace_cap) { TraceRec r; r.kid = kid; r.block = blockIdx.x + blockIdx.y * gridDim.x; r.smid = (int)smid; r.aux = aux; r.t0 = t0; r.t1 = t1; g_trace[i] = r; }
+            if (i < g_trace_cap) {
+                TraceRec r; r.kid = kid; r.block = blockIdx.x + blockIdx.y * gridDim.x; r.smid = (int)smid; r.aux = aux; r.t0 = t0; r.t1 = t1;
+                for (int k = 0; k < JG_TRACE_MARKS; ++k) r.mark[k] = mark[k];
+                g_trace[i] = r;
+            }
         }
     }
 };
 #define JG_TRACE_SCOPE(k, a) TraceScope _trace_scope(k, a)
+#define JG_TRACE_AT(i) _trace_scope.at(i)
 #else
 #define JG_TRACE_SCOPE(k, a)
+#define JG_TRACE_AT(i)
 #endif
 
 // ---- small helpers ----------------------------------------------------------------------

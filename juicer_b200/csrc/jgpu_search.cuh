@@ -19,6 +19,9 @@
 #include "jgpu_device.cuh"
 
 #define JG_MAX_LANES 512
+#ifndef JG_RUN
+#define JG_RUN 1                  // consecutive chunks of k_internal handed to one CTA (L1 reuse of per-lane tables)
+#endif
 #ifndef JG_INT_CTAS
 #define JG_INT_CTAS 3             // resident CTAs per SM of k_internal<5> (register budget 64 K / (256 * CTAs))
 #endif
@@ -466,10 +469,17 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         cp_async_commit();
         return v;
     };
-    // lane of this CTA's i-th chunk (chunk blockIdx.x + i * G), looked up once
+    // This CTA's i-th chunk: chunks are dealt to CTAs in RUNS of JG_RUN consecutive chunks (same lane, mostly), so
+    // that the lane's acoustic-score row and the HMM table lines stay in L1 across the run; run r of the CTA is
+    // global run blockIdx.x + r * G.
+    auto chunk_of = [&](int i) -> int {
+        const int c_i = ((int)blockIdx.x + (i / JG_RUN) * G) * JG_RUN + (i % JG_RUN);
+        return c_i < total ? c_i : total;
+    };
+    // lane of the i-th chunk, looked up once
     __shared__ unsigned short my_lane[JG_THREADS];
     {
-        const int c_t = blockIdx.x + tid * G;
+        const int c_t = chunk_of(tid);
         int lo = 0, hi = L;                                   // largest l with pref[l] <= c_t
         if (c_t < total)
             while (lo + 1 < hi) {
@@ -486,11 +496,11 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         return ln;
     };
 
-    int ch = blockIdx.x;
+    int ch = chunk_of(0);
     int lane = lane_of(0, ch, 0);
-    int lane1 = lane_of(1, ch + G, lane), lane2 = lane1;
+    int lane1 = lane_of(1, chunk_of(1), lane), lane2 = lane1;
     bool valid = issue(ch, lane, 0);
-    bool valid1 = issue(ch + G, lane1, 1);
+    bool valid1 = issue(chunk_of(1), lane1, 1);
     // hmm_info + scores of the first chunk (exposed once per CTA)
     int4 h0 = make_int4(2, 0, 0, 0), h1 = make_int4(0, 0, 0, 0);
     float outp[S - 2];
@@ -508,7 +518,8 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         for (int j = 1; j < S - 1; ++j) outp[j - 1] = j < nst0 - 1 ? __ldg(scores + gm[j - 1]) : 0.0f;
     }
 
-    for (int it = 0; ch < total; ++it, ch += G) {
+    JG_TRACE_AT(0);                                           // setup + first chunk's loads done
+    for (int it = 0; ch < total; ++it, ch = chunk_of(it)) {
         const int buf = it & 1;
         const float norm = sh.f0[lane], thr_emit = sh.f1[lane], thr_start = sh.f2[lane];
         const unsigned epoch = sh.epoch[lane];
@@ -529,9 +540,12 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
             }
         }
         // ---- chunk i+2 -> the buffer just read; chunk i+1 has landed: start its hmm_info gathers ----
-        lane2 = lane_of(it + 2, ch + 2 * G, lane1);
-        const bool valid2 = issue(ch + 2 * G, lane2, buf);
+        const int ch2 = chunk_of(it + 2);
+        lane2 = lane_of(it + 2, ch2, lane1);
+        const bool valid2 = issue(ch2, lane2, buf);
+        JG_TRACE_AT(1);                                       // registers loaded, next copies issued
         cp_async_wait<1>();
+        JG_TRACE_AT(2);                                       // chunk i+1 landed
         int4 n0 = make_int4(2, 0, 0, 0), n1 = make_int4(0, 0, 0, 0);
         if (valid1) {
             const int hmm = reinterpret_cast<const int4*>(stage + (size_t)(buf ^ 1) * (P + 1) * JG_THREADS)[tid].y & ~JG_FRESH;
@@ -616,6 +630,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
                 if (res.x > JG_LZ) { ex = res; has_exit = true; ++cnt_end; }
             }
         }
+        JG_TRACE_AT(3);                                       // Viterbi done
         // ---- chunk i+1: its hmm_info has landed, start its acoustic-score gathers ----
         h0 = n0; h1 = n1;
         if (valid1) {
@@ -627,6 +642,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         }
         // ---- block-wide allocation: survivors -> next list, exit tokens -> arrival records of round 0;
         //      instances that die simply stop being listed, their slotmap entry goes stale with the epoch (:924-925)
+        JG_TRACE_AT(4);                                       // next scores issued
         const unsigned m_s = __ballot_sync(0xffffffffu, survive), m_e = __ballot_sync(0xffffffffu, has_exit);
         const unsigned best_o = __reduce_max_sync(0xffffffffu, f2o(best));
         const unsigned packed = __reduce_add_sync(0xffffffffu, (unsigned)cnt_emit | ((unsigned)cnt_hist << 16));
@@ -651,6 +667,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
             if (n_hist) atomicAdd(&c->hist_count, n_hist);
         }
         __syncthreads();
+        JG_TRACE_AT(5);                                       // allocation known
         const unsigned lt = (1u << lane_id()) - 1u;
         const int pos = sh_base[0] + sh_w[wid][0] + __popc(m_s & lt);
         const int e = sh_base[1] + sh_w[wid][1] + __popc(m_e & lt);
@@ -672,6 +689,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
                 atomicMax(d.state_key + (size_t)lane * d.n_states + (meta.z & 0x7fffffff),
                           state_key_of(epoch, ex.x, (unsigned)e));
         }
+        JG_TRACE_AT(6);                                       // stores issued: end of the first chunk
         // (no barrier needed here: a warp only rewrites its own sh_w row, and thread 0 rewrites the offsets and
         //  sh_base after the next chunk's first barrier, which every warp reaches after reading its positions)
         lane = lane1; lane1 = lane2;
@@ -834,6 +852,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
         sh.epoch[l] = c->epoch;
     }
     const int total_chunks = chunk_scan(sh, L);
+    JG_TRACE_AT(0);                                           // setup done
 
     int lane = 0;
     for (int ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
@@ -854,12 +873,14 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
             tok = *reinterpret_cast<const float4*>(arr + r);
             const int4 m = *(reinterpret_cast<const int4*>(arr + r) + 1);     // {via, q | MULTI, olab, -}
             const int q = m.y & 0x7fffffff;
+            JG_TRACE_AT(1);                                   // record loaded
             const int4 st = __ldg(&d.states[q]);
             valid = m.x != -2;
             if (valid && m.y < 0)                             // still the best arrival of q?
                 valid = d.state_key[(size_t)lane * d.n_states + q] == state_key_of(epoch, tok.x, r);
             if (valid) {
                 const int n_eps = st.w & 0xffff, n_tee = (unsigned)st.w >> 16;
+                JG_TRACE_AT(2);                               // state row (and key) loaded
                 if (PASS == 0) {
                     if (m.z != 0) {                           // word boundary record: :497-509
                         const int p = agg_inc(&c->n_paths);
@@ -896,6 +917,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
                 if (lane_id() == 0) atomicMax(&c->best_final, fin);
             }
         }
+        JG_TRACE_AT(3);                                       // per-record work done
         // ---- block-wide exclusive prefix of the row lengths ----
         int incl = deg;
         for (int o = 1; o < 32; o <<= 1) {
@@ -911,6 +933,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
         if (tid == JG_THREADS - 1) s_off[JG_THREADS] = woff + incl;
         __syncthreads();
         const int total = s_off[JG_THREADS];
+        JG_TRACE_AT(4);                                       // prefix done
         // ---- (B) the rows of the chunk as ONE flattened arc list, two arcs in flight per thread ----
         int n_entry = 0;
         float best = JG_LZ;
@@ -951,6 +974,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
             }
         }
         __syncthreads();                                      // s_off / s_tok are rewritten by the next chunk
+        JG_TRACE_AT(5);                                       // first chunk done
     }
 }
 

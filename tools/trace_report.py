@@ -8,7 +8,7 @@ import sys
 import numpy as np
 
 NAMES = ["gmm", "boundary", "internal", "seed", "expand", "expand_huge", "commit", "expand_r1", "expand_r2"]
-dt = np.dtype([("kid", "i4"), ("block", "i4"), ("smid", "i4"), ("aux", "i4"), ("t0", "u8"), ("t1", "u8")])
+dt = np.dtype([("kid", "i4"), ("block", "i4"), ("smid", "i4"), ("aux", "i4"), ("t0", "u8"), ("t1", "u8"), ("mark", "u4", (8,))])
 
 
 def main():
@@ -55,6 +55,14 @@ def main():
         tot += m[0] * len(v)
         print(f"{key[0] + ':' + str(key[1]):>16} {len(v):4d} {m[5]:6.0f} {m[0]:8.1f} {m[1]:8.1f} {m[2]:8.1f} {m[3]:8.1f} {m[4]:8.1f} {m[6]:8.1f} {m[7]:8.1f} {m[8]:6.1f} {m[9]:9.1f}")
     print(f"sum of spans {tot:.1f} us")
+    # thread-0 phase marks of the first chunk (median over the CTAs that reached them), us after CTA start
+    for kid in np.unique(r["kid"]):
+        for aux in np.unique(r["aux"][r["kid"] == kid]):
+            x = r[(r["kid"] == kid) & (r["aux"] == aux)]
+            mk = x["mark"].astype(np.float64) / 1965.0    # SM cycles -> us at 1965 MHz
+            med = [np.median(mk[:, i][mk[:, i] > 0]) if (mk[:, i] > 0).any() else 0.0 for i in range(mk.shape[1])]
+            if any(med):
+                print(f"   marks {NAMES[kid] if kid < len(NAMES) else kid}:{aux}: " + " ".join(f"{m:6.2f}" for m in med))
     # detail of the longest launch of the two slowest kernels
     for key, v in sorted(agg.items(), key=lambda kv: -sum(t[0] for t in kv[1]))[:4]:
         best = None
