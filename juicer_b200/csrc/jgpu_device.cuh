@@ -19,7 +19,7 @@
 //                                   WFSTTransition::hook, valid iff the stamp is the current epoch
 //                                 state_key[nStates] u64 (per-state max of arriving tokens, self-cleaning;
 //                                   only touched for states that can see more than one arrival per frame)
-//   per lane, per frame scratch : arrival records (32 B, stored round after round)
+//   per lane, per frame scratch : arrival records (token plane + {via, state, label} plane, stored round after round)
 //   per lane, per utterance     : word-boundary arena paths[cap_paths] (32 B records)
 //
 // Cost model behind the layout (measured on B200, tools/ubench/randmem.cu): random 32 B-sector
@@ -54,14 +54,6 @@ struct ResHdr {           // 32 B per utterance
     int   status, n_frames;
     float score, ac, lm;
     int   error, pad1, pad2;
-};
-
-struct Arrival {          // 32 B: one sector
-    float4 tok;
-    int    via;           // arc through which the token arrived, -1 = utterance seed, -2 = dropped
-    int    q;             // state reached | JG_MULTI
-    int    olab;          // output label of `via` (word-boundary record needed when != 0)
-    int    pad;
 };
 
 #define JG_MULTI 0x80000000u      // arcs.x / Arrival.q / inst_meta.z flag: the destination state can receive more
@@ -116,7 +108,8 @@ struct Dev {
     float4*   tok;
     unsigned* slotmap;
     u64*      state_key;
-    Arrival*  arr;
+    float4*   arr_tok;         // arrival records, two planes: token | {via arc (-1 seed, -2 dropped), state | JG_MULTI, out label, -}
+    int4*     arr_meta;
     int2*     huge;            // [n_lanes][cap_huge] {state, arrival record} of hub-like rows met by k_commit
     PathRec*  paths;
     int*      hist;

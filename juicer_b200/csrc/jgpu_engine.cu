@@ -489,7 +489,8 @@ int build_state(jgpu_handle* h)
     if ((rc = h->alloc(&d.tok, L * 2 * P * cap, false))) return rc;
     if ((rc = h->alloc(&d.slotmap, L * d.n_arcs))) return rc;
     if ((rc = h->alloc(&d.state_key, L * d.n_states))) return rc;
-    if ((rc = h->alloc(&d.arr, L * d.cap_arr, false))) return rc;
+    if ((rc = h->alloc(&d.arr_tok, L * d.cap_arr, false))) return rc;
+    if ((rc = h->alloc(&d.arr_meta, L * d.cap_arr, false))) return rc;
     if ((rc = h->alloc(&d.huge, L * d.cap_huge, false))) return rc;
     if ((rc = h->alloc(&d.paths, L * d.cap_paths, false))) return rc;
     if ((rc = h->alloc(&d.hist, L * d.hist_nbins))) return rc;

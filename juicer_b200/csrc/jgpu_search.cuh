@@ -34,7 +34,7 @@ struct LaneView {
     float4* tok_cur; float4* tok_nxt;
     unsigned* slotmap;
     u64* skey;
-    Arrival* arr;
+    float4* arr_tok; int4* arr_meta;
     int2* huge;
     PathRec* paths;
     int* hist;
@@ -52,7 +52,8 @@ __device__ __forceinline__ LaneView lane_view(const Dev& d, int lane, LaneCtl* c
     v.tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * P * cap;
     v.slotmap = d.slotmap + (size_t)lane * d.n_arcs;
     v.skey = d.state_key + (size_t)lane * d.n_states;
-    v.arr = d.arr + (size_t)lane * d.cap_arr;
+    v.arr_tok = d.arr_tok + (size_t)lane * d.cap_arr;
+    v.arr_meta = d.arr_meta + (size_t)lane * d.cap_arr;
     v.huge = d.huge + (size_t)lane * d.cap_huge;
     v.paths = d.paths + (size_t)lane * d.cap_paths;
     v.hist = d.hist + (size_t)lane * d.hist_nbins;
@@ -262,9 +263,8 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
         if (c->n_paths > d.cap_paths) c->error |= JG_ERR_PATHS;
         const u64 key = c->best_final;
         if (key) {
-            const Arrival a = v.arr[(unsigned)key];
-            float4 t = a.tok;
-            const float fw = __int_as_float(d.states[a.q & 0x7fffffff].z);
+            float4 t = v.arr_tok[(unsigned)key];
+            const float fw = __int_as_float(d.states[v.arr_meta[(unsigned)key].y & 0x7fffffff].z);
             t.x += fw;                                        // :517-518
             t.z += fw;
             c->final_tok = t;
@@ -332,10 +332,8 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
             c->s_arcs = c->s_entry = c->s_paths = c->s_frames = c->s_gmm = 0;
             // propagateToken(&zeroToken, NULL) (:221-226) = an arrival at the initial state, walked by the
             // expansion rounds of this step with every threshold at LOG_ZERO
-            Arrival a;
-            a.tok = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
-            a.via = -1; a.q = d.init_state | (int)d.init_multi; a.olab = 0; a.pad = 0;
-            v.arr[0] = a;
+            v.arr_tok[0] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
+            v.arr_meta[0] = make_int4(-1, d.init_state | (int)d.init_multi, 0, 0);
             c->n_arr[0] = 1;
             if (d.init_multi) v.skey[d.init_state] = state_key_of(c->epoch, 0.0f, 0u);
         } else if (mode == JG_MODE_FRAME) {                  // processFrame :318-339
@@ -682,9 +680,8 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
             d.slotmap[(size_t)lane * d.n_arcs + meta.x] = ((epoch & 0x7ffu) << JG_SLOT_BITS) | ((unsigned)pos + 1u);
         }
         if (has_exit && e < d.cap_arr) {
-            Arrival* a = d.arr + (size_t)lane * d.cap_arr + e;
-            *reinterpret_cast<float4*>(a) = ex;
-            *(reinterpret_cast<int4*>(a) + 1) = make_int4(meta.x, meta.z, meta.w, 0);
+            d.arr_tok[(size_t)lane * d.cap_arr + e] = ex;
+            d.arr_meta[(size_t)lane * d.cap_arr + e] = make_int4(meta.x, meta.z, meta.w, 0);
             if (FUSE && meta.z < 0)                       // destination can see several arrivals this frame
                 atomicMax(d.state_key + (size_t)lane * d.n_states + (meta.z & 0x7fffffff),
                           state_key_of(epoch, ex.x, (unsigned)e));
@@ -723,9 +720,8 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_filter(Dev d)
         const int e = (ch - sh.pref[lane]) * JG_CH + tid;
         int proc = 0;
         if (e < sh.cnt[lane]) {
-            Arrival* a = d.arr + (size_t)lane * d.cap_arr + e;
-            const float score = a->tok.x;
-            const int4 m = *(reinterpret_cast<const int4*>(a) + 1);
+            const float score = d.arr_tok[(size_t)lane * d.cap_arr + e].x;
+            const int4 m = d.arr_meta[(size_t)lane * d.cap_arr + e];
             const float thr = m.z == 0 ? sh.f0[lane] : sh.f1[lane];                 // :952-962
             if (score > thr) {
                 proc = 1;
@@ -733,7 +729,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_filter(Dev d)
                     atomicMax(d.state_key + (size_t)lane * d.n_states + (m.y & 0x7fffffff),
                               state_key_of(sh.epoch[lane], score, (unsigned)e));
             } else {
-                a->via = -2;
+                d.arr_meta[(size_t)lane * d.cap_arr + e].x = -2;
             }
         }
         proc = __reduce_add_sync(0xffffffffu, proc);
@@ -787,9 +783,8 @@ __device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, 
         if (go) {
             const int r = out_base + agg_inc(&c->n_arr[out_round]);
             if (r < d.cap_arr) {                              // overflow is flagged by k_boundary
-                Arrival* o = d.arr + (size_t)lane * d.cap_arr + r;
-                *reinterpret_cast<float4*>(o) = t;
-                *(reinterpret_cast<int4*>(o) + 1) = make_int4(b, a.x, a.w, 0);
+                d.arr_tok[(size_t)lane * d.cap_arr + r] = t;
+                d.arr_meta[(size_t)lane * d.cap_arr + r] = make_int4(b, a.x, a.w, 0);
                 if (a.x < 0)
                     atomicMax(d.state_key + (size_t)lane * d.n_states + (a.x & 0x7fffffff), state_key_of(epoch, t.x, (unsigned)r));
             }
@@ -861,7 +856,8 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
         const unsigned epoch = sh.epoch[lane];
         const float thr_end = sh.f0[lane], thr_word = sh.f1[lane];
         const int out_base = sh.i1[lane];
-        Arrival* arr = d.arr + (size_t)lane * d.cap_arr;
+        float4* arr_tok = d.arr_tok + (size_t)lane * d.cap_arr;
+        int4* arr_meta = d.arr_meta + (size_t)lane * d.cap_arr;
         // ---- (A) one thread per record ----
         const int e = (ch - sh.pref[lane]) * JG_CH + tid;
         bool valid = e < sh.cnt[lane];
@@ -870,8 +866,8 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
         float4 tok = null_tok();
         u64 fin = 0;
         if (valid) {
-            tok = *reinterpret_cast<const float4*>(arr + r);
-            const int4 m = *(reinterpret_cast<const int4*>(arr + r) + 1);     // {via, q | MULTI, olab, -}
+            tok = arr_tok[r];
+            const int4 m = arr_meta[r];                       // {via, q | MULTI, olab, -}
             const int q = m.y & 0x7fffffff;
             JG_TRACE_AT(1);                                   // record loaded
             const int4 st = __ldg(&d.states[q]);
@@ -889,10 +885,10 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
                             st_stream(reinterpret_cast<int4*>(pr), make_int4(__float_as_int(tok.w), sh.i2[lane], m.z, __float_as_int(tok.x)));
                             st_stream(reinterpret_cast<int4*>(pr) + 1, make_int4(__float_as_int(tok.y), __float_as_int(tok.z), 0, 0));
                             tok.w = __int_as_float(p);
-                            arr[r].tok.w = tok.w;
+                            arr_tok[r].w = tok.w;
                         } else {
                             valid = false;                    // flagged by k_boundary
-                            arr[r].via = -2;
+                            arr_meta[r].x = -2;
                         }
                     }
                     const float fw = __int_as_float(st.z);
@@ -993,7 +989,7 @@ __global__ void __launch_bounds__(JG_THREADS) k_commit_huge(Dev d)
     float best = JG_LZ;
     for (int h = 0; h < n; ++h) {
         const int2 qr = d.huge[(size_t)lane * d.cap_huge + h];
-        const float4 tok = d.arr[(size_t)lane * d.cap_arr + qr.y].tok;
+        const float4 tok = d.arr_tok[(size_t)lane * d.cap_arr + qr.y];
         const int4 st = __ldg(&d.states[qr.x]);
         const int n_eps = st.w & 0xffff;
         for (int b = st.x + n_eps + blockIdx.x * blockDim.x + threadIdx.x; b < st.x + st.y; b += gridDim.x * blockDim.x) {

@@ -25,6 +25,51 @@ def shard_utterances(n_frames: Sequence[int], world: int) -> List[List[int]]:
     return shards
 
 
+class UtteranceQueue:
+    """Whole-utterance work stealing across ranks: the utterance list, sorted
+    longest first, is one shared queue; a rank claims the next `wave` utterances with an atomic
+    fetch-add on the process group's key-value store, so a rank that finishes early simply keeps
+    claiming what a static split would have left to a slower one.  Only the counter crosses ranks:
+    every rank can read every utterance's features (host side), and results are gathered at the end
+    (`gather_results`), so there is still no data-path collective.  Without a process group the
+    counter is local and the queue degenerates to a plain loop."""
+
+    def __init__(self, n_frames: Sequence[int], wave: int, name: str = "juicer_b200/utt_queue"):
+        self.order = sorted(range(len(n_frames)), key=lambda i: (-int(n_frames[i]), i))
+        self.wave = max(int(wave), 1)
+        self.key = name
+        self._local = 0
+        self._store = None
+        try:
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_world_size() > 1:
+                from torch.distributed.distributed_c10d import _get_default_store
+                self._store = _get_default_store()
+        except ImportError:
+            pass
+
+    def claim(self) -> List[int]:
+        """Next wave of utterance indices for the calling rank; empty when the queue is drained."""
+        if self._store is not None:
+            start = int(self._store.add(self.key, self.wave)) - self.wave
+        else:
+            start = self._local
+            self._local += self.wave
+        return self.order[start:start + self.wave] if start < len(self.order) else []
+
+
+def decode_with_stealing(decode_wave, n_frames: Sequence[int], wave: int, name: str = "juicer_b200/utt_queue") -> Dict[int, dict]:
+    """Drains the shared queue: `decode_wave(indices) -> {index: record}` is called with one wave at a
+    time (on the GPU: one lock-step batch of the rank's decoder).  Returns this rank's records."""
+    q = UtteranceQueue(n_frames, wave, name)
+    local: Dict[int, dict] = {}
+    while True:
+        idx = q.claim()
+        if not idx:
+            return local
+        local.update(decode_wave(idx))
+
+
 def env_rank_world() -> Tuple[int, int, int]:
     return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
             int(os.environ.get("LOCAL_RANK", "0")))

@@ -68,3 +68,45 @@ def test_two_rank_gloo_matches_single_process(oracle_port_lib, product_lib):
         r = single.decode(f)
         assert allr[u]["status"] == r.status and allr[u]["labels"] == r.labels and allr[u]["times"] == r.times
         assert allr[u]["totals"] == r.totals.view(np.uint32).tolist()
+
+
+def _steal_worker(rank, world, port, q):
+    import time
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    d = jdist.init_process_group("gloo")
+    n_frames = list(range(40, 0, -1))                       # 40 utterances, longest first already
+    claimed = []
+
+    def decode_wave(idx):
+        claimed.append(list(idx))
+        time.sleep(0.05 if rank == 1 else 0.0)              # rank 1 is the slow GPU
+        return {u: dict(rank=rank, frames=n_frames[u]) for u in idx}
+
+    local = jdist.decode_with_stealing(decode_wave, n_frames, wave=3, name="test/queue")
+    allr = jdist.gather_results(local, len(n_frames))
+    if rank == 0:
+        q.put(allr)
+    d.barrier()
+    d.destroy_process_group()
+
+
+def test_work_stealing_queue_two_ranks():
+    """Every utterance is decoded exactly once, and the fast rank ends up with more of them."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_steal_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    allr = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r["frames"] for r in allr] == list(range(40, 0, -1))
+    by_rank = [sum(1 for r in allr if r["rank"] == k) for k in range(2)]
+    assert sum(by_rank) == 40 and by_rank[0] > by_rank[1]
+
+
+def test_queue_without_process_group_is_a_plain_loop():
+    q = jdist.UtteranceQueue([5, 9, 1, 7], wave=3)
+    assert q.claim() == [1, 3, 0] and q.claim() == [2] and q.claim() == []
