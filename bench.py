@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=128, help="utterances decoded in lock-step")
     ap.add_argument("--min-frames", type=int, default=300)
     ap.add_argument("--max-frames", type=int, default=1000)
-    ap.add_argument("--cpu-sample-utts", type=int, default=2)
+    ap.add_argument("--cpu-sample-utts", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workdir", default=os.environ.get("JUICER_BENCH_DIR", "/tmp/juicer_b200_bench"))
     return ap.parse_args()

@@ -407,10 +407,22 @@ __device__ __forceinline__ float4 viterbi_into(const float4 (&src)[S], const flo
 
 // cp.async helpers: 16-byte global -> shared copies that bypass L1 and the register file; a thread
 // only ever reads back what it copied itself, so cp.async.wait_group is the only synchronisation.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+// The copies carry an L2 evict-first policy: the instance lists stream through once per step (~2 GB/s per lane)
+// and must not push the arrival records, state rows and arc rows of the expansion kernels out of L2.
+__device__ __forceinline__ u64 l2_evict_first_policy()
+{
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, u64 policy)
 {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+#ifdef JG_NO_L2_HINT
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+#else
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem_src), "l"(policy) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -447,6 +459,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
     const size_t cap = (size_t)d.cap;
     const bool hist_on = d.max_hyps > 0;
     const int G = gridDim.x;
+    const u64 l2_stream = l2_evict_first_policy();
 
     // copies of chunk `ch` (lane `ln`) into buffer `buf`; returns whether this thread has an instance there
     auto issue = [&](int ch, int ln, int buf) -> bool {
@@ -459,9 +472,9 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
                 const int4* meta_cur = d.inst_meta + ((size_t)ln * 2 + flip) * cap;
                 const float4* tok_cur = d.tok + ((size_t)ln * 2 + flip) * P * cap;
                 float4* dst = stage + (size_t)buf * (P + 1) * JG_THREADS + tid;
-                cp_async16(dst, meta_cur + k);
+                cp_async16(dst, meta_cur + k, l2_stream);
 #pragma unroll
-                for (int i = 0; i < P; ++i) cp_async16(dst + (i + 1) * JG_THREADS, tok_cur + (size_t)i * cap + k);
+                for (int i = 0; i < P; ++i) cp_async16(dst + (i + 1) * JG_THREADS, tok_cur + (size_t)i * cap + k, l2_stream);
             }
         }
         cp_async_commit();
