@@ -58,6 +58,10 @@ struct ResHdr {           // 32 B per utterance
 
 #define JG_MULTI 0x80000000u      // arcs.x / Arrival.q / inst_meta.z flag: the destination state can receive more
                                   // than one arrival per frame, so arrivals are max-reduced through state_key
+#define JG_ROUND 0x40000000u      // same fields: the destination state has work for the expansion rounds (it is MULTI,
+                                  // final, or has epsilon / tee out-arcs); every other exit token is finished inside
+                                  // k_internal (word-boundary record) and only meets the commit
+#define JG_STATE_MASK 0x3fffffff
 #define JG_SLOT_BITS 20           // slotmap entry = (epoch & 0x7ff) << 20 | position + 1
 #define JG_SLOT_MASK 0xfffffu
 
@@ -66,8 +70,8 @@ struct ResHdr {           // 32 B per utterance
 
 struct LaneCtl {
     int n_cur, n_huge, n_paths, flip;
+    int n_r0;                 // records of round 0 that need the expansion round (fused mode: indices in r0_list)
     unsigned epoch;           // advances every non-idle step of this lane, never repeats
-    int pad0_;
     int n_next;               // (n_next, n_arr[0]) sit in one aligned 64-bit word: k_internal bumps both with one atomic
     int n_arr[JG_MAX_ROUNDS + 2];    // arrivals feeding expansion round k (records are stored back to back)
     unsigned best_int;        // orderable max of emitting scores of this frame   (WFSTDecoderLite.cpp:417-418)
@@ -110,6 +114,7 @@ struct Dev {
     u64*      state_key;
     float4*   arr_tok;         // arrival records, two planes: token | {via arc (-1 seed, -2 dropped), state | JG_MULTI, out label, -}
     int4*     arr_meta;
+    int*      r0_list;         // [n_lanes][cap_arr] arrival records of round 0 whose state is JG_ROUND (fused mode)
     int2*     huge;            // [n_lanes][cap_huge] {state, arrival record} of hub-like rows met by k_commit
     PathRec*  paths;
     int*      hist;

@@ -218,6 +218,7 @@ int validate(const JgpuNet* n, const JgpuHmm* m, const JgpuGmm* g, const JgpuCfg
 {
     if (!n || !m || !g || !c) return fail(JGPU_E_ARG, "null argument");
     if (n->n_states <= 0 || n->n_arcs < 0) return fail(JGPU_E_ARG, "empty network");
+    if (n->n_states > JG_STATE_MASK) return fail(JGPU_E_ARG, "more than 2^30 states");
     if (n->init_state < 0 || n->init_state >= n->n_states) return fail(JGPU_E_ARG, "init_state out of range");
     if (m->n_hmms <= 0 || m->max_states < 2 || m->max_states > 8)
         return fail(JGPU_E_ARG, "max_states=%d unsupported (2..8)", m->max_states);
@@ -286,6 +287,14 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
             for (int b = n->state_first[s]; b < n->state_first[s] + n->state_narcs[s]; ++b)
                 if (pass[b]) multi[n->arc_to[b]] = 1;
     d.init_multi = multi[n->init_state] ? JG_MULTI : 0u;
+    // Which states have work for the expansion rounds at all?  Those that max-reduce their arrivals, final states
+    // (best final token, :513-520) and states with epsilon / tee out-arcs.  An exit token reaching any other state
+    // is finished inside k_internal.
+    std::vector<char> round_work(NS, 0);
+    for (int s = 0; s < NS; ++s) {
+        round_work[s] = multi[s] || n->state_final[s] > JG_LZ;
+        for (int b = n->state_first[s]; b < n->state_first[s] + n->state_narcs[s] && !round_work[s]; ++b) round_work[s] = pass[b];
+    }
     // every row is re-ordered [epsilon | tee-model | other model arcs] (stable), so that the expansion rounds
     // walk a prefix of the row and the commit walks the rest; arc ids are internal to the engine.
     std::vector<int4> arcs(A);
@@ -302,7 +311,8 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
                 if (c_b != cls) continue;
                 int wbits;
                 memcpy(&wbits, &n->arc_weight[b], 4);
-                arcs[pos] = make_int4(n->arc_to[b] | (multi[n->arc_to[b]] ? (int)JG_MULTI : 0), wbits, in, n->arc_out[b]);
+                const int to = n->arc_to[b];
+                arcs[pos] = make_int4(to | (multi[to] ? (int)JG_MULTI : 0) | (round_work[to] ? (int)JG_ROUND : 0), wbits, in, n->arc_out[b]);
                 arc_tee[pos] = tee_in[b];
                 ++pos;
                 n_eps += cls == 0; n_tee += cls == 1;
@@ -467,7 +477,7 @@ int build_state(jgpu_handle* h)
 
     const size_t cap = d.cap, P = d.S - 1;
     size_t need = L * (2 * cap * 16 + 2 * P * cap * 16 + (size_t)d.n_arcs * 4 + (size_t)d.n_states * 8 +
-                       (size_t)d.cap_arr * 32 + (size_t)d.cap_paths * 32);
+                       (size_t)d.cap_arr * 36 + (size_t)d.cap_paths * 32);
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     if (c.max_paths <= 0) {
@@ -492,6 +502,7 @@ int build_state(jgpu_handle* h)
     if ((rc = h->alloc(&d.arr_tok, L * d.cap_arr, false))) return rc;
     if ((rc = h->alloc(&d.arr_meta, L * d.cap_arr, false))) return rc;
     if ((rc = h->alloc(&d.huge, L * d.cap_huge, false))) return rc;
+    if ((rc = h->alloc(&d.r0_list, L * d.cap_arr, false))) return rc;
     if ((rc = h->alloc(&d.paths, L * d.cap_paths, false))) return rc;
     if ((rc = h->alloc(&d.hist, L * d.hist_nbins))) return rc;
     if ((rc = h->alloc(&d.fstat_cnt, d.frame_stats ? L * d.max_frames * 4 : 1))) return rc;

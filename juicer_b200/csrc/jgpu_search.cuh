@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
         const u64 key = c->best_final;
         if (key) {
             float4 t = v.arr_tok[(unsigned)key];
-            const float fw = __int_as_float(d.states[v.arr_meta[(unsigned)key].y & 0x7fffffff].z);
+            const float fw = __int_as_float(d.states[v.arr_meta[(unsigned)key].y & JG_STATE_MASK].z);
             t.x += fw;                                        // :517-518
             t.z += fw;
             c->final_tok = t;
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
             c->flip ^= 1;
             c->n_cur = min(c->n_next, d.cap);
         }
-        c->n_next = 0; c->n_huge = 0;
+        c->n_next = 0; c->n_huge = 0; c->n_r0 = 0;
         for (int i = 0; i <= JG_MAX_ROUNDS + 1; ++i) c->n_arr[i] = 0;
         c->best_final = 0;
         c->c_active_emit = c->c_active_end = c->c_end_proc = c->c_arcs = c->c_entry = 0;
@@ -335,6 +335,8 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
             v.arr_tok[0] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
             v.arr_meta[0] = make_int4(-1, d.init_state | (int)d.init_multi, 0, 0);
             c->n_arr[0] = 1;
+            d.r0_list[(size_t)lane * d.cap_arr] = 0;          // the seed always goes through the expansion rounds
+            c->n_r0 = 1;
             if (d.init_multi) v.skey[d.init_state] = state_key_of(c->epoch, 0.0f, 0u);
         } else if (mode == JG_MODE_FRAME) {                  // processFrame :318-339
             const float bi = o2f(c->best_int), bx = o2f(c->best_ext);
@@ -443,8 +445,8 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
     constexpr int P = S - 1;
     constexpr int NW = JG_THREADS / 32;
     __shared__ LaneSh sh;
-    __shared__ int sh_w[NW][4];                               // per warp: survivors, exits, packed counters, best
-    __shared__ int sh_base[2];
+    __shared__ int sh_w[NW][6];                               // per warp: survivors, exits, packed counters, best, path records, round-0 entries
+    __shared__ int sh_base[4];
     extern __shared__ float4 stage[];                         // [2][P + 1][JG_THREADS]; plane 0 = instance record
     const int L = d.n_lanes;
     const int tid = threadIdx.x, wid = tid >> 5;
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         const LaneCtl* c = d.ctl + l;
         sh.cnt[l] = c->mode == JG_MODE_FRAME ? c->n_cur : 0;
         sh.f0[l] = c->norm; sh.f1[l] = c->thr_emit; sh.f2[l] = c->thr_start;
-        sh.i0[l] = c->srow; sh.i1[l] = c->flip;
+        sh.i0[l] = c->srow; sh.i1[l] = c->flip; sh.i2[l] = c->frame;
         sh.epoch[l] = c->epoch;
     }
     const int total = chunk_scan(sh, L);
@@ -654,23 +656,34 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         // ---- block-wide allocation: survivors -> next list, exit tokens -> arrival records of round 0;
         //      instances that die simply stop being listed, their slotmap entry goes stale with the epoch (:924-925)
         JG_TRACE_AT(4);                                       // next scores issued
+        // With no end / word beam an exit token whose destination has nothing to do in the expansion rounds
+        // (single arrival, not final, no epsilon / tee arcs) is finished here: its word-boundary record
+        // (:497-509) is written now and the arrival record only meets the commit.  The others are listed for round 0.
+        const bool to_round = FUSE && has_exit && (meta.z & (int)JG_ROUND) != 0;
+        const bool need_path = FUSE && has_exit && !to_round && meta.w != 0;
         const unsigned m_s = __ballot_sync(0xffffffffu, survive), m_e = __ballot_sync(0xffffffffu, has_exit);
+        const unsigned m_p = __ballot_sync(0xffffffffu, need_path), m_r = __ballot_sync(0xffffffffu, to_round);
         const unsigned best_o = __reduce_max_sync(0xffffffffu, f2o(best));
         const unsigned packed = __reduce_add_sync(0xffffffffu, (unsigned)cnt_emit | ((unsigned)cnt_hist << 16));
-        if (lane_id() == 0) { sh_w[wid][0] = __popc(m_s); sh_w[wid][1] = __popc(m_e); sh_w[wid][2] = (int)packed; sh_w[wid][3] = (int)best_o; }
+        if (lane_id() == 0) {
+            sh_w[wid][0] = __popc(m_s); sh_w[wid][1] = __popc(m_e); sh_w[wid][2] = (int)packed; sh_w[wid][3] = (int)best_o;
+            sh_w[wid][4] = __popc(m_p); sh_w[wid][5] = __popc(m_r);
+        }
         __syncthreads();
         if (tid == 0) {
-            int ns = 0, ne = 0, n_emit = 0, n_hist = 0;
+            int ns = 0, ne = 0, np = 0, nr = 0, n_emit = 0, n_hist = 0;
             unsigned bo = 0;
             for (int w = 0; w < NW; ++w) {
-                const int a = sh_w[w][0], b = sh_w[w][1];
-                sh_w[w][0] = ns; sh_w[w][1] = ne;             // exclusive offsets of the warp
-                ns += a; ne += b;
+                const int a = sh_w[w][0], b = sh_w[w][1], p4 = sh_w[w][4], r5 = sh_w[w][5];
+                sh_w[w][0] = ns; sh_w[w][1] = ne; sh_w[w][4] = np; sh_w[w][5] = nr;   // exclusive offsets of the warp
+                ns += a; ne += b; np += p4; nr += r5;
                 n_emit += sh_w[w][2] & 0xffff; n_hist += (unsigned)sh_w[w][2] >> 16;
                 bo = max(bo, (unsigned)sh_w[w][3]);
             }
             sh_base[0] = ns ? atomicAdd(&c->n_next, ns) : 0;
             sh_base[1] = ne ? atomicAdd(&c->n_arr[0], ne) : 0;
+            sh_base[2] = np ? atomicAdd(&c->n_paths, np) : 0;
+            sh_base[3] = nr ? atomicAdd(&c->n_r0, nr) : 0;
             if (bo > f2o(JG_LZ)) atomicMax(&c->best_int, bo);
             if (n_emit) atomicAdd(&c->c_active_emit, n_emit);
             if (ne) atomicAdd(&c->c_active_end, ne);
@@ -693,10 +706,23 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
             d.slotmap[(size_t)lane * d.n_arcs + meta.x] = ((epoch & 0x7ffu) << JG_SLOT_BITS) | ((unsigned)pos + 1u);
         }
         if (has_exit && e < d.cap_arr) {
+            int via = meta.x;
+            if (need_path) {
+                const int p = sh_base[2] + sh_w[wid][4] + __popc(m_p & lt);
+                if (p < d.cap_paths) {
+                    PathRec* pr = d.paths + (size_t)lane * d.cap_paths + p;
+                    st_stream(reinterpret_cast<int4*>(pr), make_int4(__float_as_int(ex.w), sh.i2[lane], meta.w, __float_as_int(ex.x)));
+                    st_stream(reinterpret_cast<int4*>(pr) + 1, make_int4(__float_as_int(ex.y), __float_as_int(ex.z), 0, 0));
+                    ex.w = __int_as_float(p);
+                } else {
+                    via = -2;                             // arena full: the record is dropped, k_boundary flags the lane
+                }
+            }
+            if (to_round) d.r0_list[(size_t)lane * d.cap_arr + sh_base[3] + sh_w[wid][5] + __popc(m_r & lt)] = e;
             d.arr_tok[(size_t)lane * d.cap_arr + e] = ex;
-            d.arr_meta[(size_t)lane * d.cap_arr + e] = make_int4(meta.x, meta.z, meta.w, 0);
+            d.arr_meta[(size_t)lane * d.cap_arr + e] = make_int4(via, meta.z, meta.w, 0);
             if (FUSE && meta.z < 0)                       // destination can see several arrivals this frame
-                atomicMax(d.state_key + (size_t)lane * d.n_states + (meta.z & 0x7fffffff),
+                atomicMax(d.state_key + (size_t)lane * d.n_states + (meta.z & JG_STATE_MASK),
                           state_key_of(epoch, ex.x, (unsigned)e));
         }
         JG_TRACE_AT(6);                                       // stores issued: end of the first chunk
@@ -739,7 +765,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_filter(Dev d)
             if (score > thr) {
                 proc = 1;
                 if (m.y < 0)
-                    atomicMax(d.state_key + (size_t)lane * d.n_states + (m.y & 0x7fffffff),
+                    atomicMax(d.state_key + (size_t)lane * d.n_states + (m.y & JG_STATE_MASK),
                               state_key_of(sh.epoch[lane], score, (unsigned)e));
             } else {
                 d.arr_meta[(size_t)lane * d.cap_arr + e].x = -2;
@@ -799,7 +825,7 @@ __device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, 
                 d.arr_tok[(size_t)lane * d.cap_arr + r] = t;
                 d.arr_meta[(size_t)lane * d.cap_arr + r] = make_int4(b, a.x, a.w, 0);
                 if (a.x < 0)
-                    atomicMax(d.state_key + (size_t)lane * d.n_states + (a.x & 0x7fffffff), state_key_of(epoch, t.x, (unsigned)r));
+                    atomicMax(d.state_key + (size_t)lane * d.n_states + (a.x & JG_STATE_MASK), state_key_of(epoch, t.x, (unsigned)r));
             }
         }
     } else {
@@ -844,6 +870,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
                 rec0 = arr_base(c, round);
                 n = max(0, min(c->n_arr[round], d.cap_arr - rec0));
                 out_base = rec0 + c->n_arr[round];
+                if (round == 0 && d.fuse_exits) n = min(c->n_r0, n);   // only the records listed by k_internal / k_boundary
             } else {
                 n = min(arr_base(c, d.n_rounds + 1), d.cap_arr);
             }
@@ -874,14 +901,15 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
         // ---- (A) one thread per record ----
         const int e = (ch - sh.pref[lane]) * JG_CH + tid;
         bool valid = e < sh.cnt[lane];
-        const unsigned r = (unsigned)(sh.i0[lane] + e);
+        unsigned r = (unsigned)(sh.i0[lane] + e);
+        if (PASS == 0 && round == 0 && d.fuse_exits && valid) r = (unsigned)d.r0_list[(size_t)lane * d.cap_arr + e];
         int first = 0, deg = 0, arcs_done = 0;
         float4 tok = null_tok();
         u64 fin = 0;
         if (valid) {
             tok = arr_tok[r];
             const int4 m = arr_meta[r];                       // {via, q | MULTI, olab, -}
-            const int q = m.y & 0x7fffffff;
+            const int q = m.y & JG_STATE_MASK;
             JG_TRACE_AT(1);                                   // record loaded
             const int4 st = __ldg(&d.states[q]);
             valid = m.x != -2;

@@ -117,7 +117,7 @@ def test_output_formats():
 
 
 @pytest.mark.gpu
-def test_decode_files_matches_decode_batch(tmp_path, port_lib):
+def test_decode_files_matches_decode_batch(tmp_path, product_lib):
     """HTK files + extended names through the harness == the same frames through decode_batch."""
     from helpers import Golden, flat_tables_from_files
     from test_gpu_parity import make_decoder
