@@ -287,12 +287,13 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
             for (int b = n->state_first[s]; b < n->state_first[s] + n->state_narcs[s]; ++b)
                 if (pass[b]) multi[n->arc_to[b]] = 1;
     d.init_multi = multi[n->init_state] ? JG_MULTI : 0u;
-    // Which states have work for the expansion rounds at all?  Those that max-reduce their arrivals, final states
-    // (best final token, :513-520) and states with epsilon / tee out-arcs.  An exit token reaching any other state
-    // is finished inside k_internal.
+    // Which states have work for the expansion rounds at all?  Final states (best final token, :513-520) and states
+    // with epsilon / tee out-arcs.  An exit token reaching any other state skips the rounds: if the state has a single
+    // arrival per frame its word-boundary record is written inside k_internal, otherwise by the commit for the arrival
+    // that owns the state in the end.
     std::vector<char> round_work(NS, 0);
     for (int s = 0; s < NS; ++s) {
-        round_work[s] = multi[s] || n->state_final[s] > JG_LZ;
+        round_work[s] = n->state_final[s] > JG_LZ;        // (a MULTI state without either is resolved by the commit alone)
         for (int b = n->state_first[s]; b < n->state_first[s] + n->state_narcs[s] && !round_work[s]; ++b) round_work[s] = pass[b];
     }
     // every row is re-ordered [epsilon | tee-model | other model arcs] (stable), so that the expansion rounds

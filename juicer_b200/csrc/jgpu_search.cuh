@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         // (single arrival, not final, no epsilon / tee arcs) is finished here: its word-boundary record
         // (:497-509) is written now and the arrival record only meets the commit.  The others are listed for round 0.
         const bool to_round = FUSE && has_exit && (meta.z & (int)JG_ROUND) != 0;
-        const bool need_path = FUSE && has_exit && !to_round && meta.w != 0;
+        const bool need_path = FUSE && has_exit && !to_round && meta.z >= 0 && meta.w != 0;   // (MULTI: the commit writes it)
         const unsigned m_s = __ballot_sync(0xffffffffu, survive), m_e = __ballot_sync(0xffffffffu, has_exit);
         const unsigned m_p = __ballot_sync(0xffffffffu, need_path), m_r = __ballot_sync(0xffffffffu, to_round);
         const unsigned best_o = __reduce_max_sync(0xffffffffu, f2o(best));
@@ -873,6 +873,8 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
                 if (round == 0 && d.fuse_exits) n = min(c->n_r0, n);   // only the records listed by k_internal / k_boundary
             } else {
                 n = min(arr_base(c, d.n_rounds + 1), d.cap_arr);
+                rec0 = c->frame;                              // (PASS 1 walks from record 0: the slot carries the frame)
+                out_base = c->n_arr[0];                       // records below this index are round-0 arrivals
             }
         }
         sh.cnt[l] = n;
@@ -901,7 +903,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
         // ---- (A) one thread per record ----
         const int e = (ch - sh.pref[lane]) * JG_CH + tid;
         bool valid = e < sh.cnt[lane];
-        unsigned r = (unsigned)(sh.i0[lane] + e);
+        unsigned r = (unsigned)((PASS == 0 ? sh.i0[lane] : 0) + e);
         if (PASS == 0 && round == 0 && d.fuse_exits && valid) r = (unsigned)d.r0_list[(size_t)lane * d.cap_arr + e];
         int first = 0, deg = 0, arcs_done = 0;
         float4 tok = null_tok();
@@ -936,13 +938,27 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
                     if (valid && fw > JG_LZ && m.x >= 0) fin = ((u64)f2o(tok.x + fw) << 32) | r;   // :513-520 (not for the seed: trans == NULL)
                     if (valid) { first = st.x; deg = n_eps + n_tee; }
                 } else {
+                    if (d.fuse_exits && m.z != 0 && m.y < 0 && !(m.y & (int)JG_ROUND) && m.x >= 0 && r < (unsigned)sh.i1[lane]) {
+                        // round-0 arrival at a multi-arrival state that the rounds skipped: the word-boundary record
+                        // (:497-509) of the arrival that owns the state in the end is written here
+                        const int p = agg_inc(&c->n_paths);
+                        if (p < d.cap_paths) {
+                            PathRec* pr = d.paths + (size_t)lane * d.cap_paths + p;
+                            st_stream(reinterpret_cast<int4*>(pr), make_int4(__float_as_int(tok.w), sh.i0[lane], m.z, __float_as_int(tok.x)));
+                            st_stream(reinterpret_cast<int4*>(pr) + 1, make_int4(__float_as_int(tok.y), __float_as_int(tok.z), 0, 0));
+                            tok.w = __int_as_float(p);
+                        } else {
+                            valid = false;                    // flagged by k_boundary
+                        }
+                    }
                     first = st.x + n_eps;
-                    deg = st.y - n_eps;
+                    deg = valid ? st.y - n_eps : 0;
                     arcs_done = st.y;
                     if (deg >= d.huge_deg) {                  // hub-like row: left to k_commit_huge
                         const int h = atomicAdd(&c->n_huge, 1);
                         if (h < d.cap_huge) d.huge[(size_t)lane * d.cap_huge + h] = make_int2(q, (int)r);
                         else atomicOr(&c->error, JG_ERR_HUGE);
+                        arr_tok[r].w = tok.w;                 // (k_commit_huge reads the token from the record)
                         deg = 0;
                     }
                 }
