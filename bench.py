@@ -51,8 +51,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--utts", type=int, default=256, help="utterances per step per GPU")
-    ap.add_argument("--lanes", type=int, default=128, help="utterances decoded in lock-step")
+    ap.add_argument("--utts", type=int, default=512, help="utterances per step per GPU")
+    ap.add_argument("--lanes", type=int, default=256, help="utterances decoded in lock-step")
     ap.add_argument("--min-frames", type=int, default=300)
     ap.add_argument("--max-frames", type=int, default=1000)
     ap.add_argument("--cpu-sample-utts", type=int, default=8)

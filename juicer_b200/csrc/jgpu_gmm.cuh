@@ -28,6 +28,9 @@
 #ifndef JG_GMM_UNROLL
 #define JG_GMM_UNROLL 4       // feature rows in flight per thread (independent accumulation chains)
 #endif
+#ifndef JG_GMM_P2
+#define JG_GMM_P2 1           // (row, GMM) logAdd chains folded side by side per thread in phase 2
+#endif
 #define JG_PRAGMA_(x) _Pragma(#x)
 #define JG_PRAGMA_UNROLL(n) JG_PRAGMA_(unroll n)
 #define JG_GMM_DMAX 64        // max feature dimension held in registers
@@ -152,16 +155,33 @@ JG_PRAGMA_UNROLL(JG_GMM_UNROLL)
     }
     __syncthreads();
 
-    // phase 2: thread <-> (row, gmm); serial logAdd chain in component order
-    for (int p = tid; p < RT * gpb; p += 256) {
-        const int r = p / gpb, l = p - r * gpb;
-        const int gg = g0 + l;
-        const int rid = row_id[r];
-        if (gg < g.n_gmms && rid >= 0) {
-            const int nc = __ldg(g.ncomp + gg);
-            float lp = JG_LZ;
-            for (int cc = 0; cc < nc; ++cc) lp = jg_log_add(g.softplus, lp, vals[cc * cstride + p]);
-            out[(size_t)(out_base + r0 + r) * g.n_gmms + gg] = lp;
+    // phase 2: thread <-> (row, gmm); serial logAdd chain in component order.  JG_GMM_P2 pairs per thread are
+    // folded side by side: each chain is a string of dependent fp64 operations, the pairs are independent.
+    constexpr int PP = JG_GMM_P2;
+    for (int p0 = tid; p0 < RT * gpb; p0 += 256 * PP) {
+        float lp[PP];
+        int nc[PP], pp[PP];
+        int nc_max = 0;
+#pragma unroll
+        for (int u = 0; u < PP; ++u) {
+            const int p = p0 + u * 256;
+            pp[u] = p; nc[u] = 0; lp[u] = JG_LZ;
+            if (p < RT * gpb) {
+                const int r = p / gpb, l = p - r * gpb;
+                if (g0 + l < g.n_gmms && row_id[r] >= 0) nc[u] = __ldg(g.ncomp + g0 + l);
+            }
+            nc_max = max(nc_max, nc[u]);
         }
+        for (int cc = 0; cc < nc_max; ++cc) {
+#pragma unroll
+            for (int u = 0; u < PP; ++u)
+                if (cc < nc[u]) lp[u] = jg_log_add(g.softplus, lp[u], vals[cc * cstride + pp[u]]);
+        }
+#pragma unroll
+        for (int u = 0; u < PP; ++u)
+            if (nc[u] > 0) {
+                const int r = pp[u] / gpb, l = pp[u] - r * gpb;
+                out[(size_t)(out_base + r0 + r) * g.n_gmms + g0 + l] = lp[u];
+            }
     }
 }

@@ -6,7 +6,7 @@
 set -x
 OUT=gpurun_out
 TAG=${1:-r01}; shift
-BENCH="python bench.py --workload c3 --utts 128 --lanes 128 --min-frames 100 --max-frames 120 --steps 1 --warmup 1 --no-cpu-baseline"
+BENCH="python bench.py --workload c3 --utts 256 --lanes 256 --min-frames 100 --max-frames 120 --steps 1 --warmup 1 --no-cpu-baseline"
 for K in "$@"; do
   if [ "$K" == "launches" ]; then
     ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 1500 --csv --log-file $OUT/launches_${TAG}.csv $BENCH > $OUT/ncu_bench_${TAG}.log 2>&1

@@ -26,7 +26,7 @@ def launches():
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(P, f"{tag}_launches.md"), "w") as f:
         f.write(f"# ncu launch list ({tag}): gpu__time_duration.sum per launch, --clock-control none\n\n")
-        f.write("Command: see tools/profile_gpu.sh (shortened bench.py run on c3, 128 lanes, 128 utterances of 100-120 frames). Per-launch times are cold-cache\n"
+        f.write("Command: see tools/profile_gpu.sh (shortened bench.py run on c3, 256 lanes, 256 utterances of 100-120 frames). Per-launch times are cold-cache\n"
                 "and serialised: compare SHARES with bench.py's `roofline.kernel_share_of_step`, not absolutes.\n\n")
         f.write("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
