@@ -47,8 +47,9 @@ typedef unsigned long long u64;
 struct PathRec {          // 32 B: replaces Path (src/WFSTDecoderLite.h:39-55) minus the GC links
     int   prev, frame, label;
     float score, ac, lm;
-    int   pad0, pad1;
+    int   mark, pad1;     // mark: 0 when written, stamp of the last collection that reached it, JG_PATH_FREE on the free list
 };
+#define JG_PATH_FREE 0x7fffffff
 
 struct ResHdr {           // 32 B per utterance
     int   status, n_frames;
@@ -86,7 +87,16 @@ struct LaneCtl {
     long long s_active_models, s_active_emit, s_active_end, s_proc_emit, s_proc_end, s_arcs, s_entry,
         s_paths, s_frames, s_gmm;
     long long b_stats[10];    // sums over the utterances finished on this lane since the last batch reset
+    // word-boundary arena collection (kept behind the per-step fields: their offsets are tuned to two 128 B lines)
+    int n_free;               // records on the lane's free list (filled by k_gc_sweep)
+    int gc_gen, gc_do;        // mark stamp of the collection in progress / whether this lane takes part in it
+    int paths_recycled;       // records served from the free list in this utterance (statistics)
+    int pad_tail_[4];         // keeps sizeof(LaneCtl) off a multiple of 128 B: every CTA of every kernel reads the same
+                              // fields of all lanes at start-up, and line-aligned control blocks put those hot lines on
+                              // a subset of the L2 slices (measured: +4 us per kernel launch at a 384 B stride)
 };
+
+static_assert(sizeof(LaneCtl) % 16 == 0 && sizeof(LaneCtl) % 128 != 0, "LaneCtl stride: 16 B aligned, not line aligned");
 
 struct Dev {
     // static tables
@@ -104,6 +114,7 @@ struct Dev {
     int max_hyps, hist_min, hist_max, hist_nbins;
     int n_lanes, cap, cap_arr, cap_paths, cap_huge, n_rounds, max_frames, frame_stats, max_words;
     int huge_deg;
+    int gc_threshold;                // a lane's arena is collected when more than this many records are in use
     int fuse_exits;                  // no end / word beam: exit tokens become arrivals inside k_internal
     int grid_internal, grid_other, grid_walk;   // CTAs of the chunk-scheduled kernels
     // per-lane state
@@ -117,6 +128,7 @@ struct Dev {
     int*      r0_list;         // [n_lanes][cap_arr] arrival records of round 0 whose state is JG_ROUND (fused mode)
     int2*     huge;            // [n_lanes][cap_huge] {state, arrival record} of hub-like rows met by k_commit
     PathRec*  paths;
+    int*      path_free;       // [n_lanes][cap_paths] free list: indices of dead word-boundary records
     int*      hist;
     const float* scores;       // [ring rows][n_gmms]
     const int4*  sched;        // [n_steps + 1][n_lanes] {feature row, score row, flags, utt}

@@ -69,6 +69,7 @@ struct jgpu_handle {
     cudaGraphExec_t graph_step = nullptr, graph_block = nullptr;   // one frame step / FB frame steps of all lanes
     bool use_graphs = true;
     std::vector<unsigned> host_epoch;    // mirror of LaneCtl::epoch (advances on every non-idle step of the lane)
+    int gc_period = 64, steps_since_gc = 0;   // word-boundary arena collection every gc_period frame steps (0 = never)
     cudaStream_t stream = nullptr;       // search kernels, copies
     cudaStream_t stream_gmm = nullptr;   // acoustic scoring of the NEXT frame block overlaps the search
     cudaEvent_t ev_inputs = nullptr, ev_gmm[2] = {nullptr, nullptr}, ev_search[2] = {nullptr, nullptr};
@@ -478,18 +479,18 @@ int build_state(jgpu_handle* h)
 
     const size_t cap = d.cap, P = d.S - 1;
     size_t need = L * (2 * cap * 16 + 2 * P * cap * 16 + (size_t)d.n_arcs * 4 + (size_t)d.n_states * 8 +
-                       (size_t)d.cap_arr * 36 + (size_t)d.cap_paths * 32);
+                       (size_t)d.cap_arr * 36 + (size_t)d.cap_paths * 36);
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     if (c.max_paths <= 0) {
         // word-boundary arena: no garbage collection yet, so give it half of the free memory
         // (1M .. 32M records of 32 B per lane); an utterance that still overflows fails alone
-        const size_t fixed = need - L * (size_t)d.cap_paths * 32;
+        const size_t fixed = need - L * (size_t)d.cap_paths * 36;
         const size_t budget = free_b > fixed + (2ull << 30) ? (free_b - fixed - (2ull << 30)) / 2 : 0;
-        size_t per_lane = budget / (L * 32);
+        size_t per_lane = budget / (L * 36);
         per_lane = std::min<size_t>(std::max<size_t>(per_lane, 1u << 20), 1u << 25);
         d.cap_paths = (int)per_lane;
-        need = fixed + L * (size_t)d.cap_paths * 32;
+        need = fixed + L * (size_t)d.cap_paths * 36;
     }
     if (need + (1ull << 30) > free_b)
         return fail(JGPU_E_CAPACITY, "decoder state needs %.1f GB for %d lanes but only %.1f GB of device memory is free",
@@ -505,6 +506,11 @@ int build_state(jgpu_handle* h)
     if ((rc = h->alloc(&d.huge, L * d.cap_huge, false))) return rc;
     if ((rc = h->alloc(&d.r0_list, L * d.cap_arr, false))) return rc;
     if ((rc = h->alloc(&d.paths, L * d.cap_paths, false))) return rc;
+    if ((rc = h->alloc(&d.path_free, L * d.cap_paths, false))) return rc;
+    d.gc_threshold = d.cap_paths - d.cap_paths / 4;           // collect when 3/4 full: recycled slots are scattered, so
+                                                              // an arena that is big enough is never collected at all
+    h->gc_period = d.cap_paths < (1 << 20) ? 16 : 64;       // small arenas (tests, tight memory) are collected more often
+    if (const char* e = getenv("JUICER_B200_GC_PERIOD")) h->gc_period = atoi(e);
     if ((rc = h->alloc(&d.hist, L * d.hist_nbins))) return rc;
     if ((rc = h->alloc(&d.fstat_cnt, d.frame_stats ? L * d.max_frames * 4 : 1))) return rc;
     if ((rc = h->alloc(&d.fstat_best, d.frame_stats ? L * d.max_frames : 1))) return rc;
@@ -532,6 +538,19 @@ int build_state(jgpu_handle* h)
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_internal<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         }
         if (e != cudaSuccess) return fail(JGPU_E_CUDA, "k_internal shared memory opt-in: %s", cudaGetErrorString(e));
+    }
+    {
+        // grids = SM count x the CTAs that are really resident (a few hundred bytes of shared memory more per
+        // CTA can cost a whole CTA per SM, and a grid that no longer fits in one wave costs a second set-up)
+        int n_sm = 148, occ = 0;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
+        const size_t smem_int = (size_t)2 * h->S * JG_THREADS * sizeof(float4);
+        cudaError_t e = h->S == 5 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_internal<5, true>, JG_THREADS, smem_int)
+                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_internal<8, true>, JG_THREADS, smem_int);
+        if (e == cudaSuccess && occ > 0) d.grid_internal = n_sm * occ;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_walk<1>, JG_THREADS, 0) == cudaSuccess && occ > 0) d.grid_walk = n_sm * occ;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_filter, JG_THREADS, 0) == cudaSuccess && occ > 0) d.grid_other = n_sm * occ;
+        cudaGetLastError();
     }
     h->lanes.assign(L, LaneHost());
     h->host_epoch.assign(L, 0u);
@@ -754,6 +773,18 @@ int run_schedule(jgpu_handle* h, const std::vector<int4>& sched, int n_steps, co
                     }
                     if ((rc = graphs ? launch_steps_graph(h, 1) : launch_step(h))) return rc;
                 }
+            }
+            // word-boundary arena: mark + sweep between two frame steps, every gc_period steps (lanes whose arena
+            // is less than half full skip it on the device)
+            h->steps_since_gc += nb;
+            if (h->gc_period > 0 && h->steps_since_gc >= h->gc_period) {
+                h->steps_since_gc = 0;
+                const dim3 grid_gc(std::max(2, std::min(32, 1184 / L)), L);
+                k_gc_decide<<<(L + 127) / 128, 128, 0, h->stream>>>(d);
+                k_gc_mark<<<grid_gc, JG_THREADS, 0, h->stream>>>(d);
+                k_gc_sweep<<<grid_gc, JG_THREADS, 0, h->stream>>>(d);
+                h->launches += 3;
+                CK(cudaGetLastError());
             }
             CK(cudaEventRecord(h->ev_search[b & 1], h->stream));
         }

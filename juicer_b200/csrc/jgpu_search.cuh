@@ -22,6 +22,9 @@
 #ifndef JG_RUN
 #define JG_RUN 1                  // consecutive chunks of k_internal handed to one CTA (L1 reuse of per-lane tables)
 #endif
+#ifndef JG_WALK_CTAS
+#define JG_WALK_CTAS 6            // resident CTAs per SM of k_walk (40 registers per thread at 6)
+#endif
 #ifndef JG_INT_CTAS
 #define JG_INT_CTAS 3             // resident CTAs per SM of k_internal<5> (register budget 64 K / (256 * CTAs))
 #endif
@@ -72,6 +75,45 @@ __device__ __forceinline__ int agg_inc(int* counter)
     return base + __popc(peers & ((1u << lane_id()) - 1u));
 }
 
+// Word-boundary records (Path, src/WFSTDecoderLite.h:39-55): `n` records for the calling group come first from
+// the lane's free list (records the last garbage collection found unreachable — the reference's refcounted
+// free, :630-657 / collectPaths :699-747), then from the bump pointer n_paths.  Called by ONE thread of the
+// group; record j of the group is path_index(a, free_list, j).
+// `has_free` = the lane's free list was non-empty when the kernel started (it only shrinks during a step), read
+// once per CTA: the common case — nothing on the list — costs exactly one atomicAdd on the bump pointer.
+struct PathAlloc { int from_free, free_top, bump_base; };
+__device__ __forceinline__ PathAlloc path_alloc(LaneCtl* c, int n, bool has_free)
+{
+    PathAlloc a;
+    a.from_free = 0; a.free_top = 0; a.bump_base = 0;
+    if (has_free) {
+        const int old = atomicSub(&c->n_free, n);
+        const int got = min(max(old, 0), n);
+        if (got < n) atomicAdd(&c->n_free, n - got);          // give back what was not there
+        a.from_free = got; a.free_top = old;
+        if (got) atomicAdd(&c->paths_recycled, got);
+    }
+    if (a.from_free < n) a.bump_base = atomicAdd(&c->n_paths, n - a.from_free);
+    return a;
+}
+__device__ __forceinline__ int path_index(const PathAlloc& a, const int* __restrict__ free_list, int j)
+{
+    return j < a.from_free ? free_list[a.free_top - 1 - j] : a.bump_base + (j - a.from_free);
+}
+// one record for every thread of the warp that is here (all of the same lane), one allocation for the group
+__device__ __forceinline__ int path_alloc_here(LaneCtl* c, const int* __restrict__ free_list, bool has_free)
+{
+    const unsigned peers = __activemask();
+    const int leader = __ffs(peers) - 1;
+    PathAlloc a;
+    a.from_free = 0; a.free_top = 0; a.bump_base = 0;
+    if (lane_id() == leader) a = path_alloc(c, __popc(peers), has_free);
+    a.from_free = __shfl_sync(peers, a.from_free, leader);
+    a.free_top = __shfl_sync(peers, a.free_top, leader);
+    a.bump_base = __shfl_sync(peers, a.bump_base, leader);
+    return path_index(a, free_list, __popc(peers & ((1u << lane_id()) - 1u)));
+}
+
 // streaming (evict-first) accessors for data that is written once and read once per step
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
 __device__ __forceinline__ int4 ld_stream(const int4* p) { return __ldcs(p); }
@@ -94,6 +136,9 @@ struct LaneSh {                   // per-CTA shared copy of what a chunk needs t
     float f0[JG_MAX_LANES], f1[JG_MAX_LANES], f2[JG_MAX_LANES];   // kernel-specific
     int i0[JG_MAX_LANES], i1[JG_MAX_LANES], i2[JG_MAX_LANES];
 };
+// bit 31 of LaneSh::epoch (only the low 11 bits of the epoch are ever used as a stamp): the lane's
+// word-boundary free list was not empty when the kernel started
+#define JG_SH_HAS_FREE 0x80000000u
 
 // sh.cnt[] must be filled (and __syncthreads() NOT yet called); returns the number of chunks
 __device__ __forceinline__ int chunk_scan(LaneSh& sh, int L, int items = JG_CH)
@@ -292,7 +337,7 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
             }
             c->frame += 1;
         }
-        c->s_paths = c->n_paths;
+        c->s_paths = c->n_paths + c->paths_recycled;
     }
     __syncwarp();
     if (l == 0 && (s.z & JG_FLAG_FINISH)) finish_utterance(d, v, lane);
@@ -322,7 +367,7 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
             c->frame = 0;
             c->error = 0;
             c->n_cur = 0;                                    // previous utterance's instances are dropped (:148-158)
-            c->n_paths = 0;
+            c->n_paths = 0; c->n_free = 0; c->paths_recycled = 0;
             c->best_int = f2o(JG_LZ);
             c->best_ext = f2o(JG_LZ);
             c->norm = 0.0f; c->thr_emit = JG_LZ; c->thr_start = JG_LZ;
@@ -446,7 +491,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
     constexpr int NW = JG_THREADS / 32;
     __shared__ LaneSh sh;
     __shared__ int sh_w[NW][6];                               // per warp: survivors, exits, packed counters, best, path records, round-0 entries
-    __shared__ int sh_base[4];
+    __shared__ int sh_base[6];
     extern __shared__ float4 stage[];                         // [2][P + 1][JG_THREADS]; plane 0 = instance record
     const int L = d.n_lanes;
     const int tid = threadIdx.x, wid = tid >> 5;
@@ -455,7 +500,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         sh.cnt[l] = c->mode == JG_MODE_FRAME ? c->n_cur : 0;
         sh.f0[l] = c->norm; sh.f1[l] = c->thr_emit; sh.f2[l] = c->thr_start;
         sh.i0[l] = c->srow; sh.i1[l] = c->flip; sh.i2[l] = c->frame;
-        sh.epoch[l] = c->epoch;
+        sh.epoch[l] = (c->epoch & ~JG_SH_HAS_FREE) | (c->n_free > 0 ? JG_SH_HAS_FREE : 0u);
     }
     const int total = chunk_scan(sh, L);
     const size_t cap = (size_t)d.cap;
@@ -682,7 +727,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
             }
             sh_base[0] = ns ? atomicAdd(&c->n_next, ns) : 0;
             sh_base[1] = ne ? atomicAdd(&c->n_arr[0], ne) : 0;
-            sh_base[2] = np ? atomicAdd(&c->n_paths, np) : 0;
+            if (np) { const PathAlloc pa = path_alloc(c, np, (sh.epoch[lane] & JG_SH_HAS_FREE) != 0); sh_base[2] = pa.bump_base; sh_base[4] = pa.from_free; sh_base[5] = pa.free_top; }
             sh_base[3] = nr ? atomicAdd(&c->n_r0, nr) : 0;
             if (bo > f2o(JG_LZ)) atomicMax(&c->best_int, bo);
             if (n_emit) atomicAdd(&c->c_active_emit, n_emit);
@@ -708,7 +753,9 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         if (has_exit && e < d.cap_arr) {
             int via = meta.x;
             if (need_path) {
-                const int p = sh_base[2] + sh_w[wid][4] + __popc(m_p & lt);
+                PathAlloc pa;
+                pa.bump_base = sh_base[2]; pa.from_free = sh_base[4]; pa.free_top = sh_base[5];
+                const int p = path_index(pa, d.path_free + (size_t)lane * d.cap_paths, sh_w[wid][4] + __popc(m_p & lt));
                 if (p < d.cap_paths) {
                     PathRec* pr = d.paths + (size_t)lane * d.cap_paths + p;
                     st_stream(reinterpret_cast<int4*>(pr), make_int4(__float_as_int(ex.w), sh.i2[lane], meta.w, __float_as_int(ex.x)));
@@ -851,7 +898,7 @@ __device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, 
 }
 
 template <int PASS>
-__global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
+__global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int round)
 {
     JG_TRACE_SCOPE(PASS ? JGPU_K_COMMIT : JGPU_K_EXPAND, round);
     __shared__ LaneSh sh;
@@ -886,7 +933,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
             tw = (d.word_beam > 0.0f ? (be - d.word_beam) : JG_LZ);
         }
         sh.f0[l] = te; sh.f1[l] = tw;
-        sh.epoch[l] = c->epoch;
+                sh.epoch[l] = (c->epoch & ~JG_SH_HAS_FREE) | (c->n_free > 0 ? JG_SH_HAS_FREE : 0u);
     }
     const int total_chunks = chunk_scan(sh, L);
     JG_TRACE_AT(0);                                           // setup done
@@ -922,7 +969,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
                 JG_TRACE_AT(2);                               // state row (and key) loaded
                 if (PASS == 0) {
                     if (m.z != 0) {                           // word boundary record: :497-509
-                        const int p = agg_inc(&c->n_paths);
+                                                const int p = path_alloc_here(c, d.path_free + (size_t)lane * d.cap_paths, (sh.epoch[lane] & JG_SH_HAS_FREE) != 0);
                         if (p < d.cap_paths) {
                             PathRec* pr = d.paths + (size_t)lane * d.cap_paths + p;
                             st_stream(reinterpret_cast<int4*>(pr), make_int4(__float_as_int(tok.w), sh.i2[lane], m.z, __float_as_int(tok.x)));
@@ -941,7 +988,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_walk(Dev d, int round)
                     if (d.fuse_exits && m.z != 0 && m.y < 0 && !(m.y & (int)JG_ROUND) && m.x >= 0 && r < (unsigned)sh.i1[lane]) {
                         // round-0 arrival at a multi-arrival state that the rounds skipped: the word-boundary record
                         // (:497-509) of the arrival that owns the state in the end is written here
-                        const int p = agg_inc(&c->n_paths);
+                                                const int p = path_alloc_here(c, d.path_free + (size_t)lane * d.cap_paths, (sh.epoch[lane] & JG_SH_HAS_FREE) != 0);
                         if (p < d.cap_paths) {
                             PathRec* pr = d.paths + (size_t)lane * d.cap_paths + p;
                             st_stream(reinterpret_cast<int4*>(pr), make_int4(__float_as_int(tok.w), sh.i0[lane], m.z, __float_as_int(tok.x)));
@@ -1061,5 +1108,100 @@ __global__ void __launch_bounds__(JG_THREADS) k_commit_huge(Dev d)
     if (lane_id() == 0) {
         if (n_entry) atomicAdd(&c->c_entry, n_entry);
         if (best > JG_LZ) atomicMax(&c->best_ext, f2o(best));
+    }
+}
+
+// =========================================================================================
+// Garbage collection of the word-boundary arena — the GPU form of refPath / deRefPath and
+// collectPaths (src/WFSTDecoderLite.cpp:630-657, 699-747).  The reference ref-counts every Path
+// and sweeps every 100 frames; here a record is live iff it is reachable from a token that is
+// alive between two steps, so a collection is  mark (walk the prev chains from every live
+// token, stop at records already stamped)  +  sweep (unstamped records go to the lane's free
+// list, from which path_alloc serves them again).  Nothing moves: indices held by tokens stay
+// valid.  The host launches the three kernels between two frame steps every few dozen steps;
+// k_gc_decide lets a lane take part only when its arena is filling up.
+// =========================================================================================
+__global__ void k_gc_decide(Dev d)
+{
+    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= d.n_lanes) return;
+    LaneCtl* c = d.ctl + lane;
+    const int used = c->n_paths - c->n_free;
+    c->gc_do = c->mode != JG_MODE_IDLE && c->n_paths <= d.cap_paths && used > d.gc_threshold;
+    if (c->gc_do) {
+        c->gc_gen += 1;
+        if (c->gc_gen >= JG_PATH_FREE) c->gc_gen = 1;         // (2^31 collections: never in practice)
+    }
+}
+
+__device__ __forceinline__ void gc_mark_chain(PathRec* paths, int p, int gen)
+{
+    while (p >= 0) {
+        const int old = atomicExch(&paths[p].mark, gen);
+        if (old == gen) break;                                // the rest of the chain is already stamped
+        p = paths[p].prev;
+    }
+}
+
+// grid (CTAs per lane, n_lanes).  Roots: every live token of the list built by the last step (the lane's NEXT
+// buffer: k_boundary has not flipped yet) and the pending best final arrival.
+__global__ void __launch_bounds__(JG_THREADS) k_gc_mark(Dev d)
+{
+    const int lane = blockIdx.y;
+    LaneCtl* c = d.ctl + lane;
+    if (!c->gc_do) return;
+    const int gen = c->gc_gen;
+    const size_t cap = (size_t)d.cap;
+    const int P = d.S - 1;
+    const int flip = c->flip ^ 1;
+    const int4* meta = d.inst_meta + ((size_t)lane * 2 + flip) * cap;
+    const float4* tok = d.tok + ((size_t)lane * 2 + flip) * P * cap;
+    PathRec* paths = d.paths + (size_t)lane * d.cap_paths;
+    const int n = min(c->n_next, d.cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 m = meta[i];
+        const float4 t0 = tok[i];
+        if (t0.x > JG_LZ) gc_mark_chain(paths, __float_as_int(t0.w), gen);
+        if (!(m.y & JG_FRESH)) {
+            const int nst = __ldg(d.hmm_info + (size_t)(m.y & ~JG_FRESH) * 8) & 0xff;
+            for (int j = 1; j < nst - 1 && j < P; ++j) {
+                const float4 t = tok[(size_t)j * cap + i];
+                if (t.x > JG_LZ) gc_mark_chain(paths, __float_as_int(t.w), gen);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const u64 key = c->best_final;                        // resolved by the next k_boundary
+        if (key) gc_mark_chain(paths, __float_as_int(d.arr_tok[(size_t)lane * d.cap_arr + (unsigned)key].w), gen);
+        if (c->final_valid) gc_mark_chain(paths, __float_as_int(c->final_tok.w), gen);
+    }
+}
+
+__global__ void __launch_bounds__(JG_THREADS) k_gc_sweep(Dev d)
+{
+    const int lane = blockIdx.y;
+    LaneCtl* c = d.ctl + lane;
+    if (!c->gc_do) return;
+    const int gen = c->gc_gen;
+    PathRec* paths = d.paths + (size_t)lane * d.cap_paths;
+    int* free_list = d.path_free + (size_t)lane * d.cap_paths;
+    const int n = min(c->n_paths, d.cap_paths);
+    for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        bool dead = false;
+        if (i < n) {
+            const int mk = paths[i].mark;
+            dead = mk != gen && mk != JG_PATH_FREE;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, dead);
+        if (m) {
+            int base = 0;
+            if (lane_id() == 0) base = atomicAdd(&c->n_free, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (dead) {
+                free_list[base + __popc(m & ((1u << lane_id()) - 1u))] = i;
+                paths[i].mark = JG_PATH_FREE;
+            }
+        }
     }
 }

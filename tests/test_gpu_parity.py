@@ -297,3 +297,29 @@ def test_c3_scaled_trigram_matches_oracle(tmp_path, port_lib):
         assert np.array_equal(want.frame_cnt[:, [0, 1, 2, 4]], cnt)
         assert np.array_equal(bits(want.frame_best), bits(best))
     dec.close(); p.close()
+
+
+def test_word_boundary_arena_is_garbage_collected(c2_setup):
+    """collectPaths (src/WFSTDecoderLite.cpp:699-747): with an arena far smaller than the number of
+    word-boundary records the utterances create, decodes still equal those of a large arena (which the
+    tests above pin to the reference) — dead records are recycled by the mark + sweep collection — on
+    the batch path, on a second pass over warm free lists, and on the streaming interface."""
+    m, net, kw, tabs, netl, models = c2_setup
+    ps = synth.PathSampler(net, m)
+    rng = np.random.default_rng(4242)
+    feats = [ps.sample(int(n), rng)[0] for n in (260, 180, 90, 200)]
+    big = make_decoder(netl, models, kw, n_lanes=2)
+    want = big.decode_batch(feats)
+    made = int(big.stats(-1)["total_paths"])
+    big.close()
+    small_arena = max(16384, made // 6)                     # the collection runs every 16 steps at half occupancy
+    assert made > 3 * small_arena, f"the utterances must create many more records ({made}) than the arena holds"
+    dec = make_decoder(netl, models, kw, n_lanes=2, max_paths=small_arena)
+    for rep in range(2):                                     # second pass: arenas and free lists are re-used
+        got = dec.decode_batch(feats)
+        assert all(r.status > 0 for r in got), [r.status for r in got]
+        for u in range(len(feats)):
+            same_result(want[u], got[u], f"gc pass {rep} utt{u}")
+        assert int(dec.stats(-1)["total_paths"]) == made
+    same_result(want[0], dec.decode(feats[0], lane=1, chunk=37), "gc streaming")
+    dec.close()
