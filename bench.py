@@ -40,6 +40,8 @@ WORKLOADS = {
     "c2": "1k-word bigram C.L.G (~42k states / ~51k arcs), 2000 triphone HMMs x 16-mix, main beam 200, "
           "utterances of 300-1000 frames",
     "c3s": "c3 topology at 1/8 scale (smoke runs)",
+    "c5": "64k-word trigram-shaped C.L.G (~1.45M states / ~5.9M arcs), 4000 HMMs over 6000 tied 16-mix GMMs, "
+          "utterances of 300-1000 frames; main beam / histogram limit from --beam / --max-hyps",
 }
 METRIC = "decoded frames/sec (xRT) on composed H∘C∘L∘G WFST"
 
@@ -57,12 +59,18 @@ def parse_args():
     ap.add_argument("--max-frames", type=int, default=1000)
     ap.add_argument("--cpu-sample-utts", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--beam", type=float, default=0.0, help="override the workload's main beam (beam sweeps, BASELINE configs[4])")
+    ap.add_argument("--max-hyps", type=int, default=-1, help="override the histogram-pruning limit (0 = off)")
     ap.add_argument("--workdir", default=os.environ.get("JUICER_BENCH_DIR", "/tmp/juicer_b200_bench"))
     return ap.parse_args()
 
 
+_OVERRIDES: Dict[str, float] = {}
+
+
 def build_fixture(workload: str, workdir: str, rank: int):
     m, net, tee, kw = synth.named_config(workload)
+    kw = dict(kw, **_OVERRIDES)
     d = os.path.join(workdir, f"{workload}_r{rank}")
     files = synth.make_fixture(workload, d, m, net)
     return m, net, tee, kw, files
@@ -216,6 +224,10 @@ def algorithmic_bytes(stats: Dict[str, int], dims: Dict[str, int], n_rows: int) 
 
 def main() -> None:
     args = parse_args()
+    if args.beam > 0:
+        _OVERRIDES["main_beam"] = args.beam
+    if args.max_hyps >= 0:
+        _OVERRIDES["max_hyps"] = args.max_hyps
     if args.impl == "reference":
         run_reference(args)
         return

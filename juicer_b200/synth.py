@@ -486,6 +486,7 @@ def named_config(name: str):
     c2      BASELINE configs[1]: 1k-vocab bigram, 2000 triphone HMMs x 16-mix, ~42k states
     c3      BASELINE configs[2]: 20k-vocab trigram-shaped network, ~440k states / ~1.8M arcs, beam 250
     c3s     c3 topology at 1/8 scale (parity at sizes the CPU oracle finishes in seconds)
+    c5      BASELINE configs[4]: 64k-vocab trigram-shaped network, ~1.45M states / ~5.9M arcs (beam sweeps)
     """
     if name == "c1":
         return make_models(10, 1, sigma_mu=2.0, seed=1), digit_loop_net(10), (), dict(main_beam=200.0)
@@ -511,6 +512,11 @@ def named_config(name: str):
     if name == "c3":
         return (make_models(4000, 16, sigma_mu=1.3, seed=21, n_gmm_pool=6000),
                 trigram_net(20000, 4000, k_bigram=40, n_trigram=60000, k_trigram=8, seed=22), (),
+                dict(main_beam=250.0))
+    if name == "c5":                            # BASELINE configs[4]: 64k-vocab trigram, ~1.45M states / ~5.9M arcs;
+        #                                             the beam and histogram settings are swept by the caller
+        return (make_models(4000, 16, sigma_mu=1.3, seed=21, n_gmm_pool=6000),
+                trigram_net(64000, 4000, k_bigram=40, n_trigram=200000, k_trigram=8, seed=52), (),
                 dict(main_beam=250.0))
     if name == "c3s":
         return (make_models(600, 8, sigma_mu=1.0, seed=23, n_gmm_pool=900),
