@@ -456,7 +456,14 @@ int build_state(jgpu_handle* h)
         d.hist_nbins = d.hist_max - d.hist_min + 1;
     }
     d.n_lanes = c.n_lanes;
-    d.cap = c.max_active > 0 ? c.max_active : std::min(d.n_arcs + 1, 1 << 18);
+    d.cap = c.max_active > 0 ? c.max_active : std::min(d.n_arcs + 1, 1000000);
+    if (c.max_active <= 0) {
+        // auto: room for every arc of the network up to 1M instances per lane (wide beams on a 64k-word network keep
+        // > 260k instances alive), halved while the lists of all lanes would take more than 25 % of the free memory
+        size_t free_b0 = 0, total_b0 = 0;
+        CK(cudaMemGetInfo(&free_b0, &total_b0));
+        while (d.cap > (1 << 18) && (double)L * d.cap * (16.0 * 2 + 16.0 * 2 * (d.S - 1) + 36.0 * 2 + 4.0 * 2) > 0.25 * (double)free_b0) d.cap /= 2;
+    }
     d.cap = std::max(d.cap, 64);
     d.cap = std::min(d.cap, 1000000);                    // arrival records: 21 bits, slotmap positions: 20 bits
     d.cap_arr = 2 * d.cap + 1024;
@@ -483,10 +490,10 @@ int build_state(jgpu_handle* h)
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     if (c.max_paths <= 0) {
-        // word-boundary arena: no garbage collection yet, so give it half of the free memory
-        // (1M .. 32M records of 32 B per lane); an utterance that still overflows fails alone
+        // word-boundary arena + its free list: 4/5 of the free memory (1M .. 32M records per lane).  An arena that
+        // never fills to 3/4 is never garbage-collected, which keeps allocation sequential.
         const size_t fixed = need - L * (size_t)d.cap_paths * 36;
-        const size_t budget = free_b > fixed + (2ull << 30) ? (free_b - fixed - (2ull << 30)) / 2 : 0;
+        const size_t budget = free_b > fixed + (2ull << 30) ? (free_b - fixed - (2ull << 30)) / 5 * 4 : 0;
         size_t per_lane = budget / (L * 36);
         per_lane = std::min<size_t>(std::max<size_t>(per_lane, 1u << 20), 1u << 25);
         d.cap_paths = (int)per_lane;
