@@ -216,6 +216,10 @@ const char* jgpu_kernel_name(int32_t kind);
  * The returned structs point into library-owned host memory released by jgpu_free_*. */
 int jgpu_load_fsm(const char* fsm, const char* insyms, const char* outsyms, float lm_scale,
                   float ins_penalty, JgpuNet* out);
+/* jgpu_load_jwnt  : JWNT binary network, same semantics as WFSTNetwork::readBinary
+ *                   (src/WFSTNetwork.cpp:1228-1370; alphabets :250-297): transition weights are scaled by
+ *                   lm_scale and get ins_penalty on arcs with an output label after reading. */
+int jgpu_load_jwnt(const char* path, float lm_scale, float ins_penalty, JgpuNet* out);
 int jgpu_free_net(JgpuNet* net);
 int jgpu_load_jmbi(const char* path, JgpuHmm* hmm, JgpuGmm* gmm);
 int jgpu_free_models(JgpuHmm* hmm, JgpuGmm* gmm);

@@ -61,6 +61,7 @@ def load_library() -> C.CDLL:
     lib.jgpu_kernel_name.argtypes = [i32]
     lib.jgpu_kernel_name.restype = C.c_char_p
     lib.jgpu_load_fsm.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_float, C.c_float, vp]
+    lib.jgpu_load_jwnt.argtypes = [C.c_char_p, C.c_float, C.c_float, vp]
     lib.jgpu_free_net.argtypes = [vp]
     lib.jgpu_load_jmbi.argtypes = [C.c_char_p, vp, vp]
     lib.jgpu_free_models.argtypes = [vp, vp]
@@ -88,6 +89,15 @@ class WFSTNetwork:
         self.c = JgpuNet()
         _check(self.lib.jgpu_load_fsm(fsm.encode(), insyms.encode(), outsyms.encode(), lm_scale, ins_penalty,
                                       C.byref(self.c)), "jgpu_load_fsm")
+
+    @classmethod
+    def from_jwnt(cls, path: str, lm_scale: float = 1.0, ins_penalty: float = 0.0) -> "WFSTNetwork":
+        """JWNT binary network (WFSTNetwork::readBinary, src/WFSTNetwork.cpp:1228-1370)."""
+        self = cls.__new__(cls)
+        self.lib = load_library()
+        self.c = JgpuNet()
+        _check(self.lib.jgpu_load_jwnt(path.encode(), lm_scale, ins_penalty, C.byref(self.c)), "jgpu_load_jwnt")
+        return self
 
     def arrays(self) -> Dict[str, np.ndarray]:
         c = self.c

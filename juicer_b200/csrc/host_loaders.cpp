@@ -187,6 +187,122 @@ extern "C" int jgpu_load_fsm(const char* fsm, const char* insyms, const char* ou
     return JGPU_OK;
 }
 
+// JWNT binary network: WFSTNetwork::readBinary (src/WFSTNetwork.cpp:1228-1370) with the alphabets of
+// WFSTAlphabet::readBinary (:250-297).  Layout (native endianness, int = i32, real = f32, bool = 1 byte):
+//   "JWNT" initState maxState nStates maxOutTransitions wordEndMarker silMarker spMarker
+//   per state 0..maxState : label finalInd nTrans trans[nTrans]      (trans = ids into the transition array)
+//   nFinalStates, then (id, weight) each                               (weights as stored: already scaled)
+//   nTransitions, then (id, toState, weight, inLabel, outLabel) each   (weights unscaled, without insPenalty)
+//   bool haveInputAlphabet [alphabet]  bool haveOutputAlphabet [alphabet]  "JWNT"
+//   alphabet = "JWAL" maxLabel nLabels, per label 0..maxLabel: len [len bytes, nul-terminated], nAux, isAux[maxLabel+1]
+// After reading, the reference multiplies every transition weight by the scaling factor and adds the insertion
+// penalty to arcs with an output label (:1351-1365); final weights are used as read.
+static bool rd(FILE* fd, void* p, size_t n) { return fread(p, 1, n, fd) == n; }
+
+static int skip_alphabet(FILE* fd, const char* fname)
+{
+    char id[5] = {0, 0, 0, 0, 0};
+    int max_label, n_labels;
+    if (!rd(fd, id, 4) || strcmp(id, "JWAL") != 0) return io_fail("%s: WFSTAlphabet::readBinary - invalid ID", fname);
+    if (!rd(fd, &max_label, 4) || !rd(fd, &n_labels, 4)) return io_fail("%s: error reading alphabet header", fname);
+    if (max_label >= 0) {
+        for (int i = 0; i <= max_label; ++i) {
+            int len;
+            if (!rd(fd, &len, 4) || len < 0) return io_fail("%s: error reading label length", fname);
+            if (len > 0) {
+                std::vector<char> buf(len);
+                if (!rd(fd, buf.data(), len)) return io_fail("%s: error reading label string", fname);
+                if (buf[len - 1] != '\0') return io_fail("%s: last char of label string was not nul", fname);
+            }
+        }
+        int n_aux;
+        std::vector<char> is_aux(max_label + 1);
+        if (!rd(fd, &n_aux, 4) || !rd(fd, is_aux.data(), max_label + 1)) return io_fail("%s: error reading isAux array", fname);
+    }
+    return JGPU_OK;
+}
+
+extern "C" int jgpu_load_jwnt(const char* path, float lm_scale, float ins_penalty, JgpuNet* out)
+{
+    if (!path || !out) return io_fail("jgpu_load_jwnt: null argument");
+    memset(out, 0, sizeof(*out));
+    FILE* fd = fopen(path, "rb");
+    if (!fd) return io_fail("WFSTNetwork::readBinary - error opening input file %s", path);
+    struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{fd};
+    char id[5] = {0, 0, 0, 0, 0};
+    int hdr[7];   // initState maxState nStates maxOutTransitions wordEndMarker silMarker spMarker
+    if (!rd(fd, id, 4) || strcmp(id, "JWNT") != 0) return io_fail("%s: WFSTNetwork::readBinary - invalid ID", path);
+    if (!rd(fd, hdr, sizeof(hdr))) return io_fail("%s: error reading header", path);
+    const int init_state = hdr[0], max_state = hdr[1];
+    if (max_state < 0 || init_state < 0 || init_state > max_state) return io_fail("%s: bad initState / maxState", path);
+    const int n_states = max_state + 1;
+    std::vector<int> st_first(n_states, 0), st_n(n_states, 0), st_fin(n_states, -1);
+    std::vector<std::vector<int>> st_trans(n_states);
+    for (int s = 0; s < n_states; ++s) {
+        int rec[3];   // label finalInd nTrans
+        if (!rd(fd, rec, sizeof(rec)) || rec[2] < 0) return io_fail("%s: error reading states[%d]", path, s);
+        st_fin[s] = rec[1];
+        st_n[s] = rec[2];
+        if (rec[2] > 0) {
+            st_trans[s].resize(rec[2]);
+            if (!rd(fd, st_trans[s].data(), (size_t)rec[2] * 4)) return io_fail("%s: error reading states[%d].trans array", path, s);
+            st_first[s] = st_trans[s][0];                 // getTransitions(prev, &next): first arc + count (:709-721)
+        }
+    }
+    int n_final;
+    if (!rd(fd, &n_final, 4) || n_final < 0) return io_fail("%s: error reading nFinalStates", path);
+    std::vector<int> fin_id(n_final);
+    std::vector<float> fin_w(n_final);
+    for (int i = 0; i < n_final; ++i)
+        if (!rd(fd, &fin_id[i], 4) || !rd(fd, &fin_w[i], 4)) return io_fail("%s: error reading finalStates", path);
+    int n_arcs;
+    if (!rd(fd, &n_arcs, 4) || n_arcs < 0) return io_fail("%s: error reading nTransitions", path);
+    std::vector<int> to(n_arcs), in(n_arcs), ol(n_arcs);
+    std::vector<float> w(n_arcs);
+    for (int a = 0; a < n_arcs; ++a) {
+        int tid;
+        if (!rd(fd, &tid, 4) || !rd(fd, &to[a], 4) || !rd(fd, &w[a], 4) || !rd(fd, &in[a], 4) || !rd(fd, &ol[a], 4))
+            return io_fail("%s: error reading transitions", path);
+        if (to[a] < 0 || to[a] > max_state || in[a] < 0 || ol[a] < 0) return io_fail("%s: transition %d out of range", path, a);
+    }
+    for (int k = 0; k < 2; ++k) {
+        unsigned char have;
+        if (!rd(fd, &have, 1)) return io_fail("%s: error reading haveAlphabet", path);
+        if (have) { int rc = skip_alphabet(fd, path); if (rc) return rc; }
+    }
+    char id2[5] = {0, 0, 0, 0, 0};
+    if (!rd(fd, id2, 4) || strcmp(id2, "JWNT") != 0) return io_fail("%s: WFSTNetwork::readBinary - invalid ID (2)", path);
+
+    if (lm_scale != 1.0f)
+        for (int a = 0; a < n_arcs; ++a) w[a] *= lm_scale;
+    if (ins_penalty != 0.0f)
+        for (int a = 0; a < n_arcs; ++a)
+            if (ol[a] > 0) w[a] += ins_penalty;
+    std::vector<float> st_final(n_states, LZ);
+    for (int s = 0; s < n_states; ++s) {
+        if (st_fin[s] >= 0) {
+            if (st_fin[s] >= n_final) return io_fail("%s: state %d: finalInd out of range", path, s);
+            st_final[s] = fin_w[st_fin[s]];
+        }
+        if (st_n[s] > 0) {
+            if (st_first[s] < 0 || st_first[s] + st_n[s] > n_arcs) return io_fail("%s: arcs of state %d out of range", path, s);
+            for (int k = 0; k < st_n[s]; ++k)             // the decoder takes nTrans arcs from the first one on
+                if (st_trans[s][k] != st_first[s] + k) return io_fail("%s: arcs of state %d are not contiguous", path, s);
+        }
+    }
+    out->n_states = n_states;
+    out->n_arcs = n_arcs;
+    out->init_state = init_state;
+    out->arc_to = dup_vec(to);
+    out->arc_weight = dup_vec(w);
+    out->arc_in = dup_vec(in);
+    out->arc_out = dup_vec(ol);
+    out->state_first = dup_vec(st_first);
+    out->state_narcs = dup_vec(st_n);
+    out->state_final = dup_vec(st_final);
+    return JGPU_OK;
+}
+
 extern "C" int jgpu_free_net(JgpuNet* n)
 {
     if (!n) return JGPU_OK;

@@ -133,6 +133,11 @@ class OracleRef:
                                                                 "trP", "se", "gmm_ncomp", "dets", "means", "ivars")])
         return r
 
+    def write_jwnt(self, path: str) -> None:
+        """WFSTNetwork::writeBinary of the network as loaded (src/WFSTNetwork.cpp:1106-1226)."""
+        self.lib.oref_write_jwnt.argtypes = [C.c_void_p, C.c_char_p]
+        self.lib.oref_write_jwnt(self.h, path.encode())
+
     def dump_net(self) -> Dict[str, np.ndarray]:
         A, S = self.n_arcs, self.n_states
         r = dict(arc_to=np.zeros(A, np.int32), arc_w=np.zeros(A, np.float32), arc_in=np.zeros(A, np.int32),
@@ -141,6 +146,36 @@ class OracleRef:
         self.lib.oref_dump_net(self.h, *[_fp(r[k]) for k in ("arc_to", "arc_w", "arc_in", "arc_out",
                                                              "st_first", "st_n", "st_final")])
         return r
+
+
+class RefJwnt:
+    """A network read by the reference's own WFSTNetwork::readBinary (JWNT), tables through public getters."""
+
+    def __init__(self, path: str, lm_scale: float = 1.0, ins_penalty: float = 0.0):
+        self.lib = C.CDLL(REF_SO)
+        self.lib.oref_net_from_jwnt.restype = C.c_void_p
+        self.lib.oref_net_from_jwnt.argtypes = [C.c_char_p, C.c_float, C.c_float]
+        self.lib.oref_net_dims.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.oref_dump_net.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+        self.lib.oref_destroy.argtypes = [C.c_void_p]
+        self.h = self.lib.oref_net_from_jwnt(path.encode(), lm_scale, ins_penalty)
+        d = np.zeros(3, np.int32)
+        self.lib.oref_net_dims(self.h, _fp(d))
+        self.n_states, self.n_arcs, self.init_state = (int(x) for x in d)
+
+    def dump_net(self) -> Dict[str, np.ndarray]:
+        A, S = self.n_arcs, self.n_states
+        r = dict(arc_to=np.zeros(A, np.int32), arc_w=np.zeros(A, np.float32), arc_in=np.zeros(A, np.int32),
+                 arc_out=np.zeros(A, np.int32), st_first=np.zeros(S, np.int32), st_n=np.zeros(S, np.int32),
+                 st_final=np.zeros(S, np.float32))
+        self.lib.oref_dump_net(self.h, *[_fp(r[k]) for k in ("arc_to", "arc_w", "arc_in", "arc_out",
+                                                             "st_first", "st_n", "st_final")])
+        return r
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.oref_destroy(self.h)
+            self.h = None
 
 
 class OraclePort:

@@ -90,6 +90,31 @@ void oref_destroy(void* hv)
     delete h->dec; delete h->net; delete h->models; delete h;
 }
 
+/* JWNT binary networks (WFSTNetwork::writeBinary / readBinary, src/WFSTNetwork.cpp:1106-1370): write the
+ * network of a handle, or open a network-only handle from a JWNT file (models and decoder stay NULL; only
+ * oref_net_dims / oref_dump_net / oref_destroy may be used on it). */
+int oref_write_jwnt(void* hv, const char* path)
+{
+    Handle* h = (Handle*)hv;
+    h->net->writeBinary(path);
+    return 0;
+}
+
+void* oref_net_from_jwnt(const char* path, float lmScale, float insPenalty)
+{
+    Handle* h = new Handle;
+    h->blockSize = 0; h->models = NULL; h->dec = NULL;
+    h->net = new WFSTNetwork(lmScale, insPenalty);
+    h->net->readBinary(path);
+    return h;
+}
+
+void oref_net_dims(void* hv, int* out3)
+{
+    Handle* h = (Handle*)hv;
+    out3[0] = h->net->getNumStates(); out3[1] = h->net->getNumTransitions(); out3[2] = h->net->getInitState();
+}
+
 /* dims[0..7] = vecSize nGMMs nHMMs nTransMats maxStates maxComps nNetStates nArcs ; dims[8]=initState */
 void oref_dims(void* hv, int* dims)
 {

@@ -39,6 +39,7 @@ def main() -> None:
         ps = synth.PathSampler(net, m, tee_hmms=tee)
         rng = np.random.default_rng(1000 + len(name))
         o = OracleRef(files, **kw)
+        o.write_jwnt(os.path.join(d, name + ".jwnt"))        # the same network through WFSTNetwork::writeBinary
         out = {}
         feats = []
         for u in range(n_utts):
