@@ -17,8 +17,8 @@
 //                                 token planes          tok[2][S-1][cap] float4{score,ac,lm,path}
 //   per lane, dense             : slotmap[nArcs] u32 = epoch stamp << 20 | list position + 1 — the GPU form of
 //                                   WFSTTransition::hook, valid iff the stamp is the current epoch
-//                                 state_key[nStates] u64 (per-state max of arriving tokens, self-cleaning;
-//                                   only touched for states that can see more than one arrival per frame)
+//                                 state_key[nMulti] u64 (per-state max of arriving tokens, self-cleaning), for the
+//                                   states that can see more than one arrival per frame (numbered first)
 //   per lane, per frame scratch : arrival records (token plane + {via, state, label} plane, stored round after round)
 //   per lane, per utterance     : word-boundary arena paths[cap_paths] (32 B records)
 //
@@ -109,6 +109,8 @@ struct Dev {
     const float4* lr;          // [n_class][2]: left-to-right classes {a01,a11,a12,a22 | a23,a33,a34,-}
     int n_arcs, n_states, init_state, n_hmms, n_gmms, S;
     unsigned init_multi;       // JG_MULTI when the initial state can receive more than one arrival per frame
+    int n_multi;               // states are renumbered so that the multi-arrival ones are 0 .. n_multi-1: state_key has
+                               // n_multi entries per lane (c3: 11 % of the states) and stays L2-sized
     // settings
     float start_beam, main_beam, end_beam, word_beam;
     int max_hyps, hist_min, hist_max, hist_nbins;

@@ -288,6 +288,18 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
             for (int b = n->state_first[s]; b < n->state_first[s] + n->state_narcs[s]; ++b)
                 if (pass[b]) multi[n->arc_to[b]] = 1;
     d.init_multi = multi[n->init_state] ? JG_MULTI : 0u;
+    // Internal state numbering: multi-arrival states first, so that the per-lane state_key table only spans them
+    // (a dense table over all states is 3.5 MB per lane on c3 and every touch of it a DRAM miss).  State ids never
+    // leave the engine.
+    std::vector<int> new_id(NS);
+    int n_multi = 0;
+    for (int s = 0; s < NS; ++s) if (multi[s]) new_id[s] = n_multi++;
+    {
+        int k = n_multi;
+        for (int s = 0; s < NS; ++s) if (!multi[s]) new_id[s] = k++;
+    }
+    d.n_multi = std::max(n_multi, 1);
+    d.init_state = new_id[n->init_state];
     // Which states have work for the expansion rounds at all?  Final states (best final token, :513-520) and states
     // with epsilon / tee out-arcs.  An exit token reaching any other state skips the rounds: if the state has a single
     // arrival per frame its word-boundary record is written inside k_internal, otherwise by the commit for the arrival
@@ -314,7 +326,7 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
                 int wbits;
                 memcpy(&wbits, &n->arc_weight[b], 4);
                 const int to = n->arc_to[b];
-                arcs[pos] = make_int4(to | (multi[to] ? (int)JG_MULTI : 0) | (round_work[to] ? (int)JG_ROUND : 0), wbits, in, n->arc_out[b]);
+                arcs[pos] = make_int4(new_id[to] | (multi[to] ? (int)JG_MULTI : 0) | (round_work[to] ? (int)JG_ROUND : 0), wbits, in, n->arc_out[b]);
                 arc_tee[pos] = tee_in[b];
                 ++pos;
                 n_eps += cls == 0; n_tee += cls == 1;
@@ -323,7 +335,7 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
             return fail(JGPU_E_ARG, "state %d has %d epsilon / %d tee out-arcs (limit 65535 each)", s, n_eps, n_tee);
         int fbits;
         memcpy(&fbits, &n->state_final[s], 4);
-        states[s] = make_int4(f, k, fbits, n_eps | (n_tee << 16));
+        states[new_id[s]] = make_int4(f, k, fbits, n_eps | (n_tee << 16));
         max_deg = std::max(max_deg, k - n_eps);
         n_huge_states += (k - n_eps) >= JG_HUGE_DEG;
     }
@@ -485,7 +497,7 @@ int build_state(jgpu_handle* h)
     }
 
     const size_t cap = d.cap, P = d.S - 1;
-    size_t need = L * (2 * cap * 16 + 2 * P * cap * 16 + (size_t)d.n_arcs * 4 + (size_t)d.n_states * 8 +
+    size_t need = L * (2 * cap * 16 + 2 * P * cap * 16 + (size_t)d.n_arcs * 4 + (size_t)d.n_multi * 8 +
                        (size_t)d.cap_arr * 36 + (size_t)d.cap_paths * 36);
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
@@ -507,7 +519,7 @@ int build_state(jgpu_handle* h)
     if ((rc = h->alloc(&d.inst_meta, L * 2 * cap, false))) return rc;
     if ((rc = h->alloc(&d.tok, L * 2 * P * cap, false))) return rc;
     if ((rc = h->alloc(&d.slotmap, L * d.n_arcs))) return rc;
-    if ((rc = h->alloc(&d.state_key, L * d.n_states))) return rc;
+    if ((rc = h->alloc(&d.state_key, L * d.n_multi))) return rc;
     if ((rc = h->alloc(&d.arr_tok, L * d.cap_arr, false))) return rc;
     if ((rc = h->alloc(&d.arr_meta, L * d.cap_arr, false))) return rc;
     if ((rc = h->alloc(&d.huge, L * d.cap_huge, false))) return rc;
@@ -774,7 +786,7 @@ int run_schedule(jgpu_handle* h, const std::vector<int4>& sched, int n_steps, co
                     for (int l = 0; l < L; ++l) {
                         if ((chunk[(size_t)i * L + l].z & 3) == JG_MODE_IDLE) continue;
                         if (((++h->host_epoch[l]) & 0x7ffu) == 0u) {
-                            CK(cudaMemsetAsync(h->d.state_key + (size_t)l * d.n_states, 0, (size_t)d.n_states * sizeof(u64), h->stream));
+                            CK(cudaMemsetAsync(h->d.state_key + (size_t)l * d.n_multi, 0, (size_t)d.n_multi * sizeof(u64), h->stream));
                             CK(cudaMemsetAsync(h->d.slotmap + (size_t)l * d.n_arcs, 0, (size_t)d.n_arcs * sizeof(unsigned), h->stream));
                         }
                     }

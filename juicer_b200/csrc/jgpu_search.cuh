@@ -54,7 +54,7 @@ __device__ __forceinline__ LaneView lane_view(const Dev& d, int lane, LaneCtl* c
     v.tok_cur = d.tok + ((size_t)lane * 2 + flip) * P * cap;
     v.tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * P * cap;
     v.slotmap = d.slotmap + (size_t)lane * d.n_arcs;
-    v.skey = d.state_key + (size_t)lane * d.n_states;
+    v.skey = d.state_key + (size_t)lane * d.n_multi;
     v.arr_tok = d.arr_tok + (size_t)lane * d.cap_arr;
     v.arr_meta = d.arr_meta + (size_t)lane * d.cap_arr;
     v.huge = d.huge + (size_t)lane * d.cap_huge;
@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
             d.arr_tok[(size_t)lane * d.cap_arr + e] = ex;
             d.arr_meta[(size_t)lane * d.cap_arr + e] = make_int4(via, meta.z, meta.w, 0);
             if (FUSE && meta.z < 0)                       // destination can see several arrivals this frame
-                atomicMax(d.state_key + (size_t)lane * d.n_states + (meta.z & JG_STATE_MASK),
+                atomicMax(d.state_key + (size_t)lane * d.n_multi + (meta.z & JG_STATE_MASK),
                           state_key_of(epoch, ex.x, (unsigned)e));
         }
         JG_TRACE_AT(6);                                       // stores issued: end of the first chunk
@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_filter(Dev d)
             if (score > thr) {
                 proc = 1;
                 if (m.y < 0)
-                    atomicMax(d.state_key + (size_t)lane * d.n_states + (m.y & JG_STATE_MASK),
+                    atomicMax(d.state_key + (size_t)lane * d.n_multi + (m.y & JG_STATE_MASK),
                               state_key_of(sh.epoch[lane], score, (unsigned)e));
             } else {
                 d.arr_meta[(size_t)lane * d.cap_arr + e].x = -2;
@@ -872,7 +872,7 @@ __device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, 
                 d.arr_tok[(size_t)lane * d.cap_arr + r] = t;
                 d.arr_meta[(size_t)lane * d.cap_arr + r] = make_int4(b, a.x, a.w, 0);
                 if (a.x < 0)
-                    atomicMax(d.state_key + (size_t)lane * d.n_states + (a.x & JG_STATE_MASK), state_key_of(epoch, t.x, (unsigned)r));
+                    atomicMax(d.state_key + (size_t)lane * d.n_multi + (a.x & JG_STATE_MASK), state_key_of(epoch, t.x, (unsigned)r));
             }
         }
     } else {
@@ -963,7 +963,7 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
             const int4 st = __ldg(&d.states[q]);
             valid = m.x != -2;
             if (valid && m.y < 0)                             // still the best arrival of q?
-                valid = d.state_key[(size_t)lane * d.n_states + q] == state_key_of(epoch, tok.x, r);
+                valid = d.state_key[(size_t)lane * d.n_multi + q] == state_key_of(epoch, tok.x, r);
             if (valid) {
                 const int n_eps = st.w & 0xffff, n_tee = (unsigned)st.w >> 16;
                 JG_TRACE_AT(2);                               // state row (and key) loaded
