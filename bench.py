@@ -207,15 +207,15 @@ def algorithmic_bytes(stats: Dict[str, int], dims: Dict[str, int], n_rows: int) 
         # per live token; one arrival record per live exit token
         "k_internal": A * (16 + 16) + H * (16 + 16 + 4) + Ea * 32,
         # (only with an end / word beam) arrival records re-read and filtered
-        "k_seed": Ea * 16,
+        "k_filter": Ea * 16,
         # expansion round 0: arrival record + state row per record, word-boundary records
         "k_expand": E * (32 + 16) + P * 32,
         "k_expand_r1": 0.0, "k_expand_r2": 0.0,   # later rounds: a few hundred records per step
         # commit: arrival record + state row per record, arc + slotmap entry per arc walked, entry token +
         # instance record + slotmap entry per entry written (rows of hub-like states are walked by
-        # k_commit_huge, timed as k_expand_huge; their bytes are counted here)
+        # k_commit_huge; their bytes are counted here)
         "k_commit": E * (32 + 16) + X * (16 + 4) + W * (16 + 16 + 4),
-        "k_expand_huge": 0.0,
+        "k_commit_huge": 0.0,
         "k_boundary": 0.0,
         # one parameter pass per launch (frames x lanes rows share it) + features in, scores out
         "k_gmm_scores": dims["gmm_launches"] * G * M * (2 * D + 1) * 4 + n_rows * (D * 4 + G * 4),

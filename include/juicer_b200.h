@@ -201,8 +201,9 @@ int jgpu_set_stream(jgpu_handle* h, void* cuda_stream);
 /* Per-kernel device timing: while enabled, every launch is bracketed by CUDA events on the
  * launching stream.  jgpu_profile_read fills ms[k] / count[k] for k < JGPU_N_KERNELS (summed
  * since the last enable) and returns JGPU_N_KERNELS. */
-enum { JGPU_K_GMM = 0, JGPU_K_BOUNDARY, JGPU_K_INTERNAL, JGPU_K_SEED, JGPU_K_EXPAND, JGPU_K_EXPAND_HUGE,
-       JGPU_K_COMMIT, JGPU_K_EXPAND_R1, JGPU_K_EXPAND_R2, JGPU_N_KERNELS };   /* EXPAND = round 0, _R1 = round 1, _R2 = rounds >= 2 */
+enum { JGPU_K_GMM = 0, JGPU_K_BOUNDARY, JGPU_K_INTERNAL, JGPU_K_SEED /* k_filter */, JGPU_K_EXPAND,
+       JGPU_K_EXPAND_HUGE /* k_commit_huge */, JGPU_K_COMMIT, JGPU_K_EXPAND_R1, JGPU_K_EXPAND_R2,
+       JGPU_N_KERNELS };   /* EXPAND = expansion round 0, _R1 = round 1, _R2 = rounds >= 2 */
 int jgpu_profile(jgpu_handle* h, int32_t enable);
 int jgpu_profile_read(jgpu_handle* h, double* ms, int64_t* count);
 const char* jgpu_kernel_name(int32_t kind);

@@ -92,7 +92,7 @@ struct jgpu_handle {
     std::vector<LaneHost> lanes;
     int64_t launches = 0;
     JgpuStats batch_stats{};
-    char* static_base = nullptr;   // arcs | states | arc_tee | hmm tables: pinned in L2 by an access-policy window
+    char* static_base = nullptr;   // arcs | states | arc_tee | hmm tables
     size_t static_bytes = 0;
     bool own_stream = true;
     bool overlap = false;   // JUICER_B200_OVERLAP=1: score the next frame block on a second stream (no gain measured on B200:
@@ -388,9 +388,8 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
     }
 
     int rc;
-    // The static network + HMM tables live in ONE allocation so that a single L2 access-policy window can
-    // keep them resident: the per-lane dynamic tables stream gigabytes through L2 every frame and would
-    // otherwise evict the arc / state rows that every gather of the search kernels hits.
+    // The static network + HMM tables live in ONE allocation (an L2 access-policy window over it was measured:
+    // pinning them costs more L2 than it saves; the streams carry evict-first hints instead).
     auto pad256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t b_arcs = pad256(arcs.size() * sizeof(int4)), b_states = pad256(states.size() * sizeof(int4));
     const size_t b_tee = any_tee ? pad256(arc_tee.size() * sizeof(float)) : 0, b_info = pad256(info.size() * sizeof(int));
@@ -574,27 +573,6 @@ int build_state(jgpu_handle* h)
     h->lanes.assign(L, LaneHost());
     h->host_epoch.assign(L, 0u);
     return JGPU_OK;
-}
-
-// Pin the static network tables in L2 for the kernels of `st` (persisting hits, streaming misses).
-void apply_l2_window(jgpu_handle* h, cudaStream_t st)
-{
-    if (!h->static_base || !st) return;
-    int max_persist = 0, max_window = 0;
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
-    if (max_persist <= 0 || max_window <= 0) return;
-    const size_t want = std::min<size_t>(h->static_bytes, (size_t)max_persist);
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-    cudaStreamAttrValue v;
-    memset(&v, 0, sizeof(v));
-    v.accessPolicyWindow.base_ptr = h->static_base;
-    v.accessPolicyWindow.num_bytes = std::min<size_t>(h->static_bytes, (size_t)max_window);
-    v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)v.accessPolicyWindow.num_bytes);
-    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
-    cudaGetLastError();   // best effort: never fatal
 }
 
 void drop_graphs(jgpu_handle* h)
@@ -1006,8 +984,6 @@ int jgpu_create(const JgpuNet* net, const JgpuHmm* hmm, const JgpuGmm* gmm, cons
         }
     }
 #endif
-    // measured on B200/c3: pinning the static tables costs more L2 than it saves (177k vs 194k frames/s) -> opt-in
-    if (!rc && getenv("JUICER_B200_L2_WINDOW")) apply_l2_window(h, h->stream);
     if (!rc) {
         e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail(JGPU_E_CUDA, "create sync: %s", cudaGetErrorString(e));
@@ -1187,7 +1163,6 @@ int jgpu_set_stream(jgpu_handle* h, void* cuda_stream)
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     h->stream = (cudaStream_t)cuda_stream;
     h->own_stream = false;
-    if (getenv("JUICER_B200_L2_WINDOW")) apply_l2_window(h, h->stream);
     return JGPU_OK;
 }
 
@@ -1214,9 +1189,9 @@ int jgpu_profile_read(jgpu_handle* h, double* ms, int64_t* count)
 
 const char* jgpu_kernel_name(int32_t kind)
 {
-    // k_expand* = k_walk<0> by round (0, 1, >= 2), k_expand_huge = k_walk_huge<0>, k_commit = k_walk<1> + k_walk_huge<1>
-    static const char* names[JGPU_N_KERNELS] = {"k_gmm_scores", "k_boundary", "k_internal", "k_seed", "k_expand",
-                                                "k_expand_huge", "k_commit", "k_expand_r1", "k_expand_r2"};
+    // k_expand / _r1 / _r2 = k_walk<0> by round (0, 1, >= 2), k_commit = k_walk<1>, k_filter only with an end / word beam
+    static const char* names[JGPU_N_KERNELS] = {"k_gmm_scores", "k_boundary", "k_internal", "k_filter", "k_expand",
+                                                "k_commit_huge", "k_commit", "k_expand_r1", "k_expand_r2"};
     return (kind >= 0 && kind < JGPU_N_KERNELS) ? names[kind] : "";
 }
 

@@ -7,7 +7,7 @@ blocks that finish last — the tail the kernel duration is made of."""
 import sys
 import numpy as np
 
-NAMES = ["gmm", "boundary", "internal", "seed", "expand", "expand_huge", "commit", "expand_r1", "expand_r2"]
+NAMES = ["gmm", "boundary", "internal", "filter", "expand", "commit_huge", "commit", "expand_r1", "expand_r2"]
 dt = np.dtype([("kid", "i4"), ("block", "i4"), ("smid", "i4"), ("aux", "i4"), ("t0", "u8"), ("t1", "u8"), ("mark", "u4", (8,))])
 
 
