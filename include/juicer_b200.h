@@ -223,6 +223,15 @@ int jgpu_load_fsm(const char* fsm, const char* insyms, const char* outsyms, floa
 int jgpu_load_jwnt(const char* path, float lm_scale, float ins_penalty, JgpuNet* out);
 int jgpu_free_net(JgpuNet* net);
 int jgpu_load_jmbi(const char* path, JgpuHmm* hmm, JgpuGmm* gmm);
+/* jgpu_load_mmf   : HTK MMF text model definitions, same semantics as
+ *                   HTKFlatModels::Load(htkModelsFName, removeInitialToFinalTransitions)
+ *                   (src/HTKFlatModels.cpp:89-92 -> src/HTKModels.cpp:221-283): the tokens of
+ *                   src/htkparse.l.lpp, the grammar and checks of src/htkparse.y.ypp (~o ~h ~s ~t ~m ~v
+ *                   macros; ~u and other constructs are syntax errors as in the reference), then
+ *                   initFromHTKParseResult (src/HTKModels.cpp:397-444, 519-974), createTrPandSEIndex and the
+ *                   flat GMM tables.  remove_initial_to_final != 0 drops entry->exit (tee) transitions and
+ *                   re-normalises the entry row (src/HTKModels.cpp:921-969; juicer's -removeTeeModels). */
+int jgpu_load_mmf(const char* path, int32_t remove_initial_to_final, JgpuHmm* hmm, JgpuGmm* gmm);
 int jgpu_free_models(JgpuHmm* hmm, JgpuGmm* gmm);
 
 #ifdef __cplusplus

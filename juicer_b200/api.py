@@ -64,6 +64,7 @@ def load_library() -> C.CDLL:
     lib.jgpu_load_jwnt.argtypes = [C.c_char_p, C.c_float, C.c_float, vp]
     lib.jgpu_free_net.argtypes = [vp]
     lib.jgpu_load_jmbi.argtypes = [C.c_char_p, vp, vp]
+    lib.jgpu_load_mmf.argtypes = [C.c_char_p, i32, vp, vp]
     lib.jgpu_free_models.argtypes = [vp, vp]
     _lib = lib
     return lib
@@ -125,6 +126,16 @@ class HTKFlatModels:
         self.lib = load_library()
         self.hmm, self.gmm = JgpuHmm(), JgpuGmm()
         _check(self.lib.jgpu_load_jmbi(jmbi.encode(), C.byref(self.hmm), C.byref(self.gmm)), "jgpu_load_jmbi")
+
+    @classmethod
+    def from_mmf(cls, mmf: str, remove_initial_to_final: bool = False) -> "HTKFlatModels":
+        """HTK MMF text model definitions (HTKFlatModels::Load, src/HTKFlatModels.cpp:89-92)."""
+        self = cls.__new__(cls)
+        self.lib = load_library()
+        self.hmm, self.gmm = JgpuHmm(), JgpuGmm()
+        _check(self.lib.jgpu_load_mmf(mmf.encode(), int(remove_initial_to_final), C.byref(self.hmm), C.byref(self.gmm)),
+               "jgpu_load_mmf")
+        return self
 
     def arrays(self) -> Dict[str, np.ndarray]:
         h, g = self.hmm, self.gmm

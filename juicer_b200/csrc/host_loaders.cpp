@@ -10,6 +10,7 @@
 //                       createTrPandSEIndex                 src/HTKModels.cpp:2330-2390
 //                       tee weight                          src/HTKModels.cpp:1358-1370
 //                       HTKFlatModels::init                 src/HTKFlatModels.cpp:94-177
+//   (jgpu_load_mmf, the MMF text reader, lives in host_mmf.cpp and ends in the same jgpu_finish_models)
 // Host only: no CUDA calls here.
 #include <cfloat>
 #include <cstdarg>
@@ -21,6 +22,7 @@
 
 #include "../../include/juicer_b200.h"
 #include "jgpu_err.h"
+#include "host_models.h"
 
 std::string& jgpu_err_buf()
 {
@@ -96,6 +98,17 @@ bool rd_tag_name(FILE* f, const char* tag)
 }
 
 } // namespace
+
+int jgpu_io_fail(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    jgpu_err_buf() = buf;
+    return JGPU_E_IO;
+}
 
 extern "C" int jgpu_load_fsm(const char* fsm, const char* insyms, const char* outsyms, float lm_scale,
                              float ins_penalty, JgpuNet* out)
@@ -326,46 +339,45 @@ extern "C" int jgpu_load_jmbi(const char* path, JgpuHmm* hmm, JgpuGmm* gmm)
     if (!rd(f, hdr, 4, 7)) BAD("truncated header");
     const int D = hdr[0], nMean = hdr[1], nVar = hdr[2], nMix = hdr[3], nGMM = hdr[4], nTM = hdr[5], nHMM = hdr[6];
     if (D <= 0 || nMean < 0 || nVar < 0 || nMix < 0 || nGMM < 0 || nTM < 0 || nHMM < 0) BAD("bad counts");
-    std::vector<float> means((size_t)nMean * D), vars((size_t)nVar * D), gconst(nVar), skip(D);
+    RawModels m;
+    m.D = D;
+    m.means.resize((size_t)nMean * D); m.vars.resize((size_t)nVar * D); m.gconst.resize(nVar);
+    std::vector<float> skip(D);
     for (int i = 0; i < nMean; ++i) {
-        if (!rd_tag_name(f, "JMMN") || !rd(f, &means[(size_t)i * D], 4, D)) BAD("bad mean vector record");
+        if (!rd_tag_name(f, "JMMN") || !rd(f, &m.means[(size_t)i * D], 4, D)) BAD("bad mean vector record");
     }
     for (int i = 0; i < nVar; ++i) {
-        if (!rd_tag_name(f, "JMVR") || !rd(f, &vars[(size_t)i * D], 4, D) || !rd(f, skip.data(), 4, D) ||
-            !rd(f, &gconst[i], 4, 1))
+        if (!rd_tag_name(f, "JMVR") || !rd(f, &m.vars[(size_t)i * D], 4, D) || !rd(f, skip.data(), 4, D) ||
+            !rd(f, &m.gconst[i], 4, 1))
             BAD("bad variance vector record");
     }
-    std::vector<std::vector<int>> mix_mean(nMix), mix_var(nMix);
-    int maxC = 0;
+    m.mix_mean.resize(nMix); m.mix_var.resize(nMix); m.mix_name.resize(nMix);
     for (int i = 0; i < nMix; ++i) {
         int nc;
         if (!rd_tag_name(f, "JMMX") || !rd(f, &nc, 4, 1) || nc < 0) BAD("bad mixture record");
-        mix_mean[i].resize(nc);
-        mix_var[i].resize(nc);
-        if (!rd(f, mix_mean[i].data(), 4, nc) || !rd(f, mix_var[i].data(), 4, nc)) BAD("bad mixture record");
+        m.mix_mean[i].resize(nc);
+        m.mix_var[i].resize(nc);
+        if (!rd(f, m.mix_mean[i].data(), 4, nc) || !rd(f, m.mix_var[i].data(), 4, nc)) BAD("bad mixture record");
         for (int c = 0; c < nc; ++c)
-            if (mix_mean[i][c] < 0 || mix_mean[i][c] >= nMean || mix_var[i][c] < 0 || mix_var[i][c] >= nVar) BAD("mixture index out of range");
-        if (nc > maxC) maxC = nc;
+            if (m.mix_mean[i][c] < 0 || m.mix_mean[i][c] >= nMean || m.mix_var[i][c] < 0 || m.mix_var[i][c] >= nVar) BAD("mixture index out of range");
     }
-    std::vector<int> gmm_mix(nGMM);
-    std::vector<std::vector<float>> gmm_logw(nGMM);
+    m.gmm_mix.resize(nGMM); m.gmm_logw.resize(nGMM); m.gmm_name.resize(nGMM);
     for (int i = 0; i < nGMM; ++i) {
         int nc;
-        if (!rd_tag_name(f, "JMGM") || !rd(f, &gmm_mix[i], 4, 1) || !rd(f, &nc, 4, 1) || nc < 0) BAD("bad GMM record");
+        if (!rd_tag_name(f, "JMGM") || !rd(f, &m.gmm_mix[i], 4, 1) || !rd(f, &nc, 4, 1) || nc < 0) BAD("bad GMM record");
         std::vector<float> wts(nc);
-        gmm_logw[i].resize(nc);
-        if (!rd(f, wts.data(), 4, nc) || !rd(f, gmm_logw[i].data(), 4, nc)) BAD("bad GMM record");
-        if (gmm_mix[i] < 0 || gmm_mix[i] >= nMix) BAD("GMM mixture index out of range");
+        m.gmm_logw[i].resize(nc);
+        if (!rd(f, wts.data(), 4, nc) || !rd(f, m.gmm_logw[i].data(), 4, nc)) BAD("bad GMM record");
+        if (m.gmm_mix[i] < 0 || m.gmm_mix[i] >= nMix) BAD("GMM mixture index out of range");
     }
-    struct TM { int n; std::vector<int> nsucs; std::vector<std::vector<int>> sucs; std::vector<std::vector<float>> logp; };
-    std::vector<TM> tms(nTM);
+    m.tms.resize(nTM);
     for (int i = 0; i < nTM; ++i) {
-        TM& t = tms[i];
+        RawTransMat& t = m.tms[i];
         if (!rd_tag_name(f, "JMTM") || !rd(f, &t.n, 4, 1) || t.n <= 0 || t.n > 64) BAD("bad transition matrix record");
-        t.nsucs.resize(t.n);
-        if (!rd(f, t.nsucs.data(), 4, t.n)) BAD("bad transition matrix record");
+        std::vector<int> nsucs(t.n);
+        if (!rd(f, nsucs.data(), 4, t.n)) BAD("bad transition matrix record");
         int total = 0;
-        for (int s = 0; s < t.n; ++s) { if (t.nsucs[s] < 0) BAD("bad successor count"); total += t.nsucs[s]; }
+        for (int s = 0; s < t.n; ++s) { if (nsucs[s] < 0) BAD("bad successor count"); total += nsucs[s]; }
         std::vector<int> sucs(total);
         std::vector<float> probs(total), logp(total);
         if (!rd(f, sucs.data(), 4, total) || !rd(f, probs.data(), 4, total) || !rd(f, logp.data(), 4, total)) BAD("bad transition matrix record");
@@ -373,34 +385,48 @@ extern "C" int jgpu_load_jmbi(const char* path, JgpuHmm* hmm, JgpuGmm* gmm)
         t.logp.resize(t.n);
         int k = 0;
         for (int s = 0; s < t.n; ++s)
-            for (int j = 0; j < t.nsucs[s]; ++j, ++k) {
+            for (int j = 0; j < nsucs[s]; ++j, ++k) {
                 if (sucs[k] < 0 || sucs[k] >= t.n) BAD("successor out of range");
                 t.sucs[s].push_back(sucs[k]);
                 t.logp[s].push_back(logp[k]);
             }
     }
-    std::vector<int> hmm_n(nHMM), hmm_tm(nHMM);
-    std::vector<std::vector<int>> hmm_g(nHMM);
-    int maxS = 0;
+    m.hmm_n.resize(nHMM); m.hmm_tm.resize(nHMM); m.hmm_g.resize(nHMM);
     for (int i = 0; i < nHMM; ++i) {
-        if (!rd_tag_name(f, "JMHM") || !rd(f, &hmm_n[i], 4, 1) || hmm_n[i] <= 0 || hmm_n[i] > 64) BAD("bad HMM record");
-        hmm_g[i].resize(hmm_n[i]);
-        if (!rd(f, hmm_g[i].data(), 4, hmm_n[i]) || !rd(f, &hmm_tm[i], 4, 1)) BAD("bad HMM record");
-        if (hmm_tm[i] < 0 || hmm_tm[i] >= nTM || tms[hmm_tm[i]].n != hmm_n[i]) BAD("HMM / transition matrix mismatch");
-        if (hmm_n[i] > maxS) maxS = hmm_n[i];
+        if (!rd_tag_name(f, "JMHM") || !rd(f, &m.hmm_n[i], 4, 1) || m.hmm_n[i] <= 0 || m.hmm_n[i] > 64) BAD("bad HMM record");
+        m.hmm_g[i].resize(m.hmm_n[i]);
+        if (!rd(f, m.hmm_g[i].data(), 4, m.hmm_n[i]) || !rd(f, &m.hmm_tm[i], 4, 1)) BAD("bad HMM record");
+        if (m.hmm_tm[i] < 0 || m.hmm_tm[i] >= nTM || m.tms[m.hmm_tm[i]].n != m.hmm_n[i]) BAD("HMM / transition matrix mismatch");
     }
     unsigned char hybrid = 0;
     if (!rd(f, &hybrid, 1, 1)) BAD("missing hybridMode flag");
     fclose(f);
 #undef BAD
     if (hybrid) return io_fail("%s: hybrid (ANN posterior) models are outside the GMM decode path", path);
+    return jgpu_finish_models(m, hmm, gmm);
+}
+
+// Flat tables from the loaded records: trP / SEIndex (createTrPandSEIndex, src/HTKModels.cpp:2330-2390), tee
+// weight (:582-593 text load, :1358-1370 binary load) and the flat GMM parameters (HTKFlatModels::init,
+// src/HTKFlatModels.cpp:94-177).  Both load paths of the reference end in exactly these steps.
+int jgpu_finish_models(const RawModels& m, JgpuHmm* hmm, JgpuGmm* gmm)
+{
+    const int D = m.D, nMix = (int)m.mix_mean.size(), nGMM = (int)m.gmm_mix.size(), nHMM = (int)m.hmm_n.size();
+    const std::vector<RawTransMat>& tms = m.tms;
+    const std::vector<int>&hmm_n = m.hmm_n, &hmm_tm = m.hmm_tm, &gmm_mix = m.gmm_mix;
+    const std::vector<std::vector<int>>&hmm_g = m.hmm_g, &mix_mean = m.mix_mean, &mix_var = m.mix_var;
+    const std::vector<std::vector<float>>& gmm_logw = m.gmm_logw;
+    const std::vector<float>&means = m.means, &vars = m.vars, &gconst = m.gconst;
+    int maxS = 0, maxC = 0;
+    for (int i = 0; i < nHMM; ++i) if (hmm_n[i] > maxS) maxS = hmm_n[i];
+    for (int i = 0; i < nMix; ++i) if ((int)mix_mean[i].size() > maxC) maxC = (int)mix_mean[i].size();
 
     // ---- HMM view: trP / SEIndex / tee (src/HTKModels.cpp:2330-2390, :1358-1370) ----
     const int S = maxS;
     std::vector<int> o_n(hmm_n), o_gmm((size_t)nHMM * S, -1), o_se((size_t)nHMM * S * 2, 0);
     std::vector<float> o_trp((size_t)nHMM * S * S, LZ), o_tee(nHMM, LZ);
     for (int i = 0; i < nHMM; ++i) {
-        const TM& t = tms[hmm_tm[i]];
+        const RawTransMat& t = tms[hmm_tm[i]];
         const int n = t.n;
         std::vector<float> trp((size_t)n * n, LZ);
         for (int j = 0; j < n; ++j)

@@ -208,6 +208,85 @@ def write_jmbi(m: Models, path: str) -> None:
         f.write(b"".join(out))
 
 
+
+def write_mmf(m: Models, path: str, *, upper: bool = True, var_floor_macro: bool = True, digits: int = 9) -> None:
+    """The same model set as HTK MMF text, laid out the way HTK's HHEd writes it: one ~o header
+    (<STREAMINFO> <VECSIZE> <NULLD> <MFCC_E_D_A> <DIAGC>), an (ignored) ~v variance-floor macro, ~t macros for
+    transition matrices used by several HMMs, ~s macros for GMMs tied across several HMM states, then the ~h
+    definitions; single-component states carry no <NUMMIXES>/<MIXTURE> lines; <GCONST> is written (the reader
+    recomputes it, src/HTKModels.cpp:839-875).  `digits` significant digits: 9 round-trips float32 exactly,
+    HTK itself prints 7 (%e)."""
+    D = m.dim
+    kw = (lambda s: f"<{s.upper()}>") if upper else (lambda s: f"<{s}>")
+    fmt = f"%.{digits - 1}e"
+    vec = lambda v: " " + " ".join(fmt % float(x) for x in v)          # noqa: E731
+    gmm_uses = np.zeros(m.n_gmm, dtype=np.int64)
+    for row in m.hmm_gmm:
+        for g in row:
+            if g >= 0:
+                gmm_uses[g] += 1
+    tm_uses = np.bincount(np.asarray(m.hmm_tmat), minlength=len(m.tmats))
+    out: List[str] = []
+
+    def emit_tmat(t: TransMat, indent: str) -> None:
+        out.append(f"{indent}{kw('TransP')} {t.n_states}")
+        dense = np.zeros((t.n_states, t.n_states), dtype=np.float32)
+        for i, (ss, pp) in enumerate(zip(t.sucs, t.probs)):
+            for j, p in zip(ss, pp):
+                dense[i, j] = np.float32(p)
+        for i in range(t.n_states):
+            out.append(indent + vec(dense[i]))
+
+    def emit_gmm(g: int, indent: str) -> None:
+        w, mu, var = m.weights[g], m.means[g], m.vars_[g]
+        n = len(w)
+        if n > 1:
+            out.append(f"{indent}{kw('NumMixes')} {n}")
+        for c in range(n):
+            if n > 1:
+                out.append(f"{indent}{kw('Mixture')} {c + 1} " + fmt % float(w[c]))
+            out.append(f"{indent}{kw('Mean')} {D}")
+            out.append(indent + vec(mu[c]))
+            out.append(f"{indent}{kw('Variance')} {D}")
+            out.append(indent + vec(var[c]))
+            gc = D * LOG_2_PI + float(np.sum(np.log(var[c].astype(np.float64))))
+            out.append(f"{indent}{kw('GConst')} " + "%e" % gc)
+
+    out.append("~o")
+    out.append(f"{kw('StreamInfo')} 1 {D}")
+    out.append(f"{kw('VecSize')} {D}{kw('NullD')}<MFCC_E_D_A>{kw('DiagC')}")
+    if var_floor_macro:
+        out.append('~v "varFloor1"')
+        out.append(f"{kw('Variance')} {D}")
+        out.append(vec(np.full(D, 0.01, dtype=np.float32)))
+    for k, t in enumerate(m.tmats):
+        if tm_uses[k] > 1:
+            out.append(f'~t "T_{k}"')
+            emit_tmat(t, "")
+    for g in range(m.n_gmm):
+        if gmm_uses[g] > 1:
+            out.append(f'~s "ST_{g}"')
+            emit_gmm(g, "")
+    for h in range(m.n_hmm):
+        out.append(f'~h "{m.hmm_names[h]}"')
+        out.append(kw("BeginHMM"))
+        out.append(f"{kw('NumStates')} {m.hmm_nstates[h]}")
+        for s in range(1, m.hmm_nstates[h] - 1):
+            g = m.hmm_gmm[h][s]
+            out.append(f"{kw('State')} {s + 1}")
+            if gmm_uses[g] > 1:
+                out.append(f'~s "ST_{g}"')
+            else:
+                emit_gmm(g, "")
+        k = m.hmm_tmat[h]
+        if tm_uses[k] > 1:
+            out.append(f'~t "T_{k}"')
+        else:
+            emit_tmat(m.tmats[k], "")
+        out.append(kw("EndHMM"))
+    with open(path, "w") as f:
+        f.write("\n".join(out) + "\n")
+
 # --------------------------------------------------------------------------------------
 # networks
 # --------------------------------------------------------------------------------------

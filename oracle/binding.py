@@ -77,7 +77,10 @@ def _words_from(buf, n: int) -> List[Dict]:
 class OracleRef:
     def __init__(self, files: Dict[str, str], *, main_beam: float, start_beam: float = 0.0,
                  end_beam: float = 0.0, word_beam: float = 0.0, max_hyps: int = 0,
-                 lm_scale: float = 1.0, ins_penalty: float = 0.0, block_size: int = 5):
+                 lm_scale: float = 1.0, ins_penalty: float = 0.0, block_size: int = 5,
+                 remove_tee: bool = False):
+        """files["jmbi"] (HTKFlatModels::readBinary) or, when only files["mmf"] is given, the MMF text form
+        (HTKFlatModels::Load(mmf, remove_tee), on top of oracle/shim/htkparse_rd.cpp)."""
         if not os.path.exists(REF_SO):
             raise RuntimeError(f"{REF_SO} missing: run `make -C oracle ref` where /root/reference exists")
         self.lib = C.CDLL(REF_SO)
@@ -91,9 +94,16 @@ class OracleRef:
         self.lib.oref_dump_models.argtypes = [C.c_void_p] * 11
         self.lib.oref_dump_net.argtypes = [C.c_void_p] * 8
         self.lib.oref_destroy.argtypes = [C.c_void_p]
-        self.h = self.lib.oref_create(files["jmbi"].encode(), files["fsm"].encode(), files["insyms"].encode(),
-                                      files["outsyms"].encode(), lm_scale, ins_penalty, start_beam, main_beam,
-                                      end_beam, word_beam, max_hyps, block_size)
+        if "jmbi" in files:
+            self.h = self.lib.oref_create(files["jmbi"].encode(), files["fsm"].encode(), files["insyms"].encode(),
+                                          files["outsyms"].encode(), lm_scale, ins_penalty, start_beam, main_beam,
+                                          end_beam, word_beam, max_hyps, block_size)
+        else:
+            self.lib.oref_create_mmf.restype = C.c_void_p
+            self.lib.oref_create_mmf.argtypes = [C.c_char_p, C.c_int] + [C.c_char_p] * 3 + [C.c_float] * 6 + [C.c_int, C.c_int]
+            self.h = self.lib.oref_create_mmf(files["mmf"].encode(), int(remove_tee), files["fsm"].encode(),
+                                              files["insyms"].encode(), files["outsyms"].encode(), lm_scale, ins_penalty,
+                                              start_beam, main_beam, end_beam, word_beam, max_hyps, block_size)
         d = np.zeros(16, dtype=np.int32)
         self.lib.oref_dims(self.h, _fp(d))
         (self.dim, self.n_gmm, self.n_hmm, self.n_tmat, self.max_states, self.max_comps,
@@ -146,6 +156,44 @@ class OracleRef:
         self.lib.oref_dump_net(self.h, *[_fp(r[k]) for k in ("arc_to", "arc_w", "arc_in", "arc_out",
                                                              "st_first", "st_n", "st_final")])
         return r
+
+
+class RefModels:
+    """Acoustic models loaded by the reference alone: HTKFlatModels::Load (MMF text, parsed by
+    oracle/shim/htkparse_rd.cpp, everything after the parse is the reference's own code) or ::readBinary (JMBI)."""
+
+    def __init__(self, path: str, *, remove_tee: bool = False, block_size: int = 5):
+        if not os.path.exists(REF_SO):
+            raise RuntimeError(f"{REF_SO} missing: run `make -C oracle ref` where /root/reference exists")
+        self.lib = lib = C.CDLL(REF_SO)
+        lib.oref_models_from_mmf.restype = C.c_void_p
+        lib.oref_models_from_mmf.argtypes = [C.c_char_p, C.c_int, C.c_int]
+        lib.oref_models_from_jmbi.restype = C.c_void_p
+        lib.oref_models_from_jmbi.argtypes = [C.c_char_p, C.c_int]
+        lib.oref_model_dims.argtypes = [C.c_void_p, C.c_void_p]
+        lib.oref_dump_models.argtypes = [C.c_void_p] * 11
+        lib.oref_write_models.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        lib.oref_gmm_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        lib.oref_destroy.argtypes = [C.c_void_p]
+        with open(path, "rb") as f:
+            binary = f.read(4) == b"JMBI"
+        self.h = lib.oref_models_from_jmbi(path.encode(), block_size) if binary else \
+            lib.oref_models_from_mmf(path.encode(), int(remove_tee), block_size)
+        d = np.zeros(8, dtype=np.int32)
+        lib.oref_model_dims(self.h, _fp(d))
+        self.dim, self.n_gmm, self.n_hmm, self.n_tmat, self.max_states, self.max_comps = (int(x) for x in d[:6])
+
+    dump_models = OracleRef.dump_models
+    gmm_scores = OracleRef.gmm_scores
+
+    def write(self, path: str, binary: bool) -> None:
+        """HTKModels::output (src/HTKModels.cpp:993-1109): JMBI when binary, else the reference's MMF text."""
+        self.lib.oref_write_models(self.h, path.encode(), int(binary))
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.oref_destroy(self.h)
+            self.h = None
 
 
 class RefJwnt:

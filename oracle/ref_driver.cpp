@@ -84,6 +84,62 @@ void* oref_create(const char* jmbi, const char* fsm, const char* insyms, const c
     return h;
 }
 
+/* MMF text models (HTKFlatModels::Load -> HTKModels::Load, src/HTKModels.cpp:221-283): the UNMODIFIED reference
+ * semantics on top of oracle/shim/htkparse_rd.cpp (bison/flex are not available to generate the reference's own
+ * parser).  oref_create_mmf is oref_create with the models read from MMF text; oref_models_from_mmf opens a
+ * models-only handle (net and decoder stay NULL: only oref_model_dims / oref_dump_models / oref_write_models /
+ * oref_gmm_scores / oref_destroy may be used on it); oref_models_from_jmbi is the same for a JMBI file. */
+void* oref_create_mmf(const char* mmf, int removeTee, const char* fsm, const char* insyms, const char* outsyms,
+                      float lmScale, float insPenalty,
+                      float startBeam, float mainBeam, float endBeam, float wordBeam, int maxHyps, int blockSize)
+{
+    Handle* h = new Handle;
+    h->blockSize = blockSize;
+    h->models = new RefModels;
+    h->models->setBlockSize(blockSize);
+    h->models->Load(mmf, removeTee != 0);
+    h->net = new WFSTNetwork(fsm, insyms, outsyms, lmScale, insPenalty, REMOVEBOTH);
+    h->dec = new RefDecoder(h->net, h->models, startBeam, mainBeam, endBeam, wordBeam, maxHyps);
+    return h;
+}
+
+void* oref_models_from_mmf(const char* mmf, int removeTee, int blockSize)
+{
+    Handle* h = new Handle;
+    h->blockSize = blockSize; h->net = NULL; h->dec = NULL;
+    h->models = new RefModels;
+    h->models->setBlockSize(blockSize);
+    h->models->Load(mmf, removeTee != 0);
+    return h;
+}
+
+void* oref_models_from_jmbi(const char* jmbi, int blockSize)
+{
+    Handle* h = new Handle;
+    h->blockSize = blockSize; h->net = NULL; h->dec = NULL;
+    h->models = new RefModels;
+    h->models->setBlockSize(blockSize);
+    h->models->readBinary(jmbi);
+    return h;
+}
+
+/* HTKModels::output (src/HTKModels.cpp:993-1109): binary != 0 writes JMBI, else the reference's MMF text form. */
+int oref_write_models(void* hv, const char* path, int binary)
+{
+    Handle* h = (Handle*)hv;
+    h->models->output(path, binary != 0);
+    return 0;
+}
+
+/* dims[0..5] = vecSize nGMMs nHMMs nTransMats maxStates maxComps */
+void oref_model_dims(void* hv, int* dims)
+{
+    Handle* h = (Handle*)hv;
+    dims[0] = h->models->dimVec();   dims[1] = h->models->dimGMMs();
+    dims[2] = h->models->dimHMMs();  dims[3] = h->models->dimTMats();
+    dims[4] = h->models->maxStates(); dims[5] = h->models->maxComps();
+}
+
 void oref_destroy(void* hv)
 {
     Handle* h = (Handle*)hv;

@@ -52,6 +52,58 @@ class Golden:
             assert np.array_equal(bits(frame_best), z[f"best{u}"]), tag
 
 
+MMF_CASES = ["tee", "mixed"]
+MODEL_TABLES = ("hmm_nstates", "hmm_gmm", "hmm_tee", "trP", "se", "gmm_ncomp", "dets", "means", "ivars")
+
+
+class _Prefixed:
+    """npz view that prepends a key prefix (expected_mmf.npz holds one result set per load flag)."""
+
+    def __init__(self, z, prefix: str):
+        self.z, self.prefix = z, prefix
+
+    def __getitem__(self, k: str):
+        return self.z[self.prefix + k]
+
+
+class GoldenMmf(Golden):
+    """The MMF (HTK text) form of a golden fixture: <name>.mmf + expected_mmf.npz (tools/make_golden_mmf.py):
+    the tables the reference holds after HTKFlatModels::Load(mmf, remove_tee) and its decode results."""
+
+    def __init__(self, name: str, remove_tee: bool = False):
+        super().__init__(name)
+        self.remove_tee = bool(remove_tee)
+        self.zx = self.z                                     # features live in expected.npz
+        self.zm = np.load(os.path.join(self.dir, "expected_mmf.npz"))
+        self.z = _Prefixed(self.zm, f"r{int(self.remove_tee)}_")
+        self.files = dict(self.files, mmf=os.path.join(self.dir, name + ".mmf"))
+
+    def feats(self, u: int) -> np.ndarray:
+        return np.ascontiguousarray(self.zx[f"x{u}"], dtype=np.float32)
+
+    def tables(self, prefix: str = None) -> Dict[str, np.ndarray]:
+        prefix = prefix or f"r{int(self.remove_tee)}_tab_"
+        return {k: self.zm[prefix + k] for k in MODEL_TABLES}
+
+
+def same_model_tables(ref: Dict[str, np.ndarray], mine: Dict[str, np.ndarray], what: str = "") -> None:
+    """Bit-exact comparison of the flat model tables (floats as uint32 bit patterns on either side)."""
+    for k in MODEL_TABLES:
+        x, y = np.asarray(ref[k]), np.asarray(mine[k])
+        x = x.view(np.uint32) if x.dtype == np.float32 else x
+        y = y.view(np.uint32) if y.dtype == np.float32 else y
+        assert x.shape == y.shape, f"{what}: {k} shape {x.shape} vs {y.shape}"
+        assert np.array_equal(x, y), f"{what}: {k}"
+
+
+def flat_tables_from_mmf(files: Dict[str, str], remove_tee: bool = False, lm_scale: float = 1.0, ins_penalty: float = 0.0):
+    from juicer_b200 import _abi, api
+    net = api.WFSTNetwork(files["fsm"], files["insyms"], files["outsyms"], lm_scale, ins_penalty)
+    models = api.HTKFlatModels.from_mmf(files["mmf"], remove_tee)
+    tabs = _abi.FlatTables(net.arrays(), net.init_state, models.arrays())
+    return tabs, net, models
+
+
 def flat_tables_from_files(files: Dict[str, str], lm_scale: float = 1.0, ins_penalty: float = 0.0):
     """files -> product host loaders -> FlatTables (+ the loader objects that own the memory)."""
     from juicer_b200 import _abi, api

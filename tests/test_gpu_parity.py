@@ -7,7 +7,7 @@ compared bit-for-bit as well; where noted, the fall-back tolerance is north_star
 import numpy as np
 import pytest
 
-from helpers import GOLDEN_CASES, Golden, bits, flat_tables_from_files, same_result
+from helpers import GOLDEN_CASES, MMF_CASES, Golden, GoldenMmf, bits, flat_tables_from_files, flat_tables_from_mmf, same_result
 
 from juicer_b200 import _abi, api, synth
 
@@ -57,6 +57,21 @@ def test_decode_matches_reference_golden(case, port_lib):
     rb = dec.decode_batch([g.feats(u) for u in range(g.n_utts)])
     for u in range(g.n_utts):
         g.check(u, rb[u], what="gpu batch")
+    dec.close()
+
+
+@pytest.mark.parametrize("remove_tee", [False, True])
+@pytest.mark.parametrize("case", MMF_CASES)
+def test_decode_with_mmf_models_matches_reference_golden(case, remove_tee, port_lib):
+    """Models read from HTK MMF text (jgpu_load_mmf) instead of JMBI: the CUDA path reproduces what the reference
+    decodes after HTKFlatModels::Load(mmf, removeInitialToFinalTransitions) on the same file, bit for bit."""
+    g = GoldenMmf(case, remove_tee)
+    tabs, net, models = flat_tables_from_mmf(g.files, remove_tee)
+    dec = make_decoder(net, models, g.kw, n_lanes=2, frame_stats=True)
+    for u in range(g.n_utts):
+        r = dec.decode(g.feats(u), lane=u % 2)
+        cnt, best = dec.frame_stats(u % 2)
+        g.check(u, r, cnt, best, f"gpu, MMF models, remove_tee={remove_tee}")
     dec.close()
 
 

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import GOLDEN_CASES, Golden, bits, flat_tables_from_files, same_result
+from helpers import GOLDEN_CASES, MMF_CASES, Golden, GoldenMmf, bits, flat_tables_from_files, flat_tables_from_mmf, same_result
 
 from juicer_b200 import _abi, synth
 from oracle import binding
@@ -27,6 +27,31 @@ def test_port_matches_golden(case, oracle_port_lib, product_lib):
     sc = p.gmm_scores(g.feats(0)[:n])
     assert np.array_equal(bits(sc), g.z["gmm"])
     p.close()
+
+
+@pytest.mark.parametrize("remove_tee", [False, True])
+@pytest.mark.parametrize("case", MMF_CASES)
+def test_port_on_mmf_models_matches_golden(case, remove_tee, oracle_port_lib, product_lib):
+    """Models read from MMF text by jgpu_load_mmf, decoded by the port: the reference's results on the same
+    .mmf (HTKFlatModels::Load(mmf, removeInitialToFinalTransitions); expected_mmf.npz)."""
+    g = GoldenMmf(case, remove_tee)
+    tabs, net, models = flat_tables_from_mmf(g.files, remove_tee)
+    p = OraclePort(tabs, _abi.make_cfg(**g.kw))
+    for u in range(g.n_utts):
+        r = p.decode(g.feats(u), counters=True)
+        g.check(u, r, r.frame_cnt, r.frame_best, f"port on MMF models, remove_tee={remove_tee}")
+    p.close()
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref/liboracle_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("case", MMF_CASES)
+def test_reference_on_mmf_models_reproduces_golden(case):
+    g = GoldenMmf(case, False)
+    o = OracleRef({k: v for k, v in g.files.items() if k != "jmbi"}, **g.kw)
+    for u in range(g.n_utts):
+        r = o.decode(g.feats(u), counters=True)
+        g.check(u, r, r.frame_cnt, r.frame_best, "ref on MMF models")
+    o.close()
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref/liboracle_ref.so not built (needs /root/reference)")
