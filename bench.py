@@ -252,7 +252,7 @@ def main() -> None:
     models = api.HTKFlatModels(files["jmbi"])
     dec = api.WFSTDecoderLite(network, models, kw.get("start_beam", 0.0), kw["main_beam"], kw.get("end_beam", 0.0),
                               kw.get("word_beam", 0.0), kw.get("max_hyps", 0), n_lanes=args.lanes, device=local_rank)
-    stream = torch.cuda.Stream(device=dev)
+    stream = torch.cuda.Stream(device=dev, priority=-1)      # the search is latency-critical; scoring may run below it
     dec.set_stream(stream.cuda_stream)
 
     # per-rank batch (weak scaling: every GPU decodes its own `utts` utterances per step)

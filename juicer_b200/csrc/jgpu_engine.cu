@@ -95,8 +95,12 @@ struct jgpu_handle {
     char* static_base = nullptr;   // arcs | states | arc_tee | hmm tables
     size_t static_bytes = 0;
     bool own_stream = true;
-    bool overlap = false;   // JUICER_B200_OVERLAP=1: score the next frame block on a second stream (no gain measured on B200:
-                            // the search kernels hold every warp slot, so the two never co-reside)
+    // JUICER_B200_OVERLAP=1: the acoustic scores of frame block b+1 are computed on a second, low-priority stream
+    // while the search runs block b.  The scorer is then launched in its persistent form (one CTA of ovl_threads
+    // per SM) and the chunk-scheduled search kernels use grids that fit beside it (ovl_int / ovl_walk CTAs per SM),
+    // so both are resident on every SM: the scorer is bound by FP32 issue slots, the search by memory latency.
+    bool overlap = false;
+    int ovl_threads = 192, ovl_int = 2, ovl_walk = 4, n_sm = 148;
     // optional per-kernel timing (CUDA events on the launching stream)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -421,6 +425,7 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
     const int C = g->max_comps, D = g->dim;
     const int DP = (D + 3) & ~3;
     h->DP = DP <= 16 ? 16 : DP <= 28 ? 28 : DP <= 40 ? 40 : DP <= 52 ? 52 : 64;
+    if (h->DP > 40 || C > h->ovl_threads) h->overlap = false;   // the persistent scorer holds mu/ivar in 112 registers
     h->dim = D;
     G.n_gmms = g->n_gmms; G.C = C; G.D = D; G.gpb = std::max(1, 256 / C);
     G.g_pad = (g->n_gmms + G.gpb - 1) / G.gpb * G.gpb;
@@ -568,6 +573,11 @@ int build_state(jgpu_handle* h)
         if (e == cudaSuccess && occ > 0) d.grid_internal = n_sm * occ;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_walk<1>, JG_THREADS, 0) == cudaSuccess && occ > 0) d.grid_walk = n_sm * occ;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_filter, JG_THREADS, 0) == cudaSuccess && occ > 0) d.grid_other = n_sm * occ;
+        if (h->overlap) {                       // leave the persistent scorer's CTA its share of every SM
+            d.grid_internal = std::min(d.grid_internal, n_sm * std::max(1, h->ovl_int));
+            d.grid_walk = std::min(d.grid_walk, n_sm * std::max(1, h->ovl_walk));
+            d.grid_other = std::min(d.grid_other, n_sm * std::max(1, h->ovl_walk));
+        }
         cudaGetLastError();
     }
     h->lanes.assign(L, LaneHost());
@@ -599,23 +609,33 @@ int ensure_results(jgpu_handle* h, size_t n)
 }
 
 int launch_gmm(jgpu_handle* h, const float* d_x, const int* d_rows, int n_rows, float* d_out, long long out_base,
-               cudaStream_t st = nullptr)
+               cudaStream_t st = nullptr, bool persist = false)
 {
     if (n_rows <= 0) return JGPU_OK;
     if (!st) st = h->stream;
     const GmmDev& G = h->g;
-    dim3 grid((G.n_gmms + G.gpb - 1) / G.gpb, (n_rows + JG_GMM_RT - 1) / JG_GMM_RT);
-    const int cstride = JG_GMM_RT * G.gpb + (G.gpb & 31);
+    const int NT = persist ? h->ovl_threads : 256;
+    const int gpb = persist ? std::max(1, NT / G.C) : G.gpb;
+    const int n_bx = (G.n_gmms + gpb - 1) / gpb, n_by = (n_rows + JG_GMM_RT - 1) / JG_GMM_RT;
+    const int cstride = JG_GMM_RT * gpb + (gpb & 31);
     const size_t smem = ((size_t)JG_GMM_RT * h->DP + (size_t)G.C * cstride) * sizeof(float);
+    const long long tiles = (long long)n_bx * n_by;
+    const int grid_p = (int)std::min<long long>(tiles, h->n_sm);
     h->prof_begin(JGPU_K_GMM, st);
     switch (h->DP) {
+#define GMM_LAUNCH(KERNEL, NTV, GRID)                                                                       \
+        CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+        KERNEL<<<GRID, NTV, smem, st>>>(G, gpb, d_x, d_rows, n_rows, d_out, out_base, n_by);
 #define GMM_CASE(DPV)                                                                                          \
     case DPV:                                                                                                  \
-        CK(cudaFuncSetAttribute(k_gmm_scores<DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        k_gmm_scores<DPV><<<grid, 256, smem, st>>>(G, d_x, d_rows, n_rows, d_out, out_base);                   \
+        if (!persist) { GMM_LAUNCH(k_gmm_scores<DPV>, 256, dim3(n_bx, n_by)) }                                 \
+        else if (NT == 192) { GMM_LAUNCH((k_gmm_scores_persist<DPV, 192>), 192, grid_p) }                      \
+        else if (NT == 128) { GMM_LAUNCH((k_gmm_scores_persist<DPV, 128>), 128, grid_p) }                      \
+        else { GMM_LAUNCH((k_gmm_scores_persist<DPV, 256>), 256, grid_p) }                                     \
         break;
         GMM_CASE(16) GMM_CASE(28) GMM_CASE(40) GMM_CASE(52) GMM_CASE(64)
 #undef GMM_CASE
+#undef GMM_LAUNCH
     default: return fail(JGPU_E_ARG, "unsupported padded dim %d", h->DP);
     }
     h->prof_end(st);
@@ -731,8 +751,9 @@ int run_schedule(jgpu_handle* h, const std::vector<int4>& sched, int n_steps, co
         auto issue_gmm = [&](int b) -> int {
             const int b0 = b * FB, nb = std::min(FB, ns - b0), half = b & 1;
             CK(cudaStreamWaitEvent(h->stream_gmm, h->ev_search[half], 0));   // that half of the ring is free again
-            cudaStream_t st = (h->overlap && !h->prof_on) ? h->stream_gmm : h->stream;
-            int rc = launch_gmm(h, d_x, h->d_rows + (size_t)b0 * L, nb * L, h->d_scores, (long long)half * FB * L, st);
+            const bool ovl = h->overlap && !h->prof_on;
+            cudaStream_t st = ovl ? h->stream_gmm : h->stream;
+            int rc = launch_gmm(h, d_x, h->d_rows + (size_t)b0 * L, nb * L, h->d_scores, (long long)half * FB * L, st, ovl);
             if (rc) return rc;
             CK(cudaEventRecord(h->ev_gmm[half], st));
             return JGPU_OK;
@@ -959,10 +980,17 @@ int jgpu_create(const JgpuNet* net, const JgpuHmm* hmm, const JgpuGmm* gmm, cons
     h->cfg = *cfg;
     h->device = cfg->device;
     h->overlap = getenv("JUICER_B200_OVERLAP") && atoi(getenv("JUICER_B200_OVERLAP")) != 0;
+    if (const char* v = getenv("JUICER_B200_OVL_THREADS")) h->ovl_threads = atoi(v);
+    if (const char* v = getenv("JUICER_B200_OVL_INT")) h->ovl_int = atoi(v);
+    if (const char* v = getenv("JUICER_B200_OVL_WALK")) h->ovl_walk = atoi(v);
+    if (h->ovl_threads != 128 && h->ovl_threads != 192 && h->ovl_threads != 256) h->ovl_threads = 192;
+    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device);
     if (const char* g = getenv("JUICER_B200_GRAPHS")) h->use_graphs = atoi(g) != 0;
-    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_greatest);     // search: latency-critical
     if (e != cudaSuccess) { delete h; return fail(JGPU_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
-    e = cudaStreamCreateWithFlags(&h->stream_gmm, cudaStreamNonBlocking);
+    e = cudaStreamCreateWithPriority(&h->stream_gmm, cudaStreamNonBlocking, prio_least);    // scoring fills what is left
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_inputs, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&h->ev_gmm[i], cudaEventDisableTiming);

@@ -40,7 +40,7 @@ struct GmmDev {
     const float* iv;          // [DP][C][Gpad], zero padded
     const float* det;         // [C][Gpad]
     const int*   ncomp;       // [Gpad]
-    int n_gmms, g_pad, C, D, gpb;   // gpb = GMMs per CTA = 256 / C
+    int n_gmms, g_pad, C, D, gpb;   // gpb = GMMs per 256-thread CTA = 256 / C (also the padding unit of g_pad)
     const double* softplus;   // [JG_SP_INTERVALS][8] Taylor table of log(1+exp(d)), see jgpu_softplus_table.h
 };
 
@@ -78,10 +78,18 @@ __device__ __forceinline__ float jg_log_add(const double* __restrict__ tab, floa
 // the list goes to out[(out_base + i) * n_gmms + g].
 // DP = feature dimension padded to a multiple of 4 with mu = ivar = x = 0: the padded terms
 // add (0-0)^2*0 = +0.0f to a non-negative sum, which is exact.
-template <int DP>
-__global__ void __launch_bounds__(256, 2)
-k_gmm_scores(GmmDev g, const float* __restrict__ x, const int* __restrict__ rows, int n_rows,
-             float* __restrict__ out, long long out_base)
+// Two launch forms of the same code:
+//   PERSIST = false : one CTA per (GMM group, row tile), grid (n_bx, n_by), NT = 256 threads — the kernel timed alone;
+//   PERSIST = true  : a 1-D grid of at most one CTA per SM, CTA k walks the contiguous tile range
+//                     [k*T/grid, (k+1)*T/grid) with the row tile as the inner index, so a Gaussian's parameters stay
+//                     in registers over consecutive tiles.  Launched on the low-priority scoring stream with NT = 192
+//                     it leaves room on every SM for the search kernels of the previous frame block (section 4 of
+//                     the scorer is bound by FP32 issue slots, the search by memory latency).
+// gpb = NT / C Gaussian mixtures per CTA.
+template <int DP, int NT, bool PERSIST>
+__device__ __forceinline__ void
+gmm_scores_body(const GmmDev& g, int gpb, const float* __restrict__ x, const int* __restrict__ rows, int n_rows,
+                float* __restrict__ out, long long out_base, int n_by)
 {
     JG_TRACE_SCOPE(JGPU_K_GMM, 0);
     constexpr int RT = JG_GMM_RT;
@@ -91,97 +99,134 @@ k_gmm_scores(GmmDev g, const float* __restrict__ x, const int* __restrict__ rows
     float* vals = smem + RT * DP;              // [C][RT*gpb + pad]
     __shared__ int row_id[RT];
 
-    const int gpb = g.gpb, C = g.C;
+    const int C = g.C;
     const int cstride = RT * gpb + (gpb & 31);   // consecutive components land on different banks
     const int tid = threadIdx.x;
-    const int g0 = blockIdx.x * gpb;
-    const int r0 = blockIdx.y * RT;
-
-    // stage the feature tile
-    if (tid < RT) {
-        const int i = r0 + tid;
-        int rid = -1;
-        if (i < n_rows) rid = rows[i];
-        row_id[tid] = rid;
-    }
-    __syncthreads();
-    bool any = false;
-    for (int i = 0; i < RT; ++i) any |= row_id[i] >= 0;
-    if (!any) return;
-    for (int i = tid; i < RT * DP; i += 256) {
-        const int r = i / DP, dd = i - r * DP;
-        const int rid = row_id[r];
-        xs[i] = (rid >= 0 && dd < g.D) ? x[(size_t)rid * g.D + dd] : 0.0f;
-    }
-
-    // phase 1: thread <-> Gaussian slot
     const int c = tid / gpb, gl = tid - c * gpb;
-    const int gi = g0 + gl;
-    const bool active = c < C && gi < g.n_gmms;
     float mu[D], iv[D];
     float det = 0.0f;
-    if (active) {
-        const size_t plane = (size_t)C * g.g_pad, off = (size_t)c * g.g_pad + gi;
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            mu[d] = __ldg(g.mu + d * plane + off);
-            iv[d] = __ldg(g.iv + d * plane + off);
-        }
-        det = __ldg(g.det + off);
-    }
-    __syncthreads();
-    if (active) {
-JG_PRAGMA_UNROLL(JG_GMM_UNROLL)
-        for (int r = 0; r < RT; ++r) {
-            const float4* xr = reinterpret_cast<const float4*>(xs + r * DP);
-            float s = 0.0f;
-#pragma unroll
-            for (int q = 0; q < DP / 4; ++q) {
-                const float4 xv = xr[q];
-                const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int d = q * 4 + e;
-                    const float xmu = __fsub_rn(xa[e], mu[d]);
-                    s = __fadd_rn(s, __fmul_rn(__fmul_rn(xmu, xmu), iv[d]));
-                }
-            }
-            // the reference evaluates -0.5*s + det in double and narrows (:254).  The fp32 form below is the same
-            // value bit for bit: -0.5f*s is exact, and the sum of two floats rounded to double and then to float
-            // equals the sum rounded to float directly — exact in double when the exponents differ by <= 29, and
-            // beyond that both roundings return the larger operand.
-            vals[c * cstride + r * gpb + gl] = __fadd_rn(__fmul_rn(-0.5f, s), det);
-        }
-    }
-    __syncthreads();
+    int loaded_bx = -1;
 
-    // phase 2: thread <-> (row, gmm); serial logAdd chain in component order.  JG_GMM_P2 pairs per thread are
-    // folded side by side: each chain is a string of dependent fp64 operations, the pairs are independent.
-    constexpr int PP = JG_GMM_P2;
-    for (int p0 = tid; p0 < RT * gpb; p0 += 256 * PP) {
-        float lp[PP];
-        int nc[PP], pp[PP];
-        int nc_max = 0;
-#pragma unroll
-        for (int u = 0; u < PP; ++u) {
-            const int p = p0 + u * 256;
-            pp[u] = p; nc[u] = 0; lp[u] = JG_LZ;
-            if (p < RT * gpb) {
-                const int r = p / gpb, l = p - r * gpb;
-                if (g0 + l < g.n_gmms && row_id[r] >= 0) nc[u] = __ldg(g.ncomp + g0 + l);
-            }
-            nc_max = max(nc_max, nc[u]);
+    int t0, t1;
+    if (PERSIST) {
+        const long long T = (long long)((g.n_gmms + gpb - 1) / gpb) * n_by;
+        t0 = (int)(T * blockIdx.x / gridDim.x);
+        t1 = (int)(T * (blockIdx.x + 1) / gridDim.x);
+    } else {
+        t0 = blockIdx.x * n_by + blockIdx.y;
+        t1 = t0 + 1;
+    }
+    for (int t = t0; t < t1; ++t) {
+        const int bx = t / n_by, by = t - bx * n_by;
+        const int g0 = bx * gpb;
+        const int r0 = by * RT;
+
+        // stage the feature tile
+        if (tid < RT) {
+            const int i = r0 + tid;
+            int rid = -1;
+            if (i < n_rows) rid = rows[i];
+            row_id[tid] = rid;
         }
-        for (int cc = 0; cc < nc_max; ++cc) {
+        __syncthreads();
+        bool any = false;
+        for (int i = 0; i < RT; ++i) any |= row_id[i] >= 0;
+        if (!any) {
+            if (PERSIST) { __syncthreads(); continue; }
+            return;
+        }
+        for (int i = tid; i < RT * DP; i += NT) {
+            const int r = i / DP, dd = i - r * DP;
+            const int rid = row_id[r];
+            xs[i] = (rid >= 0 && dd < g.D) ? x[(size_t)rid * g.D + dd] : 0.0f;
+        }
+
+        // phase 1: thread <-> Gaussian slot
+        const int gi = g0 + gl;
+        const bool active = c < C && gi < g.n_gmms;
+        if (active && loaded_bx != bx) {
+            const size_t plane = (size_t)C * g.g_pad, off = (size_t)c * g.g_pad + gi;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                mu[d] = __ldg(g.mu + d * plane + off);
+                iv[d] = __ldg(g.iv + d * plane + off);
+            }
+            det = __ldg(g.det + off);
+        }
+        loaded_bx = bx;
+        __syncthreads();
+        if (active) {
+JG_PRAGMA_UNROLL(JG_GMM_UNROLL)
+            for (int r = 0; r < RT; ++r) {
+                const float4* xr = reinterpret_cast<const float4*>(xs + r * DP);
+                float s = 0.0f;
+#pragma unroll
+                for (int q = 0; q < DP / 4; ++q) {
+                    const float4 xv = xr[q];
+                    const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int d = q * 4 + e;
+                        const float xmu = __fsub_rn(xa[e], mu[d]);
+                        s = __fadd_rn(s, __fmul_rn(__fmul_rn(xmu, xmu), iv[d]));
+                    }
+                }
+                // the reference evaluates -0.5*s + det in double and narrows (:254).  The fp32 form below is the same
+                // value bit for bit: -0.5f*s is exact, and the sum of two floats rounded to double and then to float
+                // equals the sum rounded to float directly — exact in double when the exponents differ by <= 29, and
+                // beyond that both roundings return the larger operand.
+                vals[c * cstride + r * gpb + gl] = __fadd_rn(__fmul_rn(-0.5f, s), det);
+            }
+        }
+        __syncthreads();
+
+        // phase 2: thread <-> (row, gmm); serial logAdd chain in component order.  JG_GMM_P2 pairs per thread are
+        // folded side by side: each chain is a string of dependent fp64 operations, the pairs are independent.
+        constexpr int PP = JG_GMM_P2;
+        for (int p0 = tid; p0 < RT * gpb; p0 += NT * PP) {
+            float lp[PP];
+            int nc[PP], pp[PP];
+            int nc_max = 0;
+#pragma unroll
+            for (int u = 0; u < PP; ++u) {
+                const int p = p0 + u * NT;
+                pp[u] = p; nc[u] = 0; lp[u] = JG_LZ;
+                if (p < RT * gpb) {
+                    const int r = p / gpb, l = p - r * gpb;
+                    if (g0 + l < g.n_gmms && row_id[r] >= 0) nc[u] = __ldg(g.ncomp + g0 + l);
+                }
+                nc_max = max(nc_max, nc[u]);
+            }
+            for (int cc = 0; cc < nc_max; ++cc) {
+#pragma unroll
+                for (int u = 0; u < PP; ++u)
+                    if (cc < nc[u]) lp[u] = jg_log_add(g.softplus, lp[u], vals[cc * cstride + pp[u]]);
+            }
 #pragma unroll
             for (int u = 0; u < PP; ++u)
-                if (cc < nc[u]) lp[u] = jg_log_add(g.softplus, lp[u], vals[cc * cstride + pp[u]]);
+                if (nc[u] > 0) {
+                    const int r = pp[u] / gpb, l = pp[u] - r * gpb;
+                    out[(size_t)(out_base + r0 + r) * g.n_gmms + g0 + l] = lp[u];
+                }
         }
-#pragma unroll
-        for (int u = 0; u < PP; ++u)
-            if (nc[u] > 0) {
-                const int r = pp[u] / gpb, l = pp[u] - r * gpb;
-                out[(size_t)(out_base + r0 + r) * g.n_gmms + g0 + l] = lp[u];
-            }
+        if (PERSIST) __syncthreads();            // row_id / xs / vals are rewritten by the next tile
     }
+}
+
+template <int DP>
+__global__ void __launch_bounds__(256, 2)
+k_gmm_scores(GmmDev g, int gpb, const float* __restrict__ x, const int* __restrict__ rows, int n_rows,
+             float* __restrict__ out, long long out_base, int n_by)
+{
+    gmm_scores_body<DP, 256, false>(g, gpb, x, rows, n_rows, out, out_base, n_by);
+}
+
+// persistent form; 112 registers per thread keep an NT = 192 CTA at 21.5 K registers, so that it shares an SM
+// with two k_internal<5> CTAs (2 x 20.5 K) or four k_walk CTAs
+template <int DP, int NT>
+__global__ void __maxnreg__(112)
+k_gmm_scores_persist(GmmDev g, int gpb, const float* __restrict__ x, const int* __restrict__ rows, int n_rows,
+                     float* __restrict__ out, long long out_base, int n_by)
+{
+    gmm_scores_body<DP, NT, true>(g, gpb, x, rows, n_rows, out, out_base, n_by);
 }
