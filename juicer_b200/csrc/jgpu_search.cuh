@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
     constexpr int P = S - 1;
     constexpr int NW = JG_THREADS / 32;
     __shared__ LaneSh sh;
-    __shared__ int sh_w[NW][6];                               // per warp: survivors, exits, packed counters, best, path records, round-0 entries
+    __shared__ int sh_w[NW][7];                               // per warp: survivors, exits, packed counters, best, path records, round-0 entries, exits (copy)
     __shared__ int sh_base[6];
     extern __shared__ float4 stage[];                         // [2][P + 1][JG_THREADS]; plane 0 = instance record
     const int L = d.n_lanes;
@@ -712,23 +712,35 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         const unsigned packed = __reduce_add_sync(0xffffffffu, (unsigned)cnt_emit | ((unsigned)cnt_hist << 16));
         if (lane_id() == 0) {
             sh_w[wid][0] = __popc(m_s); sh_w[wid][1] = __popc(m_e); sh_w[wid][2] = (int)packed; sh_w[wid][3] = (int)best_o;
-            sh_w[wid][4] = __popc(m_p); sh_w[wid][5] = __popc(m_r);
+            sh_w[wid][4] = __popc(m_p); sh_w[wid][5] = __popc(m_r); sh_w[wid][6] = __popc(m_e);
         }
         __syncthreads();
-        if (tid == 0) {
-            int ns = 0, ne = 0, np = 0, nr = 0, n_emit = 0, n_hist = 0;
+        // The allocation counters are bumped by DIFFERENT threads so that their round trips to L2 overlap: one
+        // thread doing them in turn waits for each result before it issues the next (ATOMG -> STS pairs in SASS),
+        // i.e. up to five dependent round trips per chunk with the whole CTA parked at the barrier below.
+        if (wid == 0) {
+            const int li = lane_id();
+            if (li < 3) {                                     // lanes 0..2: next list, round-0 arrivals, round-0 work list
+                const int col = li == 2 ? 5 : li;
+                int tot = 0;
+                for (int w = 0; w < NW; ++w) { const int a = sh_w[w][col]; sh_w[w][col] = tot; tot += a; }   // exclusive offsets of the warps
+                int* ctr = li == 0 ? &c->n_next : li == 1 ? &c->n_arr[0] : &c->n_r0;
+                int base = 0;
+                if (tot) base = atomicAdd(ctr, tot);          // one predicated ATOMG for the three lanes
+                sh_base[li == 2 ? 3 : li] = base;
+            }
+        } else if (tid == 32) {                               // word-boundary records
+            int np = 0;
+            for (int w = 0; w < NW; ++w) { const int a = sh_w[w][4]; sh_w[w][4] = np; np += a; }
+            if (np) { const PathAlloc pa = path_alloc(c, np, (sh.epoch[lane] & JG_SH_HAS_FREE) != 0); sh_base[2] = pa.bump_base; sh_base[4] = pa.from_free; sh_base[5] = pa.free_top; }
+        } else if (tid == 64) {                               // counters nobody waits for
+            int ne = 0, n_emit = 0, n_hist = 0;
             unsigned bo = 0;
             for (int w = 0; w < NW; ++w) {
-                const int a = sh_w[w][0], b = sh_w[w][1], p4 = sh_w[w][4], r5 = sh_w[w][5];
-                sh_w[w][0] = ns; sh_w[w][1] = ne; sh_w[w][4] = np; sh_w[w][5] = nr;   // exclusive offsets of the warp
-                ns += a; ne += b; np += p4; nr += r5;
+                ne += sh_w[w][6];
                 n_emit += sh_w[w][2] & 0xffff; n_hist += (unsigned)sh_w[w][2] >> 16;
                 bo = max(bo, (unsigned)sh_w[w][3]);
             }
-            sh_base[0] = ns ? atomicAdd(&c->n_next, ns) : 0;
-            sh_base[1] = ne ? atomicAdd(&c->n_arr[0], ne) : 0;
-            if (np) { const PathAlloc pa = path_alloc(c, np, (sh.epoch[lane] & JG_SH_HAS_FREE) != 0); sh_base[2] = pa.bump_base; sh_base[4] = pa.from_free; sh_base[5] = pa.free_top; }
-            sh_base[3] = nr ? atomicAdd(&c->n_r0, nr) : 0;
             if (bo > f2o(JG_LZ)) atomicMax(&c->best_int, bo);
             if (n_emit) atomicAdd(&c->c_active_emit, n_emit);
             if (ne) atomicAdd(&c->c_active_end, ne);
@@ -773,8 +785,8 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
                           state_key_of(epoch, ex.x, (unsigned)e));
         }
         JG_TRACE_AT(6);                                       // stores issued: end of the first chunk
-        // (no barrier needed here: a warp only rewrites its own sh_w row, and thread 0 rewrites the offsets and
-        //  sh_base after the next chunk's first barrier, which every warp reaches after reading its positions)
+        // (no barrier needed here: a warp only rewrites its own sh_w row, and the allocating threads rewrite the offsets
+        //  and sh_base after the next chunk's first barrier, which every warp reaches after reading its positions)
         lane = lane1; lane1 = lane2;
         valid = valid1; valid1 = valid2;
     }
