@@ -36,7 +36,9 @@
 
 #define JG_LZ (-3.402823466e+38f)
 #define JG_MAX_ROUNDS 16
+#ifndef JG_THREADS
 #define JG_THREADS 256
+#endif
 
 enum { JG_MODE_IDLE = 0, JG_MODE_SEED = 1, JG_MODE_FRAME = 2, JG_FLAG_FINISH = 4 };
 enum { JG_ERR_ACTIVE = 1, JG_ERR_ARRIVALS = 2, JG_ERR_PATHS = 4, JG_ERR_HIST = 8, JG_ERR_HUGE = 16,
@@ -107,6 +109,7 @@ struct Dev {
     const float* trp;          // [n_class][S*S]
     const int2*  se;           // [n_class][S]
     const float4* lr;          // [n_class][2]: left-to-right classes {a01,a11,a12,a22 | a23,a33,a34,-}
+    int n_lr;                  // float4 entries of lr (2 per class)
     int n_arcs, n_states, init_state, n_hmms, n_gmms, S;
     unsigned init_multi;       // JG_MULTI when the initial state can receive more than one arrival per frame
     int n_multi;               // states are renumbered so that the multi-arrival ones are 0 .. n_multi-1: state_key has

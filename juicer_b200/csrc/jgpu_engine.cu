@@ -398,6 +398,10 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
     const size_t b_arcs = pad256(arcs.size() * sizeof(int4)), b_states = pad256(states.size() * sizeof(int4));
     const size_t b_tee = any_tee ? pad256(arc_tee.size() * sizeof(float)) : 0, b_info = pad256(info.size() * sizeof(int));
     const size_t b_trp = pad256(trp.size() * sizeof(float)), b_se = pad256(se.size() * sizeof(int2));
+    // k_internal keeps the left-to-right constants in shared memory: a model set with more classes than fit there
+    // takes the generic SEIndex / trP path for all of them
+    if ((int)lrtab.size() > JG_LR_SH)
+        for (int i = 0; i < H; ++i) info[(size_t)i * 8 + 0] &= ~JG_LR_CLASS;
     const size_t b_lr = pad256(lrtab.size() * sizeof(float4));
     h->static_bytes = b_arcs + b_states + b_tee + b_info + b_trp + b_se + b_lr;
     char* base = nullptr;
@@ -417,6 +421,7 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
     float* d_trp = (float*)put(trp.data(), trp.size() * sizeof(float), b_trp);
     int2* d_se = (int2*)put(se.data(), se.size() * sizeof(int2), b_se);
     d.lr = (const float4*)put(lrtab.data(), lrtab.size() * sizeof(float4), b_lr);
+    d.n_lr = (int)lrtab.size();
     CK(cudaGetLastError());
     d.hmm_info = d_info; d.trp = d_trp; d.se = d_se;
 

@@ -25,6 +25,9 @@
 #ifndef JG_WALK_CTAS
 #define JG_WALK_CTAS 6            // resident CTAs per SM of k_walk (40 registers per thread at 6)
 #endif
+#ifndef JG_LR_SH
+#define JG_LR_SH 64              // left-to-right class constants kept in shared memory by k_internal (float4 entries, 2 per class)
+#endif
 #ifndef JG_INT_CTAS
 #define JG_INT_CTAS 3             // resident CTAs per SM of k_internal<5> (register budget 64 K / (256 * CTAs))
 #endif
@@ -162,6 +165,16 @@ __device__ __forceinline__ int chunk_scan(LaneSh& sh, int L, int items = JG_CH)
     }
     __syncthreads();
     return sh.pref[L];
+}
+
+// lane of chunk `ch` (largest l with pref[l] <= ch), walked upwards from the lane of the CTA's previous chunk:
+// a CTA's chunks are gridDim.x apart, i.e. usually several lanes apart, and a linear walk over pref[] was 18 % of
+// the instructions of the commit (ncu source view, 65 steps per warp).
+__device__ __forceinline__ int lane_of_chunk(const LaneSh& sh, int L, int lane, int ch)
+{
+    while (lane + 16 < L && sh.pref[lane + 16] <= ch) lane += 16;     // (strides instead of a bisection: no extra registers)
+    while (sh.pref[lane + 1] <= ch) ++lane;
+    return lane;
 }
 
 __device__ __forceinline__ u64 warp_max_u64(u64 v)
@@ -493,8 +506,12 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
     __shared__ int sh_w[NW][7];                               // per warp: survivors, exits, packed counters, best, path records, round-0 entries, exits (copy)
     __shared__ int sh_base[6];
     extern __shared__ float4 stage[];                         // [2][P + 1][JG_THREADS]; plane 0 = instance record
+    __shared__ float4 s_lr[JG_LR_SH];                         // left-to-right class constants: the Viterbi of a chunk starts with
+                                                              // them (an LDS instead of an L1 round trip; the host clears the class
+                                                              // flag of every HMM when the table does not fit)
     const int L = d.n_lanes;
     const int tid = threadIdx.x, wid = tid >> 5;
+    if (tid < min(d.n_lr, JG_LR_SH)) s_lr[tid] = __ldg(d.lr + tid);
     for (int l = tid; l < L; l += blockDim.x) {
         const LaneCtl* c = d.ctl + l;
         sh.cnt[l] = c->mode == JG_MODE_FRAME ? c->n_cur : 0;
@@ -632,7 +649,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
             const float* __restrict__ trp = d.trp + (size_t)cls * S * S;
             const int2* __restrict__ se = d.se + (size_t)cls * S;
             if (lr) {
-                const float4 c0 = __ldg(d.lr + cls * 2), c1 = __ldg(d.lr + cls * 2 + 1);
+                const float4 c0 = s_lr[cls * 2], c1 = s_lr[cls * 2 + 1];
                 lrc[0] = c0.x; lrc[1] = c0.y; lrc[2] = c0.z; lrc[3] = c0.w;
                 lrc[4] = c1.x; lrc[5] = c1.y; lrc[6] = c1.z; lrc[7] = c1.w;
             }
@@ -814,7 +831,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_filter(Dev d)
     const int total = chunk_scan(sh, L);
     int lane = 0;
     for (int ch = blockIdx.x; ch < total; ch += gridDim.x) {
-        while (sh.pref[lane + 1] <= ch) ++lane;
+        lane = lane_of_chunk(sh, L, lane, ch);
         const int e = (ch - sh.pref[lane]) * JG_CH + tid;
         int proc = 0;
         if (e < sh.cnt[lane]) {
@@ -952,7 +969,7 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
 
     int lane = 0;
     for (int ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
-        while (sh.pref[lane + 1] <= ch) ++lane;
+        lane = lane_of_chunk(sh, L, lane, ch);
         LaneCtl* c = d.ctl + lane;
         const unsigned epoch = sh.epoch[lane];
         const float thr_end = sh.f0[lane], thr_word = sh.f1[lane];

@@ -12,7 +12,7 @@ for r in rows:
         cur["hdr"] = r
     elif cur is not None and r:
         cur["rows"].append(r)
-b = blocks[0]
+b = blocks[int(sys.argv[4]) if len(sys.argv) > 4 else 0]
 h = b["hdr"]; k = h.index("Warp Stall Sampling (All Samples)"); ie = h.index("Instructions Executed")
 src = h.index("Source")
 tot = sum(float(r[k] or 0) for r in b["rows"] if len(r) > k)
