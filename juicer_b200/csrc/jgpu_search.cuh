@@ -25,6 +25,9 @@
 #ifndef JG_WALK_CTAS
 #define JG_WALK_CTAS 6            // resident CTAs per SM of k_walk (40 registers per thread at 6)
 #endif
+#ifndef JG_HUGE_ILP
+#define JG_HUGE_ILP 2            // arcs in flight per thread in k_commit_huge (1: 32.8 us, 2: 29.0 us, 4: 31.1 us — 54 registers, two waves)
+#endif
 #ifndef JG_LR_SH
 #define JG_LR_SH 64              // left-to-right class constants kept in shared memory by k_internal (float4 entries, 2 per class)
 #endif
@@ -1125,10 +1128,25 @@ __global__ void __launch_bounds__(JG_THREADS) k_commit_huge(Dev d)
         const float4 tok = d.arr_tok[(size_t)lane * d.cap_arr + qr.y];
         const int4 st = __ldg(&d.states[qr.x]);
         const int n_eps = st.w & 0xffff;
-        for (int b = st.x + n_eps + blockIdx.x * blockDim.x + threadIdx.x; b < st.x + st.y; b += gridDim.x * blockDim.x) {
-            const int4 a = __ldg(&d.arcs[b]);
-            const unsigned sm = d.slotmap[(size_t)lane * d.n_arcs + b];
-            process_arc<1>(d, lane, c, epoch, JG_LZ, JG_LZ, 0, 0, flip, tok, b, a, sm, best, n_entry);
+        // JG_HUGE_ILP arcs in flight per thread: the arc and its slotmap entry are independent loads, the walk is
+        // otherwise one dependent round trip per arc
+        const int stride = gridDim.x * blockDim.x, end = st.x + st.y;
+        for (int b0 = st.x + n_eps + blockIdx.x * blockDim.x + threadIdx.x; b0 < end; b0 += stride * JG_HUGE_ILP) {
+            int4 a[JG_HUGE_ILP];
+            unsigned sm[JG_HUGE_ILP];
+#pragma unroll
+            for (int u = 0; u < JG_HUGE_ILP; ++u) {
+                const int b = b0 + u * stride;
+                if (b < end) {
+                    a[u] = __ldg(&d.arcs[b]);
+                    sm[u] = d.slotmap[(size_t)lane * d.n_arcs + b];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < JG_HUGE_ILP; ++u) {
+                const int b = b0 + u * stride;
+                if (b < end) process_arc<1>(d, lane, c, epoch, JG_LZ, JG_LZ, 0, 0, flip, tok, b, a[u], sm[u], best, n_entry);
+            }
         }
     }
     __syncwarp();
