@@ -183,7 +183,7 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "xrt": value / 100.0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------
@@ -222,8 +222,29 @@ def algorithmic_bytes(stats: Dict[str, int], dims: Dict[str, int], n_rows: int) 
     }
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout() -> None:
+    """stdout must carry exactly ONE JSON line, but native libraries write to file descriptor 1 on their own
+    (NCCL prints its version banner there whatever NCCL_DEBUG_FILE says): keep a private copy of the real stdout
+    for the result line and point fd 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: Dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main() -> None:
     args = parse_args()
+    claim_stdout()
     if args.beam > 0:
         _OVERRIDES["main_beam"] = args.beam
     if args.max_hyps >= 0:
@@ -399,7 +420,7 @@ def main() -> None:
         if cpu is not None:
             line["cpu_baseline"] = cpu
             line["parity_vs_cpu_sample"] = bool(parity)
-        print(json.dumps(line), flush=True)
+        emit(line)
     dec.close()
     if world > 1:
         dist.barrier()
