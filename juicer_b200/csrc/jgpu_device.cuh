@@ -39,6 +39,15 @@
 #ifndef JG_THREADS
 #define JG_THREADS 256
 #endif
+// Programmatic dependent launch: the kernels of a frame step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so that the CTAs of kernel N+1 are already resident (as far
+// as kernel N leaves room) and blocked in griddepcontrol.wait when kernel N drains; without the attribute both
+// instructions are no-ops.  Every step kernel starts with this, before it reads anything.
+#define JG_PDL_ENTER()                                                  \
+    do {                                                                \
+        asm volatile("griddepcontrol.launch_dependents;");              \
+        asm volatile("griddepcontrol.wait;" ::: "memory");              \
+    } while (0)
 
 enum { JG_MODE_IDLE = 0, JG_MODE_SEED = 1, JG_MODE_FRAME = 2, JG_FLAG_FINISH = 4 };
 enum { JG_ERR_ACTIVE = 1, JG_ERR_ARRIVALS = 2, JG_ERR_PATHS = 4, JG_ERR_HIST = 8, JG_ERR_HUGE = 16,

@@ -100,6 +100,7 @@ struct jgpu_handle {
     // per SM) and the chunk-scheduled search kernels use grids that fit beside it (ovl_int / ovl_walk CTAs per SM),
     // so both are resident on every SM: the scorer is bound by FP32 issue slots, the search by memory latency.
     bool overlap = false;
+    bool pdl = false;       // JUICER_B200_PDL=1: programmatic dependent launch between the kernels of a frame step
     int ovl_threads = 192, ovl_int = 2, ovl_walk = 4, n_sm = 148;
     // optional per-kernel timing (CUDA events on the launching stream)
     bool prof_on = false;
@@ -649,8 +650,22 @@ int launch_gmm(jgpu_handle* h, const float* d_x, const int* d_rows, int n_rows, 
     return JGPU_OK;
 }
 
+// <<<>>> with the programmatic-dependent-launch attribute (see JG_PDL_ENTER)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 int launch_step(jgpu_handle* h)
 {
+    const bool pdl = h->pdl && !h->prof_on;
     const Dev& d = h->d;
     const dim3 grid_huge(h->bpl, d.n_lanes);
 #ifdef JG_TRACE
@@ -662,37 +677,37 @@ int launch_step(jgpu_handle* h)
     }
 #endif
     h->prof_begin(JGPU_K_BOUNDARY);
-    k_boundary<<<d.n_lanes, 32, 0, h->stream>>>(d);
+    launch_k(pdl, k_boundary, dim3(d.n_lanes), dim3(32), 0, h->stream, d);
     h->prof_end();
     h->prof_begin(JGPU_K_INTERNAL);
     {
         const size_t smem = (size_t)2 * h->S * JG_THREADS * sizeof(float4);   // two chunk buffers: record + S-1 token planes
         if (h->S == 5) {
-            if (d.fuse_exits) k_internal<5, true><<<d.grid_internal, JG_THREADS, smem, h->stream>>>(d);
-            else k_internal<5, false><<<d.grid_internal, JG_THREADS, smem, h->stream>>>(d);
+            if (d.fuse_exits) launch_k(pdl, k_internal<5, true>, dim3(d.grid_internal), dim3(JG_THREADS), smem, h->stream, d);
+            else launch_k(pdl, k_internal<5, false>, dim3(d.grid_internal), dim3(JG_THREADS), smem, h->stream, d);
         } else {
-            if (d.fuse_exits) k_internal<8, true><<<d.grid_internal, JG_THREADS, smem, h->stream>>>(d);
-            else k_internal<8, false><<<d.grid_internal, JG_THREADS, smem, h->stream>>>(d);
+            if (d.fuse_exits) launch_k(pdl, k_internal<8, true>, dim3(d.grid_internal), dim3(JG_THREADS), smem, h->stream, d);
+            else launch_k(pdl, k_internal<8, false>, dim3(d.grid_internal), dim3(JG_THREADS), smem, h->stream, d);
         }
     }
     h->prof_end();
     if (!d.fuse_exits) {
         h->prof_begin(JGPU_K_SEED);
-        k_filter<<<d.grid_other, JG_THREADS, 0, h->stream>>>(d);
+        launch_k(pdl, k_filter, dim3(d.grid_other), dim3(JG_THREADS), 0, h->stream, d);
         h->prof_end();
         ++h->launches;
     }
     for (int r = 0; r < d.n_rounds; ++r) {
         h->prof_begin(r == 0 ? JGPU_K_EXPAND : r == 1 ? JGPU_K_EXPAND_R1 : JGPU_K_EXPAND_R2);
-        k_walk<0><<<d.grid_walk, JG_THREADS, 0, h->stream>>>(d, r);
+        launch_k(pdl, k_walk<0>, dim3(d.grid_walk), dim3(JG_THREADS), 0, h->stream, d, r);
         h->prof_end();
     }
     h->prof_begin(JGPU_K_COMMIT);
-    k_walk<1><<<d.grid_walk, JG_THREADS, 0, h->stream>>>(d, 0);
+    launch_k(pdl, k_walk<1>, dim3(d.grid_walk), dim3(JG_THREADS), 0, h->stream, d, 0);
     h->prof_end();
     if (h->has_huge) {
         h->prof_begin(JGPU_K_EXPAND_HUGE);
-        k_commit_huge<<<grid_huge, JG_THREADS, 0, h->stream>>>(d);
+        launch_k(pdl, k_commit_huge, grid_huge, dim3(JG_THREADS), 0, h->stream, d);
         h->prof_end();
         ++h->launches;
     }
@@ -985,6 +1000,7 @@ int jgpu_create(const JgpuNet* net, const JgpuHmm* hmm, const JgpuGmm* gmm, cons
     h->cfg = *cfg;
     h->device = cfg->device;
     h->overlap = getenv("JUICER_B200_OVERLAP") && atoi(getenv("JUICER_B200_OVERLAP")) != 0;
+    if (const char* v = getenv("JUICER_B200_PDL")) h->pdl = atoi(v) != 0;
     if (const char* v = getenv("JUICER_B200_OVL_THREADS")) h->ovl_threads = atoi(v);
     if (const char* v = getenv("JUICER_B200_OVL_INT")) h->ovl_int = atoi(v);
     if (const char* v = getenv("JUICER_B200_OVL_WALK")) h->ovl_walk = atoi(v);

@@ -294,6 +294,7 @@ __device__ float hist_thresh_warp(const Dev& d, const LaneView& v)
 // chunk), so that the launch has no per-step argument and a whole block of steps replays as one CUDA graph.
 __global__ void __launch_bounds__(32) k_boundary(Dev d)
 {
+    JG_PDL_ENTER();
     const int lane = blockIdx.x;
     const int l = lane_id();
     int step = 0;
@@ -502,6 +503,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int S, bool FUSE>
 __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_internal(Dev d)
 {
+    JG_PDL_ENTER();
     JG_TRACE_SCOPE(JGPU_K_INTERNAL, 0);
     constexpr int P = S - 1;
     constexpr int NW = JG_THREADS / 32;
@@ -820,6 +822,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
 // =========================================================================================
 __global__ void __launch_bounds__(JG_THREADS, 6) k_filter(Dev d)
 {
+    JG_PDL_ENTER();
     JG_TRACE_SCOPE(JGPU_K_SEED, 0);
     __shared__ LaneSh sh;
     const int L = d.n_lanes, tid = threadIdx.x;
@@ -932,6 +935,7 @@ __device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, 
 template <int PASS>
 __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int round)
 {
+    JG_PDL_ENTER();
     JG_TRACE_SCOPE(PASS ? JGPU_K_COMMIT : JGPU_K_EXPAND, round);
     __shared__ LaneSh sh;
     __shared__ int s_off[JG_THREADS + 1];
@@ -1113,6 +1117,7 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
 // hub-like rows met by the commit: all CTAs of the lane stride over the row.
 __global__ void __launch_bounds__(JG_THREADS) k_commit_huge(Dev d)
 {
+    JG_PDL_ENTER();
     JG_TRACE_SCOPE(JGPU_K_EXPAND_HUGE, 0);
     const int lane = blockIdx.y;
     LaneCtl* c = d.ctl + lane;
