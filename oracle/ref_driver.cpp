@@ -295,3 +295,21 @@ int oref_decode(void* hv, const float* feats, int T, OrefWord* words, int maxWor
 }
 
 } // extern "C"
+
+/* Parse stage alone (oracle/shim/htkparse_rd.cpp behind the reference's `htkparse` symbol): 0 = accepted,
+ * 1 = syntax error, 2 = a check of a grammar action failed (htkerror), -1 = cannot open.  Lets tests compare what
+ * the two restatements of htkparse.l/.y accept without the reference's error() ending the process. */
+#include "htkparse.h"
+extern "C" int oref_mmf_parse_only(const char* path, int* counts5)
+{
+    FILE* fd = fopen(path, "rb");
+    if (!fd) return -1;
+    const int rc = htkparse((void*)fd);
+    fclose(fd);
+    if (rc == 0 && counts5) {
+        counts5[0] = htk_def.n_hmms; counts5[1] = htk_def.n_sh_states; counts5[2] = htk_def.n_sh_transmats;
+        counts5[3] = htk_def.n_mix_pools; counts5[4] = htk_def.global_opts.vec_size;
+    }
+    if (rc == 0) cleanHTKDef();      /* (after a failed parse the partial records are simply leaked: test process) */
+    return rc;
+}
