@@ -392,6 +392,15 @@ static void propagate(jor_handle* h, Tok* tok, int arc)
 /* ---------------------------------------------------------------------------------------
  * HMMInternalPropagation (src/WFSTDecoderLite.cpp:376-484)
  * ------------------------------------------------------------------------------------ */
+/* Instrumentation for DESIGN.md "lazy acoustic scoring" (not part of the restated algorithm): how many distinct
+ * GMMs per frame have at least one live predecessor token at the start of the frame, i.e. the superset of the
+ * evaluated GMMs that can be marked one step ahead, before the frame's normalisation and beam are known. */
+static long long g_superset_total = 0;
+static int* g_superset_stamp = NULL;
+static int g_superset_n = 0;
+long long jor_debug_gmm_superset(void) { return g_superset_total; }
+void jor_debug_gmm_superset_reset(void) { g_superset_total = 0; }
+
 static void hmm_internal(jor_handle* h, Inst* inst)
 {
     const int M = h->hmm.max_states;
@@ -400,6 +409,18 @@ static void hmm_internal(jor_handle* h, Inst* inst)
     const int32_t* se = h->hmm.se + (size_t)inst->hmm * M * 2;
     Tok buf[SMAX];
     int i, j;
+    if (g_superset_n != h->gmm.n_gmms) {
+        free(g_superset_stamp);
+        g_superset_n = h->gmm.n_gmms;
+        g_superset_stamp = (int*)malloc(sizeof(int) * (size_t)(g_superset_n > 0 ? g_superset_n : 1));
+        for (i = 0; i < g_superset_n; ++i) g_superset_stamp[i] = -1000;
+    }
+    if (h->frame == 0) for (i = 0; i < g_superset_n && inst == &h->insts[h->active_head]; ++i) g_superset_stamp[i] = -1000;
+    for (j = 1; j < N_1; ++j) {
+        int live = 0, gi = h->hmm.gmm[inst->hmm * M + j];
+        for (i = se[j * 2 + 0]; i < se[j * 2 + 1]; ++i) live |= inst->st[i].score > LZ;
+        if (live && gi >= 0 && g_superset_stamp[gi] != h->frame) { g_superset_stamp[gi] = h->frame; ++g_superset_total; }
+    }
     buf[0] = NULL_TOK; /* :108 */
     for (j = 1; j < N_1; ++j) { /* :387-424 */
         Tok* res = &buf[j];
