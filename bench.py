@@ -329,7 +329,7 @@ def main() -> None:
     e2e_ms_max, _ = jdist.reduce_time_and_frames(1e3 * e2e_s, 0, dev)
     n_ok = sum(1 for r in res if r.status > 0)
     h2d = rows * m.dim * 4
-    d2h = args.utts * (32 + 256 * 20)                                    # ResHdr + word records per utterance
+    d2h = args.utts * 32 + 20 * sum(max(r.status, 0) for r in res) + 4   # ResHdr per utterance + the word pool in use
 
     # ---- roofline: one more step with per-kernel CUDA-event timing ----------------------
     dec.profile(True)

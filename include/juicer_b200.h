@@ -93,8 +93,10 @@ typedef struct JgpuCfg {
     int32_t max_hyps;             /* maxEmitHyps        */
     int32_t device;               /* CUDA device ordinal */
     int32_t n_lanes;              /* utterances decoded in lock-step per launch (>=1)  */
-    int32_t max_active;           /* capacity: active HMM instances per lane, 0 = auto */
-    int32_t max_frames;           /* capacity: frames per utterance, 0 = 4096          */
+    int32_t max_active;           /* first-pass capacity: active HMM instances per lane, 0 = auto (up to one per
+                                     arc, bounded by 30 % of the free device memory over n_lanes)          */
+    int32_t max_frames;           /* frames per utterance KEPT by frame_stats, 0 = 4096 (decoding itself has no
+                                     frame limit)                                                          */
     int32_t max_paths;            /* capacity: word-boundary records per lane, 0 = auto*/
     int32_t frame_stats;          /* 1 = keep per-frame work counters (parity tests)   */
     int32_t reserved;
@@ -114,12 +116,19 @@ typedef struct JgpuWord {
 
 /* Result of one utterance.  Replaces DecHyp* returned by IDecoder::finish()
  * (src/Decoder.h:29; built at src/WFSTDecoderLite.cpp:262-308).
- *   status >= 0 : number of words on the best path (words[] holds min(status,max_words),
- *                 oldest first; the last record carries the final-weight-inclusive totals);
+ *   status >= 0 : number of words on the best path.  words[] holds min(status, max_words) of them, oldest
+ *                 first; when the caller's buffer is the smaller one it gets the NEWEST max_words words, so
+ *                 the last record always carries the final-weight-inclusive totals.  The device side has
+ *                 no per-utterance word limit (the reference allocates one DecHypHist per word);
  *   status == -1: no token reached a final state in the last frame (reference: NULL hyp);
  *   status == -2: a final token survived but its path has no word label (reference:
  *                 non-NULL but inactive DecHyp, WFSTDecoderLite.cpp:273-306);
- *   status <= -10: the utterance failed (JGPU_E_CAPACITY - 10 ...) — batch continues. */
+ *   status <= -10: the utterance failed: status = JGPU_E_CAPACITY - 10 - (error bits << 8), bits: 1 active
+ *                 list, 2 arrival records, 4 word-boundary arena, 8 histogram range (the reference calls
+ *                 error() there, src/Histogram.cpp:75-79), 64 result-word pool.  The batch entry points
+ *                 decode such an utterance again with larger per-lane arenas (fewer lanes in lock-step), up
+ *                 to one instance per arc — what the reference can reach by allocating — so only the
+ *                 streaming interface and a handle whose memory cannot hold one full-size lane report it. */
 typedef struct JgpuResult {
     int32_t   status;
     int32_t   n_frames;

@@ -120,7 +120,7 @@ namespace Juicer
         if (jgpu_create(&net, &hm, &gm, &cfg, &handle) != JGPU_OK)
             error("GpuWFSTDecoder - %s", jgpu_last_error());        // Torch error(): message + exit, like the reference
         pending.resize((size_t)kBlockFrames * vecSize);
-        words.resize(4096);
+        words.resize(65536);       // the device side has no per-utterance word limit; this is the host buffer
     }
 
     GpuWFSTDecoder::~GpuWFSTDecoder()

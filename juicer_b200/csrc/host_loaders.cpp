@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -61,6 +62,7 @@ int read_alphabet(const char* fname, Alphabet* a)
     while (fgets(line, sizeof(line), fd)) {
         if (sscanf(line, "%s %d", sym, &id) != 2) continue;
         if (id < 0) { fclose(fd); return io_fail("%s: negative symbol id", fname); }
+        if (id > (1 << 28)) { fclose(fd); return io_fail("%s: symbol id %d too large", fname, id); }
         if (id >= (int)a->present.size()) {
             a->present.resize(id + 1000, 0);
             a->aux.resize(id + 1000, 0);
@@ -110,8 +112,8 @@ int jgpu_io_fail(const char* fmt, ...)
     return JGPU_E_IO;
 }
 
-extern "C" int jgpu_load_fsm(const char* fsm, const char* insyms, const char* outsyms, float lm_scale,
-                             float ins_penalty, JgpuNet* out)
+static int load_fsm_impl(const char* fsm, const char* insyms, const char* outsyms, float lm_scale,
+                         float ins_penalty, JgpuNet* out)
 {
     if (!fsm || !insyms || !outsyms || !out) return io_fail("jgpu_load_fsm: null argument (both symbol files are mandatory)");
     memset(out, 0, sizeof(*out));
@@ -151,7 +153,14 @@ extern "C" int jgpu_load_fsm(const char* fsm, const char* insyms, const char* ou
             st_n.resize((size_t)max_state * 2 + 1024, 0);
             st_first.resize(st_n.size(), 0);
         }
-        if (st_n[from]++ == 0) st_first[from] = id;      // getTransitions: first arc + count
+        // getTransitions(prev,&next) returns first arc + count (src/WFSTNetwork.cpp:709-721): a state whose arc lines
+        // are interleaved with another state's would get an overlapping row — the reference then decodes a different
+        // network without a word; here that is a load error
+        if (st_n[from] > 0 && st_first[from] + st_n[from] != id) {
+            fclose(fd);
+            return io_fail("%s: arcs of state %d are not contiguous (arc line %d)", fsm, from, id + 1);
+        }
+        if (st_n[from]++ == 0) st_first[from] = id;
     }
     fclose(fd);
     if (init_state < 0) return io_fail("%s: no arcs", fsm);
@@ -160,6 +169,7 @@ extern "C" int jgpu_load_fsm(const char* fsm, const char* insyms, const char* ou
     st_first.resize(n_states);
     std::vector<float> st_final(n_states, LZ);
     for (size_t k = 0; k < fin_id.size(); ++k) {
+        // (a final state that no arc mentions is beyond maxState: the reference errors out as well, src/WFSTNetwork.cpp:560-566)
         if (fin_id[k] < 0 || fin_id[k] > max_state) return io_fail("%s: final state %d out of range", fsm, fin_id[k]);
         st_final[fin_id[k]] = fin_w[k];
     }
@@ -212,16 +222,27 @@ extern "C" int jgpu_load_fsm(const char* fsm, const char* insyms, const char* ou
 // penalty to arcs with an output label (:1351-1365); final weights are used as read.
 static bool rd(FILE* fd, void* p, size_t n) { return fread(p, 1, n, fd) == n; }
 
+// size of an open file: every count read from a binary header is checked against it before anything is sized
+// from it, so a corrupt file is an I/O error and not a std::bad_alloc across the C ABI
+static long long file_size(FILE* fd)
+{
+    const long pos = ftell(fd);
+    if (pos < 0 || fseek(fd, 0, SEEK_END) != 0) return -1;
+    const long end = ftell(fd);
+    fseek(fd, pos, SEEK_SET);
+    return (long long)end;
+}
+
 static int skip_alphabet(FILE* fd, const char* fname)
 {
     char id[5] = {0, 0, 0, 0, 0};
     int max_label, n_labels;
     if (!rd(fd, id, 4) || strcmp(id, "JWAL") != 0) return io_fail("%s: WFSTAlphabet::readBinary - invalid ID", fname);
-    if (!rd(fd, &max_label, 4) || !rd(fd, &n_labels, 4)) return io_fail("%s: error reading alphabet header", fname);
+    if (!rd(fd, &max_label, 4) || !rd(fd, &n_labels, 4) || (long long)max_label * 4 > file_size(fd)) return io_fail("%s: error reading alphabet header", fname);
     if (max_label >= 0) {
         for (int i = 0; i <= max_label; ++i) {
             int len;
-            if (!rd(fd, &len, 4) || len < 0) return io_fail("%s: error reading label length", fname);
+            if (!rd(fd, &len, 4) || len < 0 || len > (1 << 20)) return io_fail("%s: error reading label length", fname);
             if (len > 0) {
                 std::vector<char> buf(len);
                 if (!rd(fd, buf.data(), len)) return io_fail("%s: error reading label string", fname);
@@ -235,7 +256,7 @@ static int skip_alphabet(FILE* fd, const char* fname)
     return JGPU_OK;
 }
 
-extern "C" int jgpu_load_jwnt(const char* path, float lm_scale, float ins_penalty, JgpuNet* out)
+static int load_jwnt_impl(const char* path, float lm_scale, float ins_penalty, JgpuNet* out)
 {
     if (!path || !out) return io_fail("jgpu_load_jwnt: null argument");
     memset(out, 0, sizeof(*out));
@@ -248,12 +269,14 @@ extern "C" int jgpu_load_jwnt(const char* path, float lm_scale, float ins_penalt
     if (!rd(fd, hdr, sizeof(hdr))) return io_fail("%s: error reading header", path);
     const int init_state = hdr[0], max_state = hdr[1];
     if (max_state < 0 || init_state < 0 || init_state > max_state) return io_fail("%s: bad initState / maxState", path);
+    const long long fsize = file_size(fd);
+    if (fsize < 0 || (long long)max_state * 12 > fsize) return io_fail("%s: maxState %d does not fit the file size", path, max_state);
     const int n_states = max_state + 1;
     std::vector<int> st_first(n_states, 0), st_n(n_states, 0), st_fin(n_states, -1);
     std::vector<std::vector<int>> st_trans(n_states);
     for (int s = 0; s < n_states; ++s) {
         int rec[3];   // label finalInd nTrans
-        if (!rd(fd, rec, sizeof(rec)) || rec[2] < 0) return io_fail("%s: error reading states[%d]", path, s);
+        if (!rd(fd, rec, sizeof(rec)) || rec[2] < 0 || (long long)rec[2] * 4 > fsize) return io_fail("%s: error reading states[%d]", path, s);
         st_fin[s] = rec[1];
         st_n[s] = rec[2];
         if (rec[2] > 0) {
@@ -263,13 +286,13 @@ extern "C" int jgpu_load_jwnt(const char* path, float lm_scale, float ins_penalt
         }
     }
     int n_final;
-    if (!rd(fd, &n_final, 4) || n_final < 0) return io_fail("%s: error reading nFinalStates", path);
+    if (!rd(fd, &n_final, 4) || n_final < 0 || (long long)n_final * 8 > fsize) return io_fail("%s: error reading nFinalStates", path);
     std::vector<int> fin_id(n_final);
     std::vector<float> fin_w(n_final);
     for (int i = 0; i < n_final; ++i)
         if (!rd(fd, &fin_id[i], 4) || !rd(fd, &fin_w[i], 4)) return io_fail("%s: error reading finalStates", path);
     int n_arcs;
-    if (!rd(fd, &n_arcs, 4) || n_arcs < 0) return io_fail("%s: error reading nTransitions", path);
+    if (!rd(fd, &n_arcs, 4) || n_arcs < 0 || (long long)n_arcs * 20 > fsize) return io_fail("%s: error reading nTransitions", path);
     std::vector<int> to(n_arcs), in(n_arcs), ol(n_arcs);
     std::vector<float> w(n_arcs);
     for (int a = 0; a < n_arcs; ++a) {
@@ -325,7 +348,7 @@ extern "C" int jgpu_free_net(JgpuNet* n)
     return JGPU_OK;
 }
 
-extern "C" int jgpu_load_jmbi(const char* path, JgpuHmm* hmm, JgpuGmm* gmm)
+static int load_jmbi_impl(const char* path, JgpuHmm* hmm, JgpuGmm* gmm)
 {
     if (!path || !hmm || !gmm) return io_fail("jgpu_load_jmbi: null argument");
     memset(hmm, 0, sizeof(*hmm));
@@ -339,6 +362,13 @@ extern "C" int jgpu_load_jmbi(const char* path, JgpuHmm* hmm, JgpuGmm* gmm)
     if (!rd(f, hdr, 4, 7)) BAD("truncated header");
     const int D = hdr[0], nMean = hdr[1], nVar = hdr[2], nMix = hdr[3], nGMM = hdr[4], nTM = hdr[5], nHMM = hdr[6];
     if (D <= 0 || nMean < 0 || nVar < 0 || nMix < 0 || nGMM < 0 || nTM < 0 || nHMM < 0) BAD("bad counts");
+    {
+        // smallest possible record of each kind (tag + nameLen + payload) against the file size
+        const long long fsize = file_size(f);
+        const long long least = (long long)nMean * (8 + 4ll * D) + (long long)nVar * (12 + 8ll * D) + (long long)nMix * 12 +
+                                (long long)nGMM * 16 + (long long)nTM * 12 + (long long)nHMM * 16;
+        if (fsize < 0 || D > (1 << 20) || least > fsize) BAD("record counts do not fit the file size");
+    }
     RawModels m;
     m.D = D;
     m.means.resize((size_t)nMean * D); m.vars.resize((size_t)nVar * D); m.gconst.resize(nVar);
@@ -354,7 +384,7 @@ extern "C" int jgpu_load_jmbi(const char* path, JgpuHmm* hmm, JgpuGmm* gmm)
     m.mix_mean.resize(nMix); m.mix_var.resize(nMix); m.mix_name.resize(nMix);
     for (int i = 0; i < nMix; ++i) {
         int nc;
-        if (!rd_tag_name(f, "JMMX") || !rd(f, &nc, 4, 1) || nc < 0) BAD("bad mixture record");
+        if (!rd_tag_name(f, "JMMX") || !rd(f, &nc, 4, 1) || nc < 0 || nc > nMean) BAD("bad mixture record");
         m.mix_mean[i].resize(nc);
         m.mix_var[i].resize(nc);
         if (!rd(f, m.mix_mean[i].data(), 4, nc) || !rd(f, m.mix_var[i].data(), 4, nc)) BAD("bad mixture record");
@@ -364,7 +394,7 @@ extern "C" int jgpu_load_jmbi(const char* path, JgpuHmm* hmm, JgpuGmm* gmm)
     m.gmm_mix.resize(nGMM); m.gmm_logw.resize(nGMM); m.gmm_name.resize(nGMM);
     for (int i = 0; i < nGMM; ++i) {
         int nc;
-        if (!rd_tag_name(f, "JMGM") || !rd(f, &m.gmm_mix[i], 4, 1) || !rd(f, &nc, 4, 1) || nc < 0) BAD("bad GMM record");
+        if (!rd_tag_name(f, "JMGM") || !rd(f, &m.gmm_mix[i], 4, 1) || !rd(f, &nc, 4, 1) || nc < 0 || nc > nMean) BAD("bad GMM record");
         std::vector<float> wts(nc);
         m.gmm_logw[i].resize(nc);
         if (!rd(f, wts.data(), 4, nc) || !rd(f, m.gmm_logw[i].data(), 4, nc)) BAD("bad GMM record");
@@ -377,7 +407,7 @@ extern "C" int jgpu_load_jmbi(const char* path, JgpuHmm* hmm, JgpuGmm* gmm)
         std::vector<int> nsucs(t.n);
         if (!rd(f, nsucs.data(), 4, t.n)) BAD("bad transition matrix record");
         int total = 0;
-        for (int s = 0; s < t.n; ++s) { if (nsucs[s] < 0) BAD("bad successor count"); total += nsucs[s]; }
+        for (int s = 0; s < t.n; ++s) { if (nsucs[s] < 0 || nsucs[s] > t.n) BAD("bad successor count"); total += nsucs[s]; }
         std::vector<int> sucs(total);
         std::vector<float> probs(total), logp(total);
         if (!rd(f, sucs.data(), 4, total) || !rd(f, probs.data(), 4, total) || !rd(f, logp.data(), 4, total)) BAD("bad transition matrix record");
@@ -493,4 +523,23 @@ extern "C" int jgpu_free_models(JgpuHmm* hmm, JgpuGmm* gmm)
         memset(gmm, 0, sizeof(*gmm));
     }
     return JGPU_OK;
+}
+
+// ---- C ABI wrappers: nothing may unwind across the boundary (a corrupt file must be JGPU_E_IO, not std::terminate) ----
+#define JG_GUARDED(call)                                                                  \
+    try { return call; }                                                                  \
+    catch (const std::exception& e) { return io_fail("host loader: %s", e.what()); }      \
+    catch (...) { return io_fail("host loader: unknown exception"); }
+
+extern "C" int jgpu_load_fsm(const char* fsm, const char* insyms, const char* outsyms, float lm_scale, float ins_penalty, JgpuNet* out)
+{
+    JG_GUARDED(load_fsm_impl(fsm, insyms, outsyms, lm_scale, ins_penalty, out))
+}
+extern "C" int jgpu_load_jwnt(const char* path, float lm_scale, float ins_penalty, JgpuNet* out)
+{
+    JG_GUARDED(load_jwnt_impl(path, lm_scale, ins_penalty, out))
+}
+extern "C" int jgpu_load_jmbi(const char* path, JgpuHmm* hmm, JgpuGmm* gmm)
+{
+    JG_GUARDED(load_jmbi_impl(path, hmm, gmm))
 }

@@ -613,5 +613,9 @@ extern "C" int jgpu_load_mmf(const char* path, int32_t remove_initial_to_final, 
         return jgpu_finish_models(b.m, hmm, gmm);
     } catch (const ParseError& e) {
         return jgpu_io_fail("%s: %s", path, e.msg.c_str());
+    } catch (const std::exception& e) {                      // nothing unwinds across the C ABI
+        return jgpu_io_fail("%s: %s", path, e.what());
+    } catch (...) {
+        return jgpu_io_fail("%s: unknown exception in the MMF loader", path);
     }
 }

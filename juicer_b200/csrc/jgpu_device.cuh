@@ -39,19 +39,12 @@
 #ifndef JG_THREADS
 #define JG_THREADS 256
 #endif
-// Programmatic dependent launch: the kernels of a frame step are launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization, so that the CTAs of kernel N+1 are already resident (as far
-// as kernel N leaves room) and blocked in griddepcontrol.wait when kernel N drains; without the attribute both
-// instructions are no-ops.  Every step kernel starts with this, before it reads anything.
-#define JG_PDL_ENTER()                                                  \
-    do {                                                                \
-        asm volatile("griddepcontrol.launch_dependents;");              \
-        asm volatile("griddepcontrol.wait;" ::: "memory");              \
-    } while (0)
-
 enum { JG_MODE_IDLE = 0, JG_MODE_SEED = 1, JG_MODE_FRAME = 2, JG_FLAG_FINISH = 4 };
 enum { JG_ERR_ACTIVE = 1, JG_ERR_ARRIVALS = 2, JG_ERR_PATHS = 4, JG_ERR_HIST = 8, JG_ERR_HUGE = 16,
-       JG_ERR_FRAMES = 32 };
+       JG_ERR_WORDS = 64,       // the result-word pool of the batch was too small (the host grows it and decodes again)
+       JG_ERR_LAZY = 128 };     // (self-check, frame_stats builds) k_internal used an acoustic score nobody had asked for
+// errors a second pass with larger per-lane arenas cures (jgpu_engine.cu: decode_common re-decodes those utterances)
+#define JG_ERR_RETRYABLE (JG_ERR_ACTIVE | JG_ERR_ARRIVALS | JG_ERR_PATHS | JG_ERR_WORDS)
 
 typedef unsigned long long u64;
 
@@ -65,7 +58,7 @@ struct PathRec {          // 32 B: replaces Path (src/WFSTDecoderLite.h:39-55) m
 struct ResHdr {           // 32 B per utterance
     int   status, n_frames;
     float score, ac, lm;
-    int   error, pad1, pad2;
+    int   error, word_off, n_words;   // the words of the best path are res_words[word_off .. word_off + n_words)
 };
 
 #define JG_MULTI 0x80000000u      // arcs.x / Arrival.q / inst_meta.z flag: the destination state can receive more
@@ -74,8 +67,9 @@ struct ResHdr {           // 32 B per utterance
                                   // final, or has epsilon / tee out-arcs); every other exit token is finished inside
                                   // k_internal (word-boundary record) and only meets the commit
 #define JG_STATE_MASK 0x3fffffff
-#define JG_SLOT_BITS 20           // slotmap entry = (epoch & 0x7ff) << 20 | position + 1
-#define JG_SLOT_MASK 0xfffffu
+// slotmap entry = (epoch & slot_emask) << slot_bits | list position + 1 and state key = epoch | orderable score | arrival
+// id: the field widths are chosen at create from the size of the network (Dev::slot_bits, key_id_bits), so that a lane
+// can hold an instance on every arc — the reference has no ceiling either (attachNetInst, src/WFSTDecoderLite.cpp:751-774)
 
 #define JG_LR_CLASS 0x40000000   // hmm_info[0] flag: plain left-to-right topology (no skips), nStates <= 5
 #define JG_FRESH 0x40000000   // inst_meta.y flag: only the entry token of this instance is valid
@@ -90,7 +84,8 @@ struct LaneCtl {
     unsigned best_ext;        // orderable max of entry scores of this frame      (:572-573)
     u64      best_final;      // key of the best arrival at a final state          (:513-520)
     float norm, thr_emit, thr_start;
-    int mode, srow, frame, utt, error, pad_;
+    int mode, srow, frame, utt, error;
+    int final_rec;            // arrival record behind best_final (found by the commit pass; -1 = none)
     int c_active_emit, c_active_end, c_end_proc, c_arcs, c_entry;
     int hist_count;
     int final_valid;
@@ -126,7 +121,11 @@ struct Dev {
     // settings
     float start_beam, main_beam, end_beam, word_beam;
     int max_hyps, hist_min, hist_max, hist_nbins;
-    int n_lanes, cap, cap_arr, cap_paths, cap_huge, n_rounds, max_frames, frame_stats, max_words;
+    int n_lanes, cap, cap_arr, cap_paths, cap_huge, n_rounds, max_frames, frame_stats;
+    int slot_bits;                   // slotmap: low bits = list position + 1, the rest = epoch stamp
+    unsigned slot_emask;
+    int key_id_bits;                 // state key: low bits = arrival id (2 * (via arc + 1) + pass-through flag)
+    unsigned key_emask;
     int huge_deg;
     int gc_threshold;                // a lane's arena is collected when more than this many records are in use
     int fuse_exits;                  // no end / word beam: exit tokens become arrivals inside k_internal
@@ -148,7 +147,9 @@ struct Dev {
     const int4*  sched;        // [n_steps + 1][n_lanes] {feature row, score row, flags, utt}
     int*      lane_step;       // [n_lanes] next schedule row of the lane (k_boundary)
     ResHdr*   res_hdr;
-    JgpuWord* res_words;
+    JgpuWord* res_words;       // one pool for the batch, handed out by finish_utterance (no per-utterance word limit)
+    int*      res_used;        // words handed out
+    int       res_words_cap;
     int*      fstat_cnt;       // [n_lanes][max_frames][4]
     float*    fstat_best;      // [n_lanes][max_frames]
 };
@@ -215,6 +216,17 @@ __device__ __forceinline__ float4 null_tok()
     return make_float4(JG_LZ, JG_LZ, JG_LZ, __int_as_float(-1));
 }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// slotmap entries: the GPU form of WFSTTransition::hook (src/WFSTNetwork.h:50-51), valid iff stamped with the lane's epoch
+__device__ __forceinline__ unsigned slot_entry(const Dev& d, unsigned epoch, int pos)
+{
+    return ((epoch & d.slot_emask) << d.slot_bits) | ((unsigned)pos + 1u);
+}
+__device__ __forceinline__ int slot_lookup(const Dev& d, unsigned sm, unsigned epoch)     // list position or -1
+{
+    const unsigned p = sm & ((1u << d.slot_bits) - 1u);
+    return ((sm >> d.slot_bits) == (epoch & d.slot_emask) && p != 0u) ? (int)p - 1 : -1;
+}
 
 // warp-aggregated slot allocation: every thread of the warp must call it
 __device__ __forceinline__ int warp_alloc(int* counter, bool want)

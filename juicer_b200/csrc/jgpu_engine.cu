@@ -70,9 +70,7 @@ struct jgpu_handle {
     bool use_graphs = true;
     std::vector<unsigned> host_epoch;    // mirror of LaneCtl::epoch (advances on every non-idle step of the lane)
     int gc_period = 64, steps_since_gc = 0;   // word-boundary arena collection every gc_period frame steps (0 = never)
-    cudaStream_t stream = nullptr;       // search kernels, copies
-    cudaStream_t stream_gmm = nullptr;   // acoustic scoring of the NEXT frame block overlaps the search
-    cudaEvent_t ev_inputs = nullptr, ev_gmm[2] = {nullptr, nullptr}, ev_search[2] = {nullptr, nullptr};
+    cudaStream_t stream = nullptr;       // everything is enqueued here
     std::vector<void*> allocs;
     size_t bytes = 0;
     // schedule
@@ -88,20 +86,25 @@ struct jgpu_handle {
     float* d_gmm_out = nullptr;   // jgpu_gmm_scores scratch
     int gmm_chunk = 1024;
     // results
-    size_t res_cap = 0;
+    size_t res_cap = 0;                  // utterance headers
+    size_t words_cap = 0;                // word pool of a batch (JgpuWord records)
+    // views: the per-lane arenas are pools (n_lanes x capacity); a second pass over the utterances that overflowed
+    // theirs looks at the same memory as FEWER lanes with LARGER arenas (decode_common)
+    struct View { int n_lanes, cap, cap_arr, cap_paths; };
+    View base{};                         // what jgpu_create sized
+    size_t pool_inst = 0, pool_arr = 0, pool_paths = 0;   // pool sizes in records
+    int cap_full = 0;                    // instances a lane can ever hold: one per arc (+1)
+    int retry_passes = 0;                // second passes run so far (statistics)
+    bool sticky = false;                 // the last batch mostly overflowed the base view: start with sticky_view
+    View sticky_view{};
+    unsigned epoch_wrap = 0x7ffu;        // a lane's stamped tables are wiped when (epoch & epoch_wrap) == 0
     std::vector<LaneHost> lanes;
     int64_t launches = 0;
     JgpuStats batch_stats{};
     char* static_base = nullptr;   // arcs | states | arc_tee | hmm tables
     size_t static_bytes = 0;
     bool own_stream = true;
-    // JUICER_B200_OVERLAP=1: the acoustic scores of frame block b+1 are computed on a second, low-priority stream
-    // while the search runs block b.  The scorer is then launched in its persistent form (one CTA of ovl_threads
-    // per SM) and the chunk-scheduled search kernels use grids that fit beside it (ovl_int / ovl_walk CTAs per SM),
-    // so both are resident on every SM: the scorer is bound by FP32 issue slots, the search by memory latency.
-    bool overlap = false;
-    bool pdl = false;       // JUICER_B200_PDL=1: programmatic dependent launch between the kernels of a frame step
-    int ovl_threads = 192, ovl_int = 2, ovl_walk = 4, n_sm = 148;
+    int n_sm = 148;
     // optional per-kernel timing (CUDA events on the launching stream)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -141,7 +144,6 @@ struct jgpu_handle {
     {
         if (prof_used == 0) return;
         cudaStreamSynchronize(stream);
-        cudaStreamSynchronize(stream_gmm);
         for (size_t i = 0; i + 1 < prof_used; i += 2) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, prof_ev[i], prof_ev[i + 1]);
@@ -431,7 +433,6 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
     const int C = g->max_comps, D = g->dim;
     const int DP = (D + 3) & ~3;
     h->DP = DP <= 16 ? 16 : DP <= 28 ? 28 : DP <= 40 ? 40 : DP <= 52 ? 52 : 64;
-    if (h->DP > 40 || C > h->ovl_threads) h->overlap = false;   // the persistent scorer holds mu/ivar in 112 registers
     h->dim = D;
     G.n_gmms = g->n_gmms; G.C = C; G.D = D; G.gpb = std::max(1, 256 / C);
     G.g_pad = (g->n_gmms + G.gpb - 1) / G.gpb * G.gpb;
@@ -463,6 +464,17 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
     return JGPU_OK;
 }
 
+static int bits_for(unsigned long long v)     // smallest b with v < 2^b
+{
+    int b = 0;
+    while ((v >> b) != 0ull) ++b;
+    return b;
+}
+
+// bytes of per-lane state per instance of capacity: two list buffers (record + S-1 token planes each), the arrival
+// records (two planes) and the round-0 work list at 2 per instance
+static double bytes_per_instance(int S) { return 16.0 * 2 + 16.0 * 2 * (S - 1) + 2 * (32.0 + 4.0); }
+
 int build_state(jgpu_handle* h)
 {
     Dev& d = h->d;
@@ -478,24 +490,35 @@ int build_state(jgpu_handle* h)
         d.hist_nbins = d.hist_max - d.hist_min + 1;
     }
     d.n_lanes = c.n_lanes;
-    d.cap = c.max_active > 0 ? c.max_active : std::min(d.n_arcs + 1, 1000000);
-    if (c.max_active <= 0) {
-        // auto: room for every arc of the network up to 1M instances per lane (wide beams on a 64k-word network keep
-        // > 260k instances alive), halved while the lists of all lanes would take more than 25 % of the free memory
-        size_t free_b0 = 0, total_b0 = 0;
-        CK(cudaMemGetInfo(&free_b0, &total_b0));
-        while (d.cap > (1 << 18) && (double)L * d.cap * (16.0 * 2 + 16.0 * 2 * (d.S - 1) + 36.0 * 2 + 4.0 * 2) > 0.25 * (double)free_b0) d.cap /= 2;
+    // An arc holds at most one instance (attachNetInst, src/WFSTDecoderLite.cpp:751-774), so n_arcs + 1 is all a lane
+    // can ever need — the reference simply keeps allocating.  The lists of all lanes get up to 30 % of the free
+    // memory; when that is less than a full-size lane, an utterance that overflows its lane is decoded again in a
+    // second pass that views the same pools as fewer lanes with larger arenas (decode_common).
+    h->cap_full = d.n_arcs + 1;
+    if (h->cap_full >= (1 << 28)) return fail(JGPU_E_ARG, "network too large: %d arcs", d.n_arcs);
+    size_t free_b0 = 0, total_b0 = 0;
+    CK(cudaMemGetInfo(&free_b0, &total_b0));
+    if (c.max_active > 0) {
+        d.cap = std::min(c.max_active, h->cap_full);
+    } else {
+        const double per_lane = 0.30 * (double)free_b0 / (double)L / bytes_per_instance(d.S);
+        d.cap = (int)std::min<double>(h->cap_full, std::max(per_lane, 1024.0));
     }
     d.cap = std::max(d.cap, 64);
-    d.cap = std::min(d.cap, 1000000);                    // arrival records: 21 bits, slotmap positions: 20 bits
     d.cap_arr = 2 * d.cap + 1024;
     d.cap_paths = c.max_paths > 0 ? c.max_paths : (1 << 21);   // re-sized from free memory below when 0
     d.cap_huge = std::max(h->n_huge_states, 1);          // a state is committed at most once per frame
     d.max_frames = c.max_frames > 0 ? c.max_frames : 4096;
     d.frame_stats = c.frame_stats;
-    d.max_words = 256;
     d.huge_deg = JG_HUGE_DEG;
     d.fuse_exits = !(c.end_beam > 0.0f) && !(c.word_beam > 0.0f);
+    // field widths of the stamped tables: positions up to a full-size lane, arrival ids up to 2 * (n_arcs + 1) + 1
+    d.slot_bits = bits_for((unsigned long long)h->cap_full + 1ull);
+    d.key_id_bits = bits_for(2ull * ((unsigned long long)d.n_arcs + 1ull) + 1ull);
+    d.slot_emask = (1u << std::min(32 - d.slot_bits, 16)) - 1u;
+    d.key_emask = (1u << std::min(32 - d.key_id_bits, 16)) - 1u;
+    h->epoch_wrap = std::min(d.slot_emask, d.key_emask);    // both tables are wiped when the narrower stamp wraps
+    if (h->epoch_wrap < 7u) return fail(JGPU_E_ARG, "network too large for the stamped tables: %d arcs", d.n_arcs);
     h->has_huge = h->n_huge_states > 0;
     h->bpl = std::max(2, std::min(64, (1184 + c.n_lanes - 1) / c.n_lanes));   // k_commit_huge only
     {
@@ -512,7 +535,7 @@ int build_state(jgpu_handle* h)
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     if (c.max_paths <= 0) {
-        // word-boundary arena + its free list: 4/5 of the free memory (1M .. 32M records per lane).  An arena that
+        // word-boundary arena + its free list: 4/5 of what is left (1M .. 32M records per lane).  An arena that
         // never fills to 3/4 is never garbage-collected, which keeps allocation sequential.
         const size_t fixed = need - L * (size_t)d.cap_paths * 36;
         const size_t budget = free_b > fixed + (2ull << 30) ? (free_b - fixed - (2ull << 30)) / 5 * 4 : 0;
@@ -524,18 +547,20 @@ int build_state(jgpu_handle* h)
     if (need + (1ull << 30) > free_b)
         return fail(JGPU_E_CAPACITY, "decoder state needs %.1f GB for %d lanes but only %.1f GB of device memory is free",
                     need / 1e9, c.n_lanes, free_b / 1e9);
+    h->base = jgpu_handle::View{c.n_lanes, d.cap, d.cap_arr, d.cap_paths};
+    h->pool_inst = L * cap; h->pool_arr = L * (size_t)d.cap_arr; h->pool_paths = L * (size_t)d.cap_paths;
     int rc;
     if ((rc = h->alloc(&d.ctl, L))) return rc;
-    if ((rc = h->alloc(&d.inst_meta, L * 2 * cap, false))) return rc;
-    if ((rc = h->alloc(&d.tok, L * 2 * P * cap, false))) return rc;
+    if ((rc = h->alloc(&d.inst_meta, 2 * h->pool_inst, false))) return rc;
+    if ((rc = h->alloc(&d.tok, 2 * P * h->pool_inst, false))) return rc;
     if ((rc = h->alloc(&d.slotmap, L * d.n_arcs))) return rc;
     if ((rc = h->alloc(&d.state_key, L * d.n_multi))) return rc;
-    if ((rc = h->alloc(&d.arr_tok, L * d.cap_arr, false))) return rc;
-    if ((rc = h->alloc(&d.arr_meta, L * d.cap_arr, false))) return rc;
+    if ((rc = h->alloc(&d.arr_tok, h->pool_arr, false))) return rc;
+    if ((rc = h->alloc(&d.arr_meta, h->pool_arr, false))) return rc;
     if ((rc = h->alloc(&d.huge, L * d.cap_huge, false))) return rc;
-    if ((rc = h->alloc(&d.r0_list, L * d.cap_arr, false))) return rc;
-    if ((rc = h->alloc(&d.paths, L * d.cap_paths, false))) return rc;
-    if ((rc = h->alloc(&d.path_free, L * d.cap_paths, false))) return rc;
+    if ((rc = h->alloc(&d.r0_list, h->pool_arr, false))) return rc;
+    if ((rc = h->alloc(&d.paths, h->pool_paths, false))) return rc;
+    if ((rc = h->alloc(&d.path_free, h->pool_paths, false))) return rc;
     d.gc_threshold = d.cap_paths - d.cap_paths / 4;           // collect when 3/4 full: recycled slots are scattered, so
                                                               // an arena that is big enough is never collected at all
     h->gc_period = d.cap_paths < (1 << 20) ? 16 : 64;       // small arenas (tests, tight memory) are collected more often
@@ -552,10 +577,14 @@ int build_state(jgpu_handle* h)
     if ((rc = h->alloc(&h->d_gmm_out, (size_t)h->gmm_chunk * d.n_gmms, false))) return rc;
     d.scores = h->d_scores;
     d.sched = h->d_sched;
-    // results: at least one slot per lane for the streaming interface
+    // results: at least one header per lane for the streaming interface; the words of a batch share one pool
     h->res_cap = std::max<size_t>(L, 64);
+    h->words_cap = std::max<size_t>(h->res_cap * 64, 1u << 16);
+    if (const char* e = getenv("JUICER_B200_WORD_POOL")) h->words_cap = (size_t)std::max(1, atoi(e));
     if ((rc = h->alloc(&d.res_hdr, h->res_cap))) return rc;
-    if ((rc = h->alloc(&d.res_words, h->res_cap * d.max_words))) return rc;
+    if ((rc = h->alloc(&d.res_words, h->words_cap))) return rc;
+    if ((rc = h->alloc(&d.res_used, 1))) return rc;
+    d.res_words_cap = (int)h->words_cap;
     {
         const int smem = 2 * h->S * JG_THREADS * (int)sizeof(float4);
         cudaError_t e = cudaSuccess;
@@ -579,11 +608,6 @@ int build_state(jgpu_handle* h)
         if (e == cudaSuccess && occ > 0) d.grid_internal = n_sm * occ;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_walk<1>, JG_THREADS, 0) == cudaSuccess && occ > 0) d.grid_walk = n_sm * occ;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_filter, JG_THREADS, 0) == cudaSuccess && occ > 0) d.grid_other = n_sm * occ;
-        if (h->overlap) {                       // leave the persistent scorer's CTA its share of every SM
-            d.grid_internal = std::min(d.grid_internal, n_sm * std::max(1, h->ovl_int));
-            d.grid_walk = std::min(d.grid_walk, n_sm * std::max(1, h->ovl_walk));
-            d.grid_other = std::min(d.grid_other, n_sm * std::max(1, h->ovl_walk));
-        }
         cudaGetLastError();
     }
     h->lanes.assign(L, LaneHost());
@@ -598,50 +622,90 @@ void drop_graphs(jgpu_handle* h)
     h->graph_step = h->graph_block = nullptr;
 }
 
-int ensure_results(jgpu_handle* h, size_t n)
+// room for n utterance headers and n_words result words (the pool only grows)
+int ensure_results(jgpu_handle* h, size_t n, size_t n_words)
 {
-    if (n <= h->res_cap) return JGPU_OK;
     Dev& d = h->d;
+    if (n <= h->res_cap && n_words <= h->words_cap) return JGPU_OK;
     CK(cudaStreamSynchronize(h->stream));
     drop_graphs(h);                                       // Dev (kernel argument) changes
-    h->release(d.res_hdr);
-    h->release(d.res_words);
-    d.res_hdr = nullptr; d.res_words = nullptr;
-    h->res_cap = n;
     int rc;
-    if ((rc = h->alloc(&d.res_hdr, n))) return rc;
-    if ((rc = h->alloc(&d.res_words, n * d.max_words))) return rc;
+    if (n > h->res_cap) {
+        h->release(d.res_hdr);
+        d.res_hdr = nullptr;
+        h->res_cap = n;
+        if ((rc = h->alloc(&d.res_hdr, n))) return rc;
+    }
+    if (n_words > h->words_cap) {
+        if (n_words > (size_t)1 << 30) return fail(JGPU_E_CAPACITY, "result word pool of %zu records", n_words);
+        h->release(d.res_words);
+        d.res_words = nullptr;
+        h->words_cap = n_words;
+        if ((rc = h->alloc(&d.res_words, n_words))) return rc;
+        d.res_words_cap = (int)n_words;
+    }
     return JGPU_OK;
 }
 
-int launch_gmm(jgpu_handle* h, const float* d_x, const int* d_rows, int n_rows, float* d_out, long long out_base,
-               cudaStream_t st = nullptr, bool persist = false)
+// Looks at the pools as `v.n_lanes` lanes with arenas of v.cap instances / v.cap_arr arrivals / v.cap_paths
+// word-boundary records.  Per-lane tables that do not depend on the arena sizes (slotmap, state keys, control
+// blocks, histograms) keep their stride; their stamps stay valid because a lane's epoch never goes back.
+int set_view(jgpu_handle* h, const jgpu_handle::View& v)
+{
+    Dev& d = h->d;
+    if (d.n_lanes == v.n_lanes && d.cap == v.cap && d.cap_arr == v.cap_arr && d.cap_paths == v.cap_paths) return JGPU_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    drop_graphs(h);
+    d.n_lanes = v.n_lanes; d.cap = v.cap; d.cap_arr = v.cap_arr; d.cap_paths = v.cap_paths;
+    d.gc_threshold = d.cap_paths - d.cap_paths / 4;
+    h->bpl = std::max(2, std::min(64, (1184 + v.n_lanes - 1) / v.n_lanes));
+    return JGPU_OK;
+}
+
+// The view for a second pass over `n_failed` utterances whose lanes overflowed (error bits or-ed in `errors`):
+// four times the arena that was too small (at most what a lane can ever hold), on as many lanes as the pools
+// then have room for.  Returns false when nothing can grow any more.
+bool grow_view(const jgpu_handle* h, int errors, int n_failed, jgpu_handle::View* out)
+{
+    const Dev& d = h->d;
+    jgpu_handle::View v{d.n_lanes, d.cap, d.cap_arr, d.cap_paths};
+    long long cap = v.cap;
+    if (errors & (JG_ERR_ACTIVE | JG_ERR_ARRIVALS)) cap = std::min<long long>(h->cap_full, 4ll * cap);
+    long long lanes = std::min<long long>(v.n_lanes, std::max(1, n_failed));
+    if (errors & JG_ERR_PATHS) lanes = std::max(1ll, std::min<long long>(lanes, v.n_lanes / 4));
+    lanes = std::min<long long>(lanes, (long long)(h->pool_inst / (size_t)cap));
+    lanes = std::min<long long>(lanes, (long long)(h->pool_arr / (size_t)(2 * cap + 1024)));
+    if (lanes < 1) {                                      // not even one lane of that size: one lane takes the whole pool
+        lanes = 1;
+        cap = std::min<long long>((long long)h->pool_inst, ((long long)h->pool_arr - 1024) / 2);
+    }
+    v.n_lanes = (int)lanes;
+    v.cap = (int)cap;
+    v.cap_arr = (int)(2 * cap + 1024);
+    v.cap_paths = (int)std::min<size_t>(h->pool_paths / (size_t)lanes, (size_t)1 << 30);
+    const bool grew = v.cap > d.cap || v.cap_paths > d.cap_paths;
+    *out = v;
+    return grew;
+}
+
+int launch_gmm(jgpu_handle* h, const float* d_x, const int* d_rows, int n_rows, float* d_out, long long out_base)
 {
     if (n_rows <= 0) return JGPU_OK;
-    if (!st) st = h->stream;
+    cudaStream_t st = h->stream;
     const GmmDev& G = h->g;
-    const int NT = persist ? h->ovl_threads : 256;
-    const int gpb = persist ? std::max(1, NT / G.C) : G.gpb;
+    const int gpb = G.gpb;
     const int n_bx = (G.n_gmms + gpb - 1) / gpb, n_by = (n_rows + JG_GMM_RT - 1) / JG_GMM_RT;
     const int cstride = JG_GMM_RT * gpb + (gpb & 31);
     const size_t smem = ((size_t)JG_GMM_RT * h->DP + (size_t)G.C * cstride) * sizeof(float);
-    const long long tiles = (long long)n_bx * n_by;
-    const int grid_p = (int)std::min<long long>(tiles, h->n_sm);
     h->prof_begin(JGPU_K_GMM, st);
     switch (h->DP) {
-#define GMM_LAUNCH(KERNEL, NTV, GRID)                                                                       \
-        CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-        KERNEL<<<GRID, NTV, smem, st>>>(G, gpb, d_x, d_rows, n_rows, d_out, out_base, n_by);
 #define GMM_CASE(DPV)                                                                                          \
     case DPV:                                                                                                  \
-        if (!persist) { GMM_LAUNCH(k_gmm_scores<DPV>, 256, dim3(n_bx, n_by)) }                                 \
-        else if (NT == 192) { GMM_LAUNCH((k_gmm_scores_persist<DPV, 192>), 192, grid_p) }                      \
-        else if (NT == 128) { GMM_LAUNCH((k_gmm_scores_persist<DPV, 128>), 128, grid_p) }                      \
-        else { GMM_LAUNCH((k_gmm_scores_persist<DPV, 256>), 256, grid_p) }                                     \
+        CK(cudaFuncSetAttribute(k_gmm_scores<DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        k_gmm_scores<DPV><<<dim3(n_bx, n_by), 256, smem, st>>>(G, gpb, d_x, d_rows, n_rows, d_out, out_base, n_by); \
         break;
         GMM_CASE(16) GMM_CASE(28) GMM_CASE(40) GMM_CASE(52) GMM_CASE(64)
 #undef GMM_CASE
-#undef GMM_LAUNCH
     default: return fail(JGPU_E_ARG, "unsupported padded dim %d", h->DP);
     }
     h->prof_end(st);
@@ -650,24 +714,11 @@ int launch_gmm(jgpu_handle* h, const float* d_x, const int* d_rows, int n_rows, 
     return JGPU_OK;
 }
 
-// <<<>>> with the programmatic-dependent-launch attribute (see JG_PDL_ENTER)
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
-}
-
 int launch_step(jgpu_handle* h)
 {
-    const bool pdl = h->pdl && !h->prof_on;
     const Dev& d = h->d;
     const dim3 grid_huge(h->bpl, d.n_lanes);
+    cudaStream_t st = h->stream;
 #ifdef JG_TRACE
     if (h->d_trace) {
         static const int on = 1, off = 0;
@@ -677,37 +728,37 @@ int launch_step(jgpu_handle* h)
     }
 #endif
     h->prof_begin(JGPU_K_BOUNDARY);
-    launch_k(pdl, k_boundary, dim3(d.n_lanes), dim3(32), 0, h->stream, d);
+    k_boundary<<<d.n_lanes, 32, 0, st>>>(d);
     h->prof_end();
     h->prof_begin(JGPU_K_INTERNAL);
     {
         const size_t smem = (size_t)2 * h->S * JG_THREADS * sizeof(float4);   // two chunk buffers: record + S-1 token planes
         if (h->S == 5) {
-            if (d.fuse_exits) launch_k(pdl, k_internal<5, true>, dim3(d.grid_internal), dim3(JG_THREADS), smem, h->stream, d);
-            else launch_k(pdl, k_internal<5, false>, dim3(d.grid_internal), dim3(JG_THREADS), smem, h->stream, d);
+            if (d.fuse_exits) k_internal<5, true><<<d.grid_internal, JG_THREADS, smem, st>>>(d);
+            else k_internal<5, false><<<d.grid_internal, JG_THREADS, smem, st>>>(d);
         } else {
-            if (d.fuse_exits) launch_k(pdl, k_internal<8, true>, dim3(d.grid_internal), dim3(JG_THREADS), smem, h->stream, d);
-            else launch_k(pdl, k_internal<8, false>, dim3(d.grid_internal), dim3(JG_THREADS), smem, h->stream, d);
+            if (d.fuse_exits) k_internal<8, true><<<d.grid_internal, JG_THREADS, smem, st>>>(d);
+            else k_internal<8, false><<<d.grid_internal, JG_THREADS, smem, st>>>(d);
         }
     }
     h->prof_end();
     if (!d.fuse_exits) {
         h->prof_begin(JGPU_K_SEED);
-        launch_k(pdl, k_filter, dim3(d.grid_other), dim3(JG_THREADS), 0, h->stream, d);
+        k_filter<<<d.grid_other, JG_THREADS, 0, st>>>(d);
         h->prof_end();
         ++h->launches;
     }
     for (int r = 0; r < d.n_rounds; ++r) {
         h->prof_begin(r == 0 ? JGPU_K_EXPAND : r == 1 ? JGPU_K_EXPAND_R1 : JGPU_K_EXPAND_R2);
-        launch_k(pdl, k_walk<0>, dim3(d.grid_walk), dim3(JG_THREADS), 0, h->stream, d, r);
+        k_walk<0><<<d.grid_walk, JG_THREADS, 0, st>>>(d, r);
         h->prof_end();
     }
     h->prof_begin(JGPU_K_COMMIT);
-    launch_k(pdl, k_walk<1>, dim3(d.grid_walk), dim3(JG_THREADS), 0, h->stream, d, 0);
+    k_walk<1><<<d.grid_walk, JG_THREADS, 0, st>>>(d, 0);
     h->prof_end();
     if (h->has_huge) {
         h->prof_begin(JGPU_K_EXPAND_HUGE);
-        launch_k(pdl, k_commit_huge, grid_huge, dim3(JG_THREADS), 0, h->stream, d);
+        k_commit_huge<<<grid_huge, JG_THREADS, 0, st>>>(d);
         h->prof_end();
         ++h->launches;
     }
@@ -765,34 +816,25 @@ int run_schedule(jgpu_handle* h, const std::vector<int4>& sched, int n_steps, co
         CK(cudaMemcpyAsync(h->d_sched, chunk.data(), chunk.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemsetAsync(h->d.lane_step, 0, (size_t)L * sizeof(int), h->stream));
         if (ns) CK(cudaMemcpyAsync(h->d_rows, rows.data(), (size_t)ns * L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaEventRecord(h->ev_inputs, h->stream));            // features + row table are in place
-        CK(cudaStreamWaitEvent(h->stream_gmm, h->ev_inputs, 0));
-        // acoustic scores of frame block b+1 are computed on the second stream while the search runs block b
+        // the acoustic scores of frame block b+1 are enqueued ahead of the search of block b (two halves of the ring)
         auto issue_gmm = [&](int b) -> int {
             const int b0 = b * FB, nb = std::min(FB, ns - b0), half = b & 1;
-            CK(cudaStreamWaitEvent(h->stream_gmm, h->ev_search[half], 0));   // that half of the ring is free again
-            const bool ovl = h->overlap && !h->prof_on;
-            cudaStream_t st = ovl ? h->stream_gmm : h->stream;
-            int rc = launch_gmm(h, d_x, h->d_rows + (size_t)b0 * L, nb * L, h->d_scores, (long long)half * FB * L, st, ovl);
-            if (rc) return rc;
-            CK(cudaEventRecord(h->ev_gmm[half], st));
-            return JGPU_OK;
+            return launch_gmm(h, d_x, h->d_rows + (size_t)b0 * L, nb * L, h->d_scores, (long long)half * FB * L);
         };
         const int n_blocks = (ns + FB - 1) / FB;
         if (n_blocks > 0) { int rc = issue_gmm(0); if (rc) return rc; }
         for (int b = 0; b < n_blocks; ++b) {
             int rc;
             if (b + 1 < n_blocks && (rc = issue_gmm(b + 1))) return rc;
-            CK(cudaStreamWaitEvent(h->stream, h->ev_gmm[b & 1], 0));
             const int b0 = b * FB, nb = std::min(FB, ns - b0);
-            // a lane whose 11-bit epoch stamp wraps inside this block gets its stamped tables wiped right before
-            // that step (once per 2048 steps); such a block is launched step by step
+            // a lane whose epoch stamp wraps inside this block gets its stamped tables wiped right before that
+            // step (every epoch_wrap + 1 steps: 2048 on a 2M-arc network); such a block is launched step by step
             bool wipe_in_block = false;
             {
                 std::vector<unsigned> ep(h->host_epoch);
                 for (int i = b0; i < b0 + nb && !wipe_in_block; ++i)
                     for (int l = 0; l < L; ++l)
-                        if ((chunk[(size_t)i * L + l].z & 3) != JG_MODE_IDLE && ((++ep[l]) & 0x7ffu) == 0u) { wipe_in_block = true; break; }
+                        if ((chunk[(size_t)i * L + l].z & 3) != JG_MODE_IDLE && ((++ep[l]) & h->epoch_wrap) == 0u) { wipe_in_block = true; break; }
             }
             const bool graphs = h->use_graphs && !h->prof_on && !JG_TRACING(h);
             if (graphs && nb == FB && !wipe_in_block) {
@@ -804,7 +846,7 @@ int run_schedule(jgpu_handle* h, const std::vector<int4>& sched, int n_steps, co
                 for (int i = b0; i < b0 + nb; ++i) {
                     for (int l = 0; l < L; ++l) {
                         if ((chunk[(size_t)i * L + l].z & 3) == JG_MODE_IDLE) continue;
-                        if (((++h->host_epoch[l]) & 0x7ffu) == 0u) {
+                        if (((++h->host_epoch[l]) & h->epoch_wrap) == 0u) {
                             CK(cudaMemsetAsync(h->d.state_key + (size_t)l * d.n_multi, 0, (size_t)d.n_multi * sizeof(u64), h->stream));
                             CK(cudaMemsetAsync(h->d.slotmap + (size_t)l * d.n_arcs, 0, (size_t)d.n_arcs * sizeof(unsigned), h->stream));
                         }
@@ -824,7 +866,6 @@ int run_schedule(jgpu_handle* h, const std::vector<int4>& sched, int n_steps, co
                 h->launches += 3;
                 CK(cudaGetLastError());
             }
-            CK(cudaEventRecord(h->ev_search[b & 1], h->stream));
         }
         if (last) {
             h->prof_begin(JGPU_K_BOUNDARY);
@@ -839,44 +880,54 @@ int run_schedule(jgpu_handle* h, const std::vector<int4>& sched, int n_steps, co
     return JGPU_OK;
 }
 
+void fill_result(const ResHdr& hdr, const JgpuWord* pool, JgpuResult* out)
+{
+    out->status = hdr.status; out->n_frames = hdr.n_frames;
+    out->score = hdr.score; out->ac = hdr.ac; out->lm = hdr.lm;
+    if (hdr.status > 0 && out->words && out->max_words > 0) {
+        // words[] holds min(status, max_words) records; when the caller's buffer is the smaller one it gets the NEWEST
+        // words, so that the last record is always the one carrying the final-weight-inclusive totals
+        const int n = std::min(hdr.status, out->max_words);
+        memcpy(out->words, pool + hdr.word_off + (hdr.status - n), (size_t)n * sizeof(JgpuWord));
+    }
+}
+
 int fetch_result(jgpu_handle* h, int slot, JgpuResult* out)
 {
     const Dev& d = h->d;
     ResHdr hdr;
     CK(cudaMemcpy(&hdr, d.res_hdr + slot, sizeof(hdr), cudaMemcpyDeviceToHost));
-    out->status = hdr.status; out->n_frames = hdr.n_frames;
-    out->score = hdr.score; out->ac = hdr.ac; out->lm = hdr.lm;
-    if (hdr.status > 0 && out->words && out->max_words > 0) {
-        const int n = std::min(std::min(hdr.status, out->max_words), d.max_words);
-        CK(cudaMemcpy(out->words, d.res_words + (size_t)slot * d.max_words, (size_t)n * sizeof(JgpuWord), cudaMemcpyDeviceToHost));
+    std::vector<JgpuWord> words;
+    if (hdr.status > 0) {
+        words.resize((size_t)hdr.word_off + hdr.status);
+        CK(cudaMemcpy(words.data() + hdr.word_off, d.res_words + hdr.word_off, (size_t)hdr.status * sizeof(JgpuWord), cudaMemcpyDeviceToHost));
     }
+    fill_result(hdr, words.data(), out);
     return JGPU_OK;
 }
 
-int decode_common(jgpu_handle* h, const float* d_feats, const int64_t* row_offset, const int32_t* n_frames,
-                  int32_t n_utts, JgpuResult* out)
+// One pass over the utterances `ids` (indices into the caller's arrays) with the current view: LPT assignment to
+// lanes, lock-step schedule, results into out[ids[k]].  err[k] = the utterance's device error bits, need_words[k] =
+// the words its best path has.
+int decode_pass(jgpu_handle* h, const float* d_feats, const int64_t* row_offset, const int32_t* n_frames,
+                const std::vector<int>& ids, JgpuResult* out, std::vector<int>* err, std::vector<int>* need_words)
 {
     Dev& d = h->d;
-    const int L = d.n_lanes;
-    for (auto& l : h->lanes)
-        if (l.begun) return fail(JGPU_E_STATE, "streaming utterance in flight: finish it before a batch call");
-    int rc = ensure_results(h, (size_t)n_utts);
-    if (rc) return rc;
+    const int L = d.n_lanes, n_utts = (int)ids.size();
     // LPT assignment of utterances to lanes (longest first, to the least loaded lane)
     std::vector<int> order(n_utts);
     for (int i = 0; i < n_utts; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n_frames[a] > n_frames[b]; });
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n_frames[ids[a]] > n_frames[ids[b]]; });
     typedef std::pair<long long, int> LoadLane;
     std::priority_queue<LoadLane, std::vector<LoadLane>, std::greater<LoadLane>> pq;
     for (int l = 0; l < L; ++l) pq.push(LoadLane(0, l));
     std::vector<std::vector<int>> per_lane(L);
     long long n_steps = 0;
-    for (int i : order) {
-        if (n_frames[i] < 0) return fail(JGPU_E_ARG, "utterance %d: negative frame count", i);
+    for (int k : order) {
         LoadLane t = pq.top();
         pq.pop();
-        per_lane[t.second].push_back(i);
-        t.first += (long long)n_frames[i] + 1;             // +1: the seeding step
+        per_lane[t.second].push_back(k);
+        t.first += (long long)n_frames[ids[k]] + 1;         // +1: the seeding step
         n_steps = std::max(n_steps, t.first);
         pq.push(t);
     }
@@ -884,22 +935,24 @@ int decode_common(jgpu_handle* h, const float* d_feats, const int64_t* row_offse
     std::vector<int4> sched((size_t)(n_steps + 1) * L, make_int4(-1, 0, JG_MODE_IDLE, -1));
     for (int l = 0; l < L; ++l) {
         long long s = 0;
-        for (int u : per_lane[l]) {
+        for (int k : per_lane[l]) {
+            const int u = ids[k];
             int4& e = sched[(size_t)s * L + l];
             e.z |= JG_MODE_SEED;                            // keeps a FINISH flag set by the previous utterance
-            e.w = u;
+            e.w = k;                                        // result slot = position in `ids`
             ++s;
             for (int t = 0; t < n_frames[u]; ++t, ++s) {
                 int4& f = sched[(size_t)s * L + l];
                 f.x = (int)(row_offset[u] + t);
                 f.z = JG_MODE_FRAME;
-                f.w = u;
+                f.w = k;
             }
             sched[(size_t)s * L + l].z |= JG_FLAG_FINISH;   // row after the last frame
         }
     }
     k_reset_batch_stats<<<(L + 127) / 128, 128, 0, h->stream>>>(d);
     ++h->launches;
+    CK(cudaMemsetAsync(d.res_used, 0, sizeof(int), h->stream));
 #ifdef JG_TRACE
     if (h->d_trace) {
         static const unsigned zero = 0;
@@ -909,7 +962,7 @@ int decode_common(jgpu_handle* h, const float* d_feats, const int64_t* row_offse
         cudaMemcpyToSymbolAsync(g_trace_on, &off, sizeof(int), 0, cudaMemcpyHostToDevice, h->stream);
     }
 #endif
-    rc = run_schedule(h, sched, (int)n_steps, d_feats);
+    int rc = run_schedule(h, sched, (int)n_steps, d_feats);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
 #ifdef JG_TRACE
@@ -931,30 +984,75 @@ int decode_common(jgpu_handle* h, const float* d_feats, const int64_t* row_offse
         long long b[10] = {0};
         for (int l = 0; l < L; ++l)
             for (int i = 0; i < 10; ++i) b[i] += ctl[l].b_stats[i];
-        JgpuStats& st = h->batch_stats;
-        st.n_frames = b[0]; st.total_active_models = b[1]; st.total_active_emit_hyps = b[2];
-        st.total_active_end_hyps = b[3]; st.total_proc_emit_hyps = b[4]; st.total_proc_end_hyps = b[5];
-        st.total_gmm_evals = b[6]; st.total_arcs_expanded = b[7]; st.total_entry_writes = b[8]; st.total_paths = b[9];
+        JgpuStats& st = h->batch_stats;                      // (summed over the passes of a batch call)
+        st.n_frames += b[0]; st.total_active_models += b[1]; st.total_active_emit_hyps += b[2];
+        st.total_active_end_hyps += b[3]; st.total_proc_emit_hyps += b[4]; st.total_proc_end_hyps += b[5];
+        st.total_gmm_evals += b[6]; st.total_arcs_expanded += b[7]; st.total_entry_writes += b[8]; st.total_paths += b[9];
     }
     // results
     std::vector<ResHdr> hdr(n_utts);
     if (n_utts) CK(cudaMemcpy(hdr.data(), d.res_hdr, (size_t)n_utts * sizeof(ResHdr), cudaMemcpyDeviceToHost));
-    std::vector<JgpuWord> words;
-    bool need_words = false;
-    for (int u = 0; u < n_utts; ++u) need_words |= (hdr[u].status > 0 && out[u].words && out[u].max_words > 0);
-    if (need_words) {
-        words.resize((size_t)n_utts * d.max_words);
-        CK(cudaMemcpy(words.data(), d.res_words, words.size() * sizeof(JgpuWord), cudaMemcpyDeviceToHost));
-    }
-    for (int u = 0; u < n_utts; ++u) {
-        out[u].status = hdr[u].status; out[u].n_frames = hdr[u].n_frames;
-        out[u].score = hdr[u].score; out[u].ac = hdr[u].ac; out[u].lm = hdr[u].lm;
-        if (hdr[u].status > 0 && out[u].words && out[u].max_words > 0) {
-            const int n = std::min(std::min(hdr[u].status, out[u].max_words), d.max_words);
-            memcpy(out[u].words, words.data() + (size_t)u * d.max_words, (size_t)n * sizeof(JgpuWord));
-        }
+    int used = 0;
+    CK(cudaMemcpy(&used, d.res_used, sizeof(int), cudaMemcpyDeviceToHost));
+    used = std::max(0, std::min(used, d.res_words_cap));
+    std::vector<JgpuWord> words((size_t)used);
+    bool want_words = false;
+    for (int k = 0; k < n_utts; ++k) want_words |= (hdr[k].status > 0 && out[ids[k]].words && out[ids[k]].max_words > 0);
+    if (want_words && used) CK(cudaMemcpy(words.data(), d.res_words, (size_t)used * sizeof(JgpuWord), cudaMemcpyDeviceToHost));
+    err->assign(n_utts, 0);
+    need_words->assign(n_utts, 0);
+    for (int k = 0; k < n_utts; ++k) {
+        fill_result(hdr[k], words.data(), &out[ids[k]]);
+        (*err)[k] = hdr[k].error;
+        (*need_words)[k] = hdr[k].n_words;
     }
     return JGPU_OK;
+}
+
+// A batch call: one pass with the handle's view; utterances whose lane overflowed an arena (wide beams on a large
+// network) are then decoded again, from their first frame, with the pools viewed as fewer lanes with larger arenas,
+// until nothing fails or nothing can grow: the reference has no capacity at all (it keeps allocating,
+// src/WFSTDecoderLite.cpp:751-805), so a capacity failure must never be what the caller sees.
+int decode_common(jgpu_handle* h, const float* d_feats, const int64_t* row_offset, const int32_t* n_frames,
+                  int32_t n_utts, JgpuResult* out)
+{
+    for (auto& l : h->lanes)
+        if (l.begun) return fail(JGPU_E_STATE, "streaming utterance in flight: finish it before a batch call");
+    for (int i = 0; i < n_utts; ++i)
+        if (n_frames[i] < 0) return fail(JGPU_E_ARG, "utterance %d: negative frame count", i);
+    size_t pool0 = std::max<size_t>((size_t)n_utts * 64, 1u << 16);
+    if (const char* e = getenv("JUICER_B200_WORD_POOL")) pool0 = (size_t)std::max(1, atoi(e));   // (tests: force the pool to grow)
+    int rc = ensure_results(h, (size_t)n_utts, pool0);
+    if (rc) return rc;
+    memset(&h->batch_stats, 0, sizeof(h->batch_stats));
+    std::vector<int> ids(n_utts), err, need_words;
+    for (int i = 0; i < n_utts; ++i) ids[i] = i;
+    if ((rc = set_view(h, h->sticky ? h->sticky_view : h->base))) return rc;
+    for (int pass = 0; pass < 4 && !ids.empty(); ++pass) {
+        if ((rc = decode_pass(h, d_feats, row_offset, n_frames, ids, out, &err, &need_words))) break;
+        std::vector<int> failed;
+        int errors = 0;
+        size_t words = 0;
+        for (size_t k = 0; k < ids.size(); ++k)
+            if (err[k] & JG_ERR_RETRYABLE) {
+                failed.push_back(ids[k]);
+                errors |= err[k];
+                words += (size_t)std::max(need_words[k], 64);
+            }
+        if (failed.empty()) break;
+        jgpu_handle::View v;
+        const bool grew = grow_view(h, errors, (int)failed.size(), &v);
+        const bool more_words = (errors & JG_ERR_WORDS) != 0;
+        if (!grew && !more_words) break;                      // nothing left to enlarge: the statuses stand
+        if (more_words && (rc = ensure_results(h, failed.size(), words + words / 2))) break;
+        if (grew && (rc = set_view(h, v))) break;
+        // a batch that mostly overflowed starts the next call with the larger arenas straight away
+        if (grew && pass == 0 && failed.size() * 2 > ids.size()) { h->sticky = true; h->sticky_view = v; }
+        ++h->retry_passes;
+        ids.swap(failed);
+    }
+    const int rc2 = set_view(h, h->base);                     // the streaming interface always sees the base view
+    return rc ? rc : rc2;
 }
 
 int lane_stats(jgpu_handle* h, int lane, JgpuStats* out)
@@ -999,25 +1097,10 @@ int jgpu_create(const JgpuNet* net, const JgpuHmm* hmm, const JgpuGmm* gmm, cons
     jgpu_handle* h = new jgpu_handle;
     h->cfg = *cfg;
     h->device = cfg->device;
-    h->overlap = getenv("JUICER_B200_OVERLAP") && atoi(getenv("JUICER_B200_OVERLAP")) != 0;
-    if (const char* v = getenv("JUICER_B200_PDL")) h->pdl = atoi(v) != 0;
-    if (const char* v = getenv("JUICER_B200_OVL_THREADS")) h->ovl_threads = atoi(v);
-    if (const char* v = getenv("JUICER_B200_OVL_INT")) h->ovl_int = atoi(v);
-    if (const char* v = getenv("JUICER_B200_OVL_WALK")) h->ovl_walk = atoi(v);
-    if (h->ovl_threads != 128 && h->ovl_threads != 192 && h->ovl_threads != 256) h->ovl_threads = 192;
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device);
     if (const char* g = getenv("JUICER_B200_GRAPHS")) h->use_graphs = atoi(g) != 0;
-    int prio_least = 0, prio_greatest = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-    e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_greatest);     // search: latency-critical
+    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return fail(JGPU_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
-    e = cudaStreamCreateWithPriority(&h->stream_gmm, cudaStreamNonBlocking, prio_least);    // scoring fills what is left
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_inputs, cudaEventDisableTiming);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-        e = cudaEventCreateWithFlags(&h->ev_gmm[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_search[i], cudaEventDisableTiming);
-    }
-    if (e != cudaSuccess) { jgpu_destroy(h); return fail(JGPU_E_CUDA, "stream/event setup: %s", cudaGetErrorString(e)); }
     rc = build_tables(h, net, hmm, gmm);
     if (!rc) rc = build_state(h);
 #ifdef JG_TRACE
@@ -1047,13 +1130,7 @@ int jgpu_destroy(jgpu_handle* h)
     if (!h) return JGPU_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->stream_gmm) { cudaStreamSynchronize(h->stream_gmm); cudaStreamDestroy(h->stream_gmm); }
     drop_graphs(h);
-    if (h->ev_inputs) cudaEventDestroy(h->ev_inputs);
-    for (int i = 0; i < 2; ++i) {
-        if (h->ev_gmm[i]) cudaEventDestroy(h->ev_gmm[i]);
-        if (h->ev_search[i]) cudaEventDestroy(h->ev_search[i]);
-    }
     for (void* p : h->allocs) cudaFree(p);
     if (h->d_feats) cudaFree(h->d_feats);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
@@ -1138,6 +1215,7 @@ int jgpu_utt_end(jgpu_handle* h, int32_t lane, JgpuResult* out)
     const int L = h->d.n_lanes;
     std::vector<int4> sched((size_t)L, make_int4(-1, 0, JG_MODE_IDLE, -1));
     sched[lane].z |= JG_FLAG_FINISH;
+    CK(cudaMemsetAsync(h->d.res_used, 0, sizeof(int), h->stream));   // one result at a time sits in the word pool
     if ((rc = run_schedule(h, sched, 0, h->d_stream_feats))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     lh.begun = false;

@@ -220,13 +220,3 @@ k_gmm_scores(GmmDev g, int gpb, const float* __restrict__ x, const int* __restri
 {
     gmm_scores_body<DP, 256, false>(g, gpb, x, rows, n_rows, out, out_base, n_by);
 }
-
-// persistent form; 112 registers per thread keep an NT = 192 CTA at 21.5 K registers, so that it shares an SM
-// with two k_internal<5> CTAs (2 x 20.5 K) or four k_walk CTAs
-template <int DP, int NT>
-__global__ void __maxnreg__(112)
-k_gmm_scores_persist(GmmDev g, int gpb, const float* __restrict__ x, const int* __restrict__ rows, int n_rows,
-                     float* __restrict__ out, long long out_base, int n_by)
-{
-    gmm_scores_body<DP, NT, true>(g, gpb, x, rows, n_rows, out, out_base, n_by);
-}

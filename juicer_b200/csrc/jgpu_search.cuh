@@ -189,13 +189,23 @@ __device__ __forceinline__ u64 warp_max_u64(u64 v)
     return v;
 }
 
-// state key = epoch (11 bits) | orderable score (32 bits) | arrival record (21 bits): keys of older
-// steps always lose the atomicMax and never compare equal, so state_key needs no per-frame cleaning
-// (the host wipes a lane's table when its 11-bit epoch wraps, once every 2048 steps).
-#define JG_R_BITS 21
-__device__ __forceinline__ u64 state_key_of(unsigned epoch, float score, unsigned r)
+// state key = epoch stamp | orderable score (32 bits) | arrival id (key_id_bits): keys of older steps always lose
+// the atomicMax and never compare equal, so state_key needs no per-frame cleaning (the host wipes a lane's table
+// when its epoch stamp wraps).
+// Arrival id = 2 * (via arc + 1) + pass-through flag (0 for the utterance seed): a property of the NETWORK, not of
+// the order in which records were allocated, so that an exact score tie between two arrivals at one state is broken
+// the same way in every run (the larger id wins; the reference keeps whichever it met first in its list order,
+// src/WFSTDecoderLite.cpp:563-571).  An arc delivers an exit token (flag 0) and, for a tee model, a pass-through
+// token (flag 1) at most once per frame each, except a pass-through arc whose source state is expanded again in a
+// later round: then the later arrival has a score >= the earlier one, and when it is EQUAL its key is equal too —
+// process_arc<0> sees that in the value atomicMax returns and drops the later record, so keys stay unique.
+__device__ __forceinline__ unsigned arrival_id(int via, int pass_through)
 {
-    return ((u64)(epoch & 0x7ffu) << 53) | ((u64)f2o(score) << JG_R_BITS) | (u64)r;
+    return ((unsigned)(via + 1) << 1) | (unsigned)pass_through;
+}
+__device__ __forceinline__ u64 state_key_of(const Dev& d, unsigned epoch, float score, unsigned id)
+{
+    return ((u64)(epoch & d.key_emask) << (32 + d.key_id_bits)) | ((u64)f2o(score) << d.key_id_bits) | (u64)id;
 }
 
 // =========================================================================================
@@ -211,7 +221,7 @@ __device__ void finish_utterance(const Dev& d, const LaneView& v, int lane)
     if (utt < 0) return;
     ResHdr h;
     h.status = -1; h.n_frames = c->frame; h.score = h.ac = h.lm = JG_LZ;
-    h.error = c->error; h.pad1 = h.pad2 = 0;
+    h.error = c->error; h.word_off = 0; h.n_words = 0;
     if (c->error) {
         h.status = JGPU_E_CAPACITY - 10 - (c->error << 8);
     } else if (c->final_valid) {
@@ -221,12 +231,20 @@ __device__ void finish_utterance(const Dev& d, const LaneView& v, int lane)
         if (n == 0) {
             h.status = -2;                                   // :273-306: no word label on the path
         } else {
-            h.status = n; h.score = best.x; h.ac = best.y; h.lm = best.z;
-            JgpuWord* w = d.res_words + (size_t)utt * d.max_words;
-            int k = n;
-            for (int p = __float_as_int(best.w); p >= 0; p = v.paths[p].prev) {
-                --k;
-                if (k < d.max_words) {
+            // the chain goes into the batch's word pool, oldest word first: no per-utterance limit (the reference
+            // allocates one DecHypHist per word, :279-301)
+            const int off = atomicAdd(d.res_used, n);
+            h.n_words = n;
+            if (off < 0 || off + n > d.res_words_cap) {
+                h.error = JG_ERR_WORDS;                       // the host grows the pool and decodes this utterance again
+                h.status = JGPU_E_CAPACITY - 10 - (JG_ERR_WORDS << 8);
+            } else {
+                h.status = n; h.score = best.x; h.ac = best.y; h.lm = best.z;
+                h.word_off = off;
+                JgpuWord* w = d.res_words + off;
+                int k = n;
+                for (int p = __float_as_int(best.w); p >= 0; p = v.paths[p].prev) {
+                    --k;
                     const PathRec r = v.paths[p];
                     JgpuWord o;
                     o.label = r.label; o.time = r.frame; o.score = r.score; o.ac = r.ac; o.lm = r.lm;
@@ -237,11 +255,13 @@ __device__ void finish_utterance(const Dev& d, const LaneView& v, int lane)
         }
     }
     d.res_hdr[utt] = h;
-    c->b_stats[0] += c->s_frames;        c->b_stats[1] += c->s_active_models;
-    c->b_stats[2] += c->s_active_emit;   c->b_stats[3] += c->s_active_end;
-    c->b_stats[4] += c->s_proc_emit;     c->b_stats[5] += c->s_proc_end;
-    c->b_stats[6] += c->s_gmm;           c->b_stats[7] += c->s_arcs;
-    c->b_stats[8] += c->s_entry;         c->b_stats[9] += c->s_paths;
+    if (!(h.error & JG_ERR_RETRYABLE)) {                     // (an utterance that is decoded again counts once)
+        c->b_stats[0] += c->s_frames;        c->b_stats[1] += c->s_active_models;
+        c->b_stats[2] += c->s_active_emit;   c->b_stats[3] += c->s_active_end;
+        c->b_stats[4] += c->s_proc_emit;     c->b_stats[5] += c->s_proc_end;
+        c->b_stats[6] += c->s_gmm;           c->b_stats[7] += c->s_arcs;
+        c->b_stats[8] += c->s_entry;         c->b_stats[9] += c->s_paths;
+    }
 }
 
 __global__ void k_reset_batch_stats(Dev d)
@@ -294,7 +314,6 @@ __device__ float hist_thresh_warp(const Dev& d, const LaneView& v)
 // chunk), so that the launch has no per-step argument and a whole block of steps replays as one CUDA graph.
 __global__ void __launch_bounds__(32) k_boundary(Dev d)
 {
-    JG_PDL_ENTER();
     const int lane = blockIdx.x;
     const int l = lane_id();
     int step = 0;
@@ -324,9 +343,10 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
         if (n_arr_total > d.cap_arr) c->error |= JG_ERR_ARRIVALS;
         if (c->n_paths > d.cap_paths) c->error |= JG_ERR_PATHS;
         const u64 key = c->best_final;
-        if (key) {
-            float4 t = v.arr_tok[(unsigned)key];
-            const float fw = __int_as_float(d.states[v.arr_meta[(unsigned)key].y & JG_STATE_MASK].z);
+        if (key && c->final_rec >= 0) {                      // (the commit pass found the record behind the key)
+            const int fr = c->final_rec;
+            float4 t = v.arr_tok[fr];
+            const float fw = __int_as_float(d.states[v.arr_meta[fr].y & JG_STATE_MASK].z);
             t.x += fw;                                        // :517-518
             t.z += fw;
             c->final_tok = t;
@@ -376,6 +396,7 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
         c->n_next = 0; c->n_huge = 0; c->n_r0 = 0;
         for (int i = 0; i <= JG_MAX_ROUNDS + 1; ++i) c->n_arr[i] = 0;
         c->best_final = 0;
+        c->final_rec = -1;
         c->c_active_emit = c->c_active_end = c->c_end_proc = c->c_arcs = c->c_entry = 0;
         c->mode = mode;
         if (mode != JG_MODE_IDLE) c->epoch += 1;             // invalidates every arcdyn.slot of older steps
@@ -399,7 +420,7 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
             c->n_arr[0] = 1;
             d.r0_list[(size_t)lane * d.cap_arr] = 0;          // the seed always goes through the expansion rounds
             c->n_r0 = 1;
-            if (d.init_multi) v.skey[d.init_state] = state_key_of(c->epoch, 0.0f, 0u);
+            if (d.init_multi) v.skey[d.init_state] = state_key_of(d, c->epoch, 0.0f, arrival_id(-1, 0));
         } else if (mode == JG_MODE_FRAME) {                  // processFrame :318-339
             const float bi = o2f(c->best_int), bx = o2f(c->best_ext);
             const float be = bi > bx ? bi : bx;              // bestEmitScore at the end of the last frame
@@ -417,8 +438,7 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
             c->thr_start = (d.start_beam > 0.0f ? (be - d.start_beam) : JG_LZ);
             c->best_int = f2o(JG_LZ);                        // :905
             c->best_ext = f2o(JG_LZ);
-            c->srow = s.y;
-            if (c->frame >= d.max_frames && d.frame_stats) c->error |= JG_ERR_FRAMES;
+            c->srow = s.y;                                   // (per-frame statistics simply stop at max_frames)
         }
     }
     if (mode == JG_MODE_SEED && d.max_hyps > 0)
@@ -503,7 +523,6 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int S, bool FUSE>
 __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_internal(Dev d)
 {
-    JG_PDL_ENTER();
     JG_TRACE_SCOPE(JGPU_K_INTERNAL, 0);
     constexpr int P = S - 1;
     constexpr int NW = JG_THREADS / 32;
@@ -782,7 +801,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
 #pragma unroll
             for (int i = 1; i < P; ++i)
                 if (i < nst - 1) st_stream(tok_nxt + (size_t)i * cap + pos, nt[i]);
-            d.slotmap[(size_t)lane * d.n_arcs + meta.x] = ((epoch & 0x7ffu) << JG_SLOT_BITS) | ((unsigned)pos + 1u);
+            d.slotmap[(size_t)lane * d.n_arcs + meta.x] = slot_entry(d, epoch, pos);
         }
         if (has_exit && e < d.cap_arr) {
             int via = meta.x;
@@ -804,7 +823,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
             d.arr_meta[(size_t)lane * d.cap_arr + e] = make_int4(via, meta.z, meta.w, 0);
             if (FUSE && meta.z < 0)                       // destination can see several arrivals this frame
                 atomicMax(d.state_key + (size_t)lane * d.n_multi + (meta.z & JG_STATE_MASK),
-                          state_key_of(epoch, ex.x, (unsigned)e));
+                          state_key_of(d, epoch, ex.x, arrival_id(meta.x, 0)));
         }
         JG_TRACE_AT(6);                                       // stores issued: end of the first chunk
         // (no barrier needed here: a warp only rewrites its own sh_w row, and the allocating threads rewrite the offsets
@@ -822,7 +841,6 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
 // =========================================================================================
 __global__ void __launch_bounds__(JG_THREADS, 6) k_filter(Dev d)
 {
-    JG_PDL_ENTER();
     JG_TRACE_SCOPE(JGPU_K_SEED, 0);
     __shared__ LaneSh sh;
     const int L = d.n_lanes, tid = threadIdx.x;
@@ -848,7 +866,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_filter(Dev d)
                 proc = 1;
                 if (m.y < 0)
                     atomicMax(d.state_key + (size_t)lane * d.n_multi + (m.y & JG_STATE_MASK),
-                              state_key_of(sh.epoch[lane], score, (unsigned)e));
+                              state_key_of(d, sh.epoch[lane], score, arrival_id(m.x, 0)));
             } else {
                 d.arr_meta[(size_t)lane * d.cap_arr + e].x = -2;
             }
@@ -892,6 +910,7 @@ __device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, 
     if (PASS == 0) {
         float4 t;
         bool go;
+        int pt = 0;
         if (a.z == 0) {                                       // epsilon input: :533-540
             t = make_float4(s, tok.y, tok.z + w, tok.w);
             go = s > thr_end;
@@ -900,14 +919,20 @@ __device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, 
             const float s2 = s + tee;
             t = make_float4(s2, tok.y + tee, tok.z + w, tok.w);
             go = s2 > (a.w != 0 ? thr_word : thr_end);
+            pt = 1;
         }
         if (go) {
             const int r = out_base + agg_inc(&c->n_arr[out_round]);
             if (r < d.cap_arr) {                              // overflow is flagged by k_boundary
+                int via = b;
+                if (a.x < 0) {
+                    // the same arc fired in an earlier round with the same score (its source state changed owner to
+                    // an arrival that rounds to the same sum): the earlier record stays, this one is dropped
+                    const u64 key = state_key_of(d, epoch, t.x, arrival_id(b, pt));
+                    if (atomicMax(d.state_key + (size_t)lane * d.n_multi + (a.x & JG_STATE_MASK), key) == key) via = -2;
+                }
                 d.arr_tok[(size_t)lane * d.cap_arr + r] = t;
-                d.arr_meta[(size_t)lane * d.cap_arr + r] = make_int4(b, a.x, a.w, 0);
-                if (a.x < 0)
-                    atomicMax(d.state_key + (size_t)lane * d.n_multi + (a.x & JG_STATE_MASK), state_key_of(epoch, t.x, (unsigned)r));
+                d.arr_meta[(size_t)lane * d.cap_arr + r] = make_int4(via, a.x, a.w, pt);
             }
         }
     } else {
@@ -917,15 +942,16 @@ __device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, 
             ++n_entry;
             const size_t cap = (size_t)d.cap;
             float4* tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * (size_t)(d.S - 1) * cap;
-            if ((sm >> JG_SLOT_BITS) == (epoch & 0x7ffu) && (sm & JG_SLOT_MASK) != 0) {
-                tok_nxt[(sm & JG_SLOT_MASK) - 1] = t;         // the instance survived the internal phase: plane 0 = entry token
+            const int slot = slot_lookup(d, sm, epoch);
+            if (slot >= 0) {
+                tok_nxt[slot] = t;                            // the instance survived the internal phase: plane 0 = entry token
             } else {
                 const int pos = agg_inc(&c->n_next);
                 if (pos < d.cap) {                            // overflow is flagged by k_boundary
                     int4* meta_nxt = d.inst_meta + ((size_t)lane * 2 + (flip ^ 1)) * cap;
                     st_stream(meta_nxt + pos, make_int4(b, (a.z - 1) | JG_FRESH, a.x, a.w));
                     tok_nxt[pos] = t;
-                    d.slotmap[(size_t)lane * d.n_arcs + b] = ((epoch & 0x7ffu) << JG_SLOT_BITS) | ((unsigned)pos + 1u);
+                    d.slotmap[(size_t)lane * d.n_arcs + b] = slot_entry(d, epoch, pos);
                 }
             }
         }
@@ -935,7 +961,6 @@ __device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, 
 template <int PASS>
 __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int round)
 {
-    JG_PDL_ENTER();
     JG_TRACE_SCOPE(PASS ? JGPU_K_COMMIT : JGPU_K_EXPAND, round);
     __shared__ LaneSh sh;
     __shared__ int s_off[JG_THREADS + 1];
@@ -969,7 +994,12 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
             tw = (d.word_beam > 0.0f ? (be - d.word_beam) : JG_LZ);
         }
         sh.f0[l] = te; sh.f1[l] = tw;
-                sh.epoch[l] = (c->epoch & ~JG_SH_HAS_FREE) | (c->n_free > 0 ? JG_SH_HAS_FREE : 0u);
+        if (PASS == 1) {                                      // the commit has no use for the two beams: the slots carry the
+            const u64 bf = c->best_final;                     // lane's best-final key, whose record this pass looks up
+            sh.f0[l] = __uint_as_float((unsigned)(bf >> 32));
+            sh.f1[l] = __uint_as_float((unsigned)bf);
+        }
+        sh.epoch[l] = (c->epoch & ~JG_SH_HAS_FREE) | (c->n_free > 0 ? JG_SH_HAS_FREE : 0u);
     }
     const int total_chunks = chunk_scan(sh, L);
     JG_TRACE_AT(0);                                           // setup done
@@ -998,8 +1028,14 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
             JG_TRACE_AT(1);                                   // record loaded
             const int4 st = __ldg(&d.states[q]);
             valid = m.x != -2;
+            if (PASS == 1 && valid && m.x >= 0 && __int_as_float(st.z) > JG_LZ) {
+                // best final token (:513-520): the rounds max-reduced (score + final weight | arrival id); the record
+                // that made the winning proposal is the one whose key it is (arrival ids are unique per state)
+                const u64 bf = ((u64)__float_as_uint(sh.f0[lane]) << 32) | (u64)__float_as_uint(sh.f1[lane]);
+                if (bf != 0 && (((u64)f2o(tok.x + __int_as_float(st.z)) << 32) | (u64)arrival_id(m.x, m.w)) == bf) c->final_rec = (int)r;
+            }
             if (valid && m.y < 0)                             // still the best arrival of q?
-                valid = d.state_key[(size_t)lane * d.n_multi + q] == state_key_of(epoch, tok.x, r);
+                valid = d.state_key[(size_t)lane * d.n_multi + q] == state_key_of(d, epoch, tok.x, arrival_id(m.x, m.w));
             if (valid) {
                 const int n_eps = st.w & 0xffff, n_tee = (unsigned)st.w >> 16;
                 JG_TRACE_AT(2);                               // state row (and key) loaded
@@ -1018,7 +1054,7 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
                         }
                     }
                     const float fw = __int_as_float(st.z);
-                    if (valid && fw > JG_LZ && m.x >= 0) fin = ((u64)f2o(tok.x + fw) << 32) | r;   // :513-520 (not for the seed: trans == NULL)
+                    if (valid && fw > JG_LZ && m.x >= 0) fin = ((u64)f2o(tok.x + fw) << 32) | (u64)arrival_id(m.x, m.w);   // :513-520 (not for the seed: trans == NULL)
                     if (valid) { first = st.x; deg = n_eps + n_tee; }
                 } else {
                     if (d.fuse_exits && m.z != 0 && m.y < 0 && !(m.y & (int)JG_ROUND) && m.x >= 0 && r < (unsigned)sh.i1[lane]) {
@@ -1117,7 +1153,6 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
 // hub-like rows met by the commit: all CTAs of the lane stride over the row.
 __global__ void __launch_bounds__(JG_THREADS) k_commit_huge(Dev d)
 {
-    JG_PDL_ENTER();
     JG_TRACE_SCOPE(JGPU_K_EXPAND_HUGE, 0);
     const int lane = blockIdx.y;
     LaneCtl* c = d.ctl + lane;
@@ -1223,8 +1258,8 @@ __global__ void __launch_bounds__(JG_THREADS) k_gc_mark(Dev d)
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const u64 key = c->best_final;                        // resolved by the next k_boundary
-        if (key) gc_mark_chain(paths, __float_as_int(d.arr_tok[(size_t)lane * d.cap_arr + (unsigned)key].w), gen);
+        // the pending best final arrival (resolved by the next k_boundary)
+        if (c->best_final && c->final_rec >= 0) gc_mark_chain(paths, __float_as_int(d.arr_tok[(size_t)lane * d.cap_arr + c->final_rec].w), gen);
         if (c->final_valid) gc_mark_chain(paths, __float_as_int(c->final_tok.w), gen);
     }
 }

@@ -342,6 +342,22 @@ def tee_eps_net(n_words: int = 4, sp_label: Optional[int] = None) -> Net:
     return _finish_net(src, dst, il, ol, w, {0: 0.5}, sp + 1, n_words + 1)
 
 
+def ties_net() -> Net:
+    """Exact score ties by construction (the tie-break test): a two-state loop whose weights are multiples of
+    0.5, with homophones — words 0, 1 and 6 share HMM 0, words 2 and 3 share HMM 1 — and two routes of equal
+    total weight to the same pronunciation: 0 -h0:W0/1-> 0 directly, or 0 -eps/0.5-> 1 -h0:W6/0.5-> 0.  Tokens on
+    homophone arcs carry bit-identical scores, leave their models in the same frame and meet at state 0."""
+    src = [0] * 7 + [1]
+    dst = [0] * 6 + [1, 0]
+    il = [1, 1, 2, 2, 3, 4, 0, 1]
+    ol = [1, 2, 3, 4, 5, 6, 0, 7]
+    w = [1.0] * 6 + [0.5, 0.5]
+    return _finish_net(src, dst, il, ol, w, {0: 0.0}, 5, 8)
+
+
+TIE_CLASSES = {1: 0, 2: 0, 7: 0, 3: 1, 4: 1, 5: 2, 6: 3}     # output label -> homophone class of ties_net()
+
+
 def bigram_net(n_words: int, n_hmm: int, *, k_bigram: int = 8, seed: int = 0,
                pron_len: Tuple[int, int] = (3, 8), sp_label: Optional[int] = None,
                positive_weights: bool = True) -> Net:
@@ -559,6 +575,7 @@ def named_config(name: str):
     """Returns (models, net, tee_hmms, decoder_kwargs) for a named, seeded configuration.
 
     c1      BASELINE configs[0]: 10-word digit loop, 3-state monophones, 1-mix
+    ties    homophones and equal-weight routes: exact score ties between different arrivals at one state
     tee     tee model + eps arcs with word labels + final weight
     mixed   4/5/6-state HMMs with skips, ragged mixtures, optional-silence tee, all four beams + histogram
     c2mini  small bigram network with tied states
@@ -575,6 +592,8 @@ def named_config(name: str):
         net = digit_loop_net(4)
         net.olab[:] = 0
         return make_models(4, 1, sigma_mu=2.0, seed=5), net, (), dict(main_beam=200.0)
+    if name == "ties":                          # exact ties between different arrivals (homophones, equal-weight routes)
+        return make_models(4, 2, sigma_mu=1.5, seed=9), ties_net(), (), dict(main_beam=200.0)
     if name == "tee":
         return (make_models(4, 2, sigma_mu=2.0, seed=2, with_tee=True), tee_eps_net(4, sp_label=5), (4,),
                 dict(main_beam=200.0))

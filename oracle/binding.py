@@ -114,6 +114,12 @@ class OracleRef:
             self.lib.oref_destroy(self.h)
             self.h = None
 
+    def set_decoder(self, *, main_beam: float, start_beam: float = 0.0, end_beam: float = 0.0,
+                    word_beam: float = 0.0, max_hyps: int = 0) -> None:
+        """A new WFSTDecoderLite with other pruning settings on the same network and models."""
+        self.lib.oref_set_decoder.argtypes = [C.c_void_p] + [C.c_float] * 4 + [C.c_int]
+        self.lib.oref_set_decoder(self.h, start_beam, main_beam, end_beam, word_beam, max_hyps)
+
     def decode(self, feats: np.ndarray, counters: bool = False, max_words: int = 4096) -> DecodeResult:
         feats = np.ascontiguousarray(feats, dtype=np.float32)
         T = feats.shape[0]

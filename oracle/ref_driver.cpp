@@ -140,6 +140,19 @@ void oref_model_dims(void* hv, int* dims)
     dims[4] = h->models->maxStates(); dims[5] = h->models->maxComps();
 }
 
+/* A new decoder with other pruning settings on the SAME network and models (loading a 6M-arc text network takes
+ * longer than decoding the test utterances).  The reference leaves its instances hooked to the network's
+ * transitions when a decoder dies (WFSTTransition::hook, src/WFSTNetwork.h:50-51; attachNetInst asserts the hook is
+ * NULL, src/WFSTDecoderLite.cpp:752), so the hooks are cleared first. */
+void oref_set_decoder(void* hv, float startBeam, float mainBeam, float endBeam, float wordBeam, int maxHyps)
+{
+    Handle* h = (Handle*)hv;
+    delete h->dec;
+    const int n = h->net->getNumTransitions();
+    for (int i = 0; i < n; ++i) h->net->getOneTransition(i)->hook = NULL;
+    h->dec = new RefDecoder(h->net, h->models, startBeam, mainBeam, endBeam, wordBeam, maxHyps);
+}
+
 void oref_destroy(void* hv)
 {
     Handle* h = (Handle*)hv;

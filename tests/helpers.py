@@ -9,7 +9,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["c1", "c1h", "tee", "mixed", "c2mini", "nolabel"]
+GOLDEN_CASES = ["c1", "c1h", "tee", "mixed", "c2mini", "nolabel", "ties"]
 
 
 def bits(a) -> np.ndarray:

@@ -27,12 +27,16 @@ CASES = {                                           # name -> (config, n_utts, m
     "mixed": ("mixed", 3, 150, False),
     "c2mini": ("c2mini", 2, 120, True),
     "nolabel": ("nolabel", 1, 40, False),
+    "ties": ("ties", 3, 120, False),
 }
 
 
 def main() -> None:
     build(ref=True, port=False)
+    only = set(sys.argv[1:])                        # `python tools/make_golden.py ties` regenerates one fixture
     for name, (cfg, n_utts, frames, trunc) in CASES.items():
+        if only and name not in only:
+            continue
         m, net, tee, kw = synth.named_config(cfg)
         d = os.path.join(GOLD, name)
         files = synth.make_fixture(name, d, m, net)
