@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <queue>
 #include <string>
@@ -77,6 +78,7 @@ struct jgpu_handle {
     int sched_chunk = 2048;
     int4* d_sched = nullptr;
     int* d_rows = nullptr;
+    std::vector<int> rows_host;          // staging of the feature-row table of a chunk
     // features / scores
     float* d_feats = nullptr;
     size_t feats_cap = 0;   // rows
@@ -792,92 +794,171 @@ int launch_steps_graph(jgpu_handle* h, int n)
     return JGPU_OK;
 }
 
-// Runs `n_steps` schedule rows (plus the trailing close-only row n_steps).
-// sched: (n_steps + 1) * n_lanes entries {feature row, -, flags, utt}; d_x: feature base.
-int run_schedule(jgpu_handle* h, const std::vector<int4>& sched, int n_steps, const float* d_x)
+// Enqueues one chunk of the lock-step schedule: `ns` frame / seed steps of all lanes (rows {feature row, -, flags,
+// result slot}, at most sched_chunk of them) and, when `last`, the trailing close-only row that runs the pending
+// finishes.  d_x: feature base.  `chunk` is modified (score-ring rows are filled in).
+int submit_chunk(jgpu_handle* h, std::vector<int4>& chunk, int ns, bool last, const float* d_x)
 {
     const Dev& d = h->d;
-    const int L = d.n_lanes, CH = h->sched_chunk, FB = h->FB;
+    const int L = d.n_lanes, FB = h->FB;
+    if (ns + (last ? 1 : 0) == 0) return JGPU_OK;
+    std::vector<int>& rows = h->rows_host;
+    rows.resize((size_t)std::max(ns, 1) * L);
+    for (int i = 0; i < ns; ++i)
+        for (int l = 0; l < L; ++l) {
+            int4& e = chunk[(size_t)i * L + l];
+            e.y = (((i / FB) & 1) * FB + (i % FB)) * L + l;   // score-ring row of (step, lane): two halves
+            rows[(size_t)i * L + l] = ((e.z & 3) == JG_MODE_FRAME) ? e.x : -1;
+        }
+    CK(cudaMemcpyAsync(h->d_sched, chunk.data(), (size_t)(ns + (last ? 1 : 0)) * L * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d.lane_step, 0, (size_t)L * sizeof(int), h->stream));
+    if (ns) CK(cudaMemcpyAsync(h->d_rows, rows.data(), (size_t)ns * L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    // the acoustic scores of frame block b+1 are enqueued ahead of the search of block b (two halves of the ring)
+    auto issue_gmm = [&](int b) -> int {
+        const int b0 = b * FB, nb = std::min(FB, ns - b0), half = b & 1;
+        return launch_gmm(h, d_x, h->d_rows + (size_t)b0 * L, nb * L, h->d_scores, (long long)half * FB * L);
+    };
+    const int n_blocks = (ns + FB - 1) / FB;
+    if (n_blocks > 0) { int rc = issue_gmm(0); if (rc) return rc; }
+    for (int b = 0; b < n_blocks; ++b) {
+        int rc;
+        if (b + 1 < n_blocks && (rc = issue_gmm(b + 1))) return rc;
+        const int b0 = b * FB, nb = std::min(FB, ns - b0);
+        // a lane whose epoch stamp wraps inside this block gets its stamped tables wiped right before that
+        // step (every epoch_wrap + 1 steps: 2048 on a 2M-arc network); such a block is launched step by step
+        bool wipe_in_block = false;
+        {
+            std::vector<unsigned> ep(h->host_epoch);
+            for (int i = b0; i < b0 + nb && !wipe_in_block; ++i)
+                for (int l = 0; l < L; ++l)
+                    if ((chunk[(size_t)i * L + l].z & 3) != JG_MODE_IDLE && ((++ep[l]) & h->epoch_wrap) == 0u) { wipe_in_block = true; break; }
+        }
+        const bool graphs = h->use_graphs && !h->prof_on && !JG_TRACING(h);
+        if (graphs && nb == FB && !wipe_in_block) {
+            for (int i = b0; i < b0 + nb; ++i)
+                for (int l = 0; l < L; ++l)
+                    if ((chunk[(size_t)i * L + l].z & 3) != JG_MODE_IDLE) ++h->host_epoch[l];
+            if ((rc = launch_steps_graph(h, nb))) return rc;
+        } else {
+            for (int i = b0; i < b0 + nb; ++i) {
+                for (int l = 0; l < L; ++l) {
+                    if ((chunk[(size_t)i * L + l].z & 3) == JG_MODE_IDLE) continue;
+                    if (((++h->host_epoch[l]) & h->epoch_wrap) == 0u) {
+                        CK(cudaMemsetAsync(h->d.state_key + (size_t)l * d.n_multi, 0, (size_t)d.n_multi * sizeof(u64), h->stream));
+                        CK(cudaMemsetAsync(h->d.slotmap + (size_t)l * d.n_arcs, 0, (size_t)d.n_arcs * sizeof(unsigned), h->stream));
+                    }
+                }
+                if ((rc = graphs ? launch_steps_graph(h, 1) : launch_step(h))) return rc;
+            }
+        }
+        // word-boundary arena: mark + sweep between two frame steps, every gc_period steps (lanes whose arena
+        // is less than half full skip it on the device)
+        h->steps_since_gc += nb;
+        if (h->gc_period > 0 && h->steps_since_gc >= h->gc_period) {
+            h->steps_since_gc = 0;
+            const dim3 grid_gc(std::max(2, std::min(32, 1184 / L)), L);
+            k_gc_decide<<<(L + 127) / 128, 128, 0, h->stream>>>(d);
+            k_gc_mark<<<grid_gc, JG_THREADS, 0, h->stream>>>(d);
+            k_gc_sweep<<<grid_gc, JG_THREADS, 0, h->stream>>>(d);
+            h->launches += 3;
+            CK(cudaGetLastError());
+        }
+    }
+    if (last) {
+        h->prof_begin(JGPU_K_BOUNDARY);
+        k_boundary<<<L, 32, 0, h->stream>>>(d);          // close the last step, run pending finishes
+        h->prof_end();
+        ++h->launches;
+        CK(cudaGetLastError());
+    }
+    // (the host vectors may be reused at once: pageable copies are staged before cudaMemcpyAsync returns)
+    return JGPU_OK;
+}
+
+// Runs a prebuilt schedule of `n_steps` rows (plus the trailing close-only row n_steps): the streaming interface.
+int run_schedule(jgpu_handle* h, const std::vector<int4>& sched, int n_steps, const float* d_x)
+{
+    const int L = h->d.n_lanes, CH = h->sched_chunk;
     std::vector<int4> chunk;
-    std::vector<int> rows;
     for (int s0 = 0; s0 <= n_steps; s0 += CH) {
         const int ns = std::min(CH, n_steps - s0);          // frame/seed steps in this chunk
         const bool last = s0 + ns == n_steps;
-        const int n_entries = ns + (last ? 1 : 0);
-        if (n_entries == 0) break;
-        chunk.assign(sched.begin() + (size_t)s0 * L, sched.begin() + (size_t)(s0 + n_entries) * L);
-        rows.resize((size_t)std::max(ns, 1) * L);
-        for (int i = 0; i < ns; ++i)
-            for (int l = 0; l < L; ++l) {
-                int4& e = chunk[(size_t)i * L + l];
-                e.y = (((i / FB) & 1) * FB + (i % FB)) * L + l;   // score-ring row of (step, lane): two halves
-                rows[(size_t)i * L + l] = ((e.z & 3) == JG_MODE_FRAME) ? e.x : -1;
-            }
-        CK(cudaMemcpyAsync(h->d_sched, chunk.data(), chunk.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemsetAsync(h->d.lane_step, 0, (size_t)L * sizeof(int), h->stream));
-        if (ns) CK(cudaMemcpyAsync(h->d_rows, rows.data(), (size_t)ns * L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        // the acoustic scores of frame block b+1 are enqueued ahead of the search of block b (two halves of the ring)
-        auto issue_gmm = [&](int b) -> int {
-            const int b0 = b * FB, nb = std::min(FB, ns - b0), half = b & 1;
-            return launch_gmm(h, d_x, h->d_rows + (size_t)b0 * L, nb * L, h->d_scores, (long long)half * FB * L);
-        };
-        const int n_blocks = (ns + FB - 1) / FB;
-        if (n_blocks > 0) { int rc = issue_gmm(0); if (rc) return rc; }
-        for (int b = 0; b < n_blocks; ++b) {
-            int rc;
-            if (b + 1 < n_blocks && (rc = issue_gmm(b + 1))) return rc;
-            const int b0 = b * FB, nb = std::min(FB, ns - b0);
-            // a lane whose epoch stamp wraps inside this block gets its stamped tables wiped right before that
-            // step (every epoch_wrap + 1 steps: 2048 on a 2M-arc network); such a block is launched step by step
-            bool wipe_in_block = false;
-            {
-                std::vector<unsigned> ep(h->host_epoch);
-                for (int i = b0; i < b0 + nb && !wipe_in_block; ++i)
-                    for (int l = 0; l < L; ++l)
-                        if ((chunk[(size_t)i * L + l].z & 3) != JG_MODE_IDLE && ((++ep[l]) & h->epoch_wrap) == 0u) { wipe_in_block = true; break; }
-            }
-            const bool graphs = h->use_graphs && !h->prof_on && !JG_TRACING(h);
-            if (graphs && nb == FB && !wipe_in_block) {
-                for (int i = b0; i < b0 + nb; ++i)
-                    for (int l = 0; l < L; ++l)
-                        if ((chunk[(size_t)i * L + l].z & 3) != JG_MODE_IDLE) ++h->host_epoch[l];
-                if ((rc = launch_steps_graph(h, nb))) return rc;
-            } else {
-                for (int i = b0; i < b0 + nb; ++i) {
-                    for (int l = 0; l < L; ++l) {
-                        if ((chunk[(size_t)i * L + l].z & 3) == JG_MODE_IDLE) continue;
-                        if (((++h->host_epoch[l]) & h->epoch_wrap) == 0u) {
-                            CK(cudaMemsetAsync(h->d.state_key + (size_t)l * d.n_multi, 0, (size_t)d.n_multi * sizeof(u64), h->stream));
-                            CK(cudaMemsetAsync(h->d.slotmap + (size_t)l * d.n_arcs, 0, (size_t)d.n_arcs * sizeof(unsigned), h->stream));
-                        }
-                    }
-                    if ((rc = graphs ? launch_steps_graph(h, 1) : launch_step(h))) return rc;
-                }
-            }
-            // word-boundary arena: mark + sweep between two frame steps, every gc_period steps (lanes whose arena
-            // is less than half full skip it on the device)
-            h->steps_since_gc += nb;
-            if (h->gc_period > 0 && h->steps_since_gc >= h->gc_period) {
-                h->steps_since_gc = 0;
-                const dim3 grid_gc(std::max(2, std::min(32, 1184 / L)), L);
-                k_gc_decide<<<(L + 127) / 128, 128, 0, h->stream>>>(d);
-                k_gc_mark<<<grid_gc, JG_THREADS, 0, h->stream>>>(d);
-                k_gc_sweep<<<grid_gc, JG_THREADS, 0, h->stream>>>(d);
-                h->launches += 3;
-                CK(cudaGetLastError());
-            }
-        }
-        if (last) {
-            h->prof_begin(JGPU_K_BOUNDARY);
-            k_boundary<<<L, 32, 0, h->stream>>>(d);          // close the last step, run pending finishes
-            h->prof_end();
-            ++h->launches;
-            CK(cudaGetLastError());
-            break;
-        }
-        // the host vectors are reused next iteration: pageable copies are staged before return
+        chunk.assign(sched.begin() + (size_t)s0 * L, sched.begin() + (size_t)(s0 + ns + (last ? 1 : 0)) * L);
+        int rc = submit_chunk(h, chunk, ns, last, d_x);
+        if (rc) return rc;
+        if (last) break;
     }
     return JGPU_OK;
+}
+
+// Where the scheduler gets its utterances from: the caller's list in a fixed order (one rank, or a second pass),
+// or a queue shared by the ranks of a node (jgpu_decode_queue: whole-utterance work stealing).
+struct UttSource {
+    virtual ~UttSource() {}
+    virtual int next() = 0;                               // index into the caller's arrays, -1 when exhausted
+    virtual bool shared() const { return false; }
+};
+struct ListSource : UttSource {
+    const std::vector<int>& ids;
+    size_t pos = 0;
+    explicit ListSource(const std::vector<int>& v) : ids(v) {}
+    int next() override { return pos < ids.size() ? ids[pos++] : -1; }
+};
+
+// The lock-step scheduler.  Lanes are refilled as their utterances end: a free lane takes the next utterance of the
+// source — with the list sorted longest first that is LPT assignment; with a shared queue it is work stealing, and
+// then the schedule is built in short chunks that stay at most one chunk ahead of the device, so that a claim
+// reflects how far THIS GPU really is.  slot_utt[k] = utterance decoded into result slot k.
+int run_stream(jgpu_handle* h, UttSource* src, const float* d_feats, const int64_t* row_offset, const int32_t* n_frames,
+               std::vector<int>* slot_utt, const std::function<int(int)>& on_claim)
+{
+    const int L = h->d.n_lanes;
+    const int CH = src->shared() ? 4 * h->FB : h->sched_chunk;
+    std::vector<int> cur(L, -1), pos(L, 0), slot(L, -1);
+    std::vector<char> fin(L, 0);
+    bool exhausted = false;
+    std::vector<int4> chunk;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (src->shared())
+        for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    int rc = JGPU_OK;
+    for (int k = 0; !rc; ++k) {
+        // (shared queue) chunk k-2 must be done before anything is claimed for chunk k: chunk k-1 keeps the GPU busy
+        if (src->shared() && k >= 2 && cudaEventSynchronize(ev[k & 1]) != cudaSuccess) { rc = fail(JGPU_E_CUDA, "queue throttle: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        chunk.assign((size_t)(CH + 1) * L, make_int4(-1, 0, JG_MODE_IDLE, -1));
+        int ns = 0;
+        bool done = false;
+        for (; ns < CH && !rc; ++ns) {
+            bool any = false;
+            for (int l = 0; l < L && !rc; ++l) {
+                int4& e = chunk[(size_t)ns * L + l];
+                if (fin[l]) { e.z |= JG_FLAG_FINISH; fin[l] = 0; }   // row after the last frame of the lane's previous utterance
+                if (cur[l] < 0 && !exhausted) {
+                    const int u = src->next();
+                    if (u < 0) exhausted = true;
+                    else {
+                        cur[l] = u; pos[l] = -1;
+                        slot[l] = (int)slot_utt->size();
+                        slot_utt->push_back(u);
+                        if (on_claim) rc = on_claim(u);
+                    }
+                }
+                if (cur[l] < 0) continue;
+                const int u = cur[l];
+                any = true;
+                if (pos[l] < 0) { e.z |= JG_MODE_SEED; e.w = slot[l]; pos[l] = 0; }
+                else { e.x = (int)(row_offset[u] + pos[l]); e.z |= JG_MODE_FRAME; e.w = slot[l]; ++pos[l]; }
+                if (pos[l] >= n_frames[u]) { fin[l] = 1; cur[l] = -1; }
+            }
+            if (!any) { done = true; break; }              // this row is the close-only row: pending finishes only
+        }
+        if (rc) break;
+        rc = submit_chunk(h, chunk, ns, done, d_feats);
+        if (!rc && src->shared()) cudaEventRecord(ev[k & 1], h->stream);
+        if (done) break;
+    }
+    for (int i = 0; i < 2; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+    return rc;
 }
 
 void fill_result(const ResHdr& hdr, const JgpuWord* pool, JgpuResult* out)
@@ -906,50 +987,16 @@ int fetch_result(jgpu_handle* h, int slot, JgpuResult* out)
     return JGPU_OK;
 }
 
-// One pass over the utterances `ids` (indices into the caller's arrays) with the current view: LPT assignment to
-// lanes, lock-step schedule, results into out[ids[k]].  err[k] = the utterance's device error bits, need_words[k] =
-// the words its best path has.
-int decode_pass(jgpu_handle* h, const float* d_feats, const int64_t* row_offset, const int32_t* n_frames,
-                const std::vector<int>& ids, JgpuResult* out, std::vector<int>* err, std::vector<int>* need_words)
+// One pass with the current view: the scheduler takes utterances from `src` (result slot k <- utterance
+// slot_utt[k]), results go into out[utterance].  err[k] = device error bits of slot k, need_words[k] = the words
+// its best path has.
+int decode_pass(jgpu_handle* h, UttSource* src, const float* d_feats, const int64_t* row_offset, const int32_t* n_frames,
+                JgpuResult* out, std::vector<int>* slot_utt, std::vector<int>* err, std::vector<int>* need_words,
+                const std::function<int(int)>& on_claim)
 {
     Dev& d = h->d;
-    const int L = d.n_lanes, n_utts = (int)ids.size();
-    // LPT assignment of utterances to lanes (longest first, to the least loaded lane)
-    std::vector<int> order(n_utts);
-    for (int i = 0; i < n_utts; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n_frames[ids[a]] > n_frames[ids[b]]; });
-    typedef std::pair<long long, int> LoadLane;
-    std::priority_queue<LoadLane, std::vector<LoadLane>, std::greater<LoadLane>> pq;
-    for (int l = 0; l < L; ++l) pq.push(LoadLane(0, l));
-    std::vector<std::vector<int>> per_lane(L);
-    long long n_steps = 0;
-    for (int k : order) {
-        LoadLane t = pq.top();
-        pq.pop();
-        per_lane[t.second].push_back(k);
-        t.first += (long long)n_frames[ids[k]] + 1;         // +1: the seeding step
-        n_steps = std::max(n_steps, t.first);
-        pq.push(t);
-    }
-    if (n_steps > (1ll << 30)) return fail(JGPU_E_ARG, "schedule too long");
-    std::vector<int4> sched((size_t)(n_steps + 1) * L, make_int4(-1, 0, JG_MODE_IDLE, -1));
-    for (int l = 0; l < L; ++l) {
-        long long s = 0;
-        for (int k : per_lane[l]) {
-            const int u = ids[k];
-            int4& e = sched[(size_t)s * L + l];
-            e.z |= JG_MODE_SEED;                            // keeps a FINISH flag set by the previous utterance
-            e.w = k;                                        // result slot = position in `ids`
-            ++s;
-            for (int t = 0; t < n_frames[u]; ++t, ++s) {
-                int4& f = sched[(size_t)s * L + l];
-                f.x = (int)(row_offset[u] + t);
-                f.z = JG_MODE_FRAME;
-                f.w = k;
-            }
-            sched[(size_t)s * L + l].z |= JG_FLAG_FINISH;   // row after the last frame
-        }
-    }
+    const int L = d.n_lanes;
+    slot_utt->clear();
     k_reset_batch_stats<<<(L + 127) / 128, 128, 0, h->stream>>>(d);
     ++h->launches;
     CK(cudaMemsetAsync(d.res_used, 0, sizeof(int), h->stream));
@@ -962,9 +1009,11 @@ int decode_pass(jgpu_handle* h, const float* d_feats, const int64_t* row_offset,
         cudaMemcpyToSymbolAsync(g_trace_on, &off, sizeof(int), 0, cudaMemcpyHostToDevice, h->stream);
     }
 #endif
-    int rc = run_schedule(h, sched, (int)n_steps, d_feats);
+    int rc = run_stream(h, src, d_feats, row_offset, n_frames, slot_utt, on_claim);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
+    const int n_utts = (int)slot_utt->size();
+    const std::vector<int>& ids = *slot_utt;
 #ifdef JG_TRACE
     if (h->d_trace && !h->prof_on) {                   // (the per-kernel event timing widens the launch gaps)
         unsigned n = 0;

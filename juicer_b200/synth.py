@@ -408,14 +408,20 @@ def bigram_net(n_words: int, n_hmm: int, *, k_bigram: int = 8, seed: int = 0,
 
 
 def trigram_net(n_words: int, n_hmm: int, *, k_bigram: int = 40, n_trigram: int = 60000,
-                k_trigram: int = 8, seed: int = 0, pron_len: Tuple[int, int] = (3, 8)) -> Net:
+                k_trigram: int = 8, seed: int = 0, pron_len: Tuple[int, int] = (3, 8),
+                prefix_tree: bool = False) -> Net:
     """C3/C5-shaped network, built vectorised:
       hub (state 0)        --first phone of w / out=w / unigram weight--> shared tail of w --> h_w
       bigram state h_v     --k_bigram first arcs into shared tails + eps back-off to hub
       trigram state t_(u,v): reached from h_u through a DEDICATED chain for v;
                              k_trigram first arcs into shared tails + eps back-off to h_v
     Shared tails make arcs >> states with a heavy-tailed out-degree (hub = V arcs); the
-    eps back-off chain tri -> bi -> uni has depth 2.  All history states are final."""
+    eps back-off chain tri -> bi -> uni has depth 2.  All history states are final.
+    prefix_tree=True replaces the hub's one-arc-per-word row by a PREFIX-TREE lexicon: words
+    sharing their first phones share arcs, the hub's out-degree is the number of distinct first phones, the
+    word label sits on the first arc that is unique to the word, and the unigram weights are pushed towards
+    the root (an arc into a tree node carries min-cost(below it) - min-cost(below its parent)), the way a
+    determinised and weight-pushed C.L.G looks.  After its unique arc a word runs into its shared tail."""
     rng = np.random.default_rng(seed)
     V = n_words
     plen = rng.integers(pron_len[0], pron_len[1] + 1, size=V)
@@ -432,6 +438,7 @@ def trigram_net(n_words: int, n_hmm: int, *, k_bigram: int = 40, n_trigram: int 
     ded_len = plen[tri_v] - 1                        # dedicated chain inner states for v from h_u
     ded0 = tri0 + n_trigram
     ded_base = ded0 + np.concatenate([[0], np.cumsum(ded_len)])[:-1]
+    tree0 = int(ded0 + ded_len.sum())                # shared prefix-tree nodes (prefix_tree=True)
 
     S: List[np.ndarray] = []; T: List[np.ndarray] = []; I: List[np.ndarray] = []
     O: List[np.ndarray] = []; W: List[np.ndarray] = []
@@ -454,7 +461,53 @@ def trigram_net(n_words: int, n_hmm: int, *, k_bigram: int = 40, n_trigram: int 
     t_ = np.where(last, hist0 + w_rep, s_ + 1)
     add(s_, t_, phones[pron_off[w_rep] + pos + 1], np.zeros_like(s_), np.zeros(len(s_)))
     # hub
-    first_arcs(np.zeros(V, dtype=np.int64), np.arange(V), -np.log(rng.dirichlet(np.full(V, 2.0))))
+    uni = -np.log(rng.dirichlet(np.full(V, 2.0)))
+    n_tree = 0
+    if not prefix_tree:
+        first_arcs(np.zeros(V, dtype=np.int64), np.arange(V), uni)
+    else:
+        # trie over the pronunciations; node ids are handed out after every other state (see tree0 below)
+        kids: List[Dict[int, int]] = [{}]              # node -> {phone: child node}; node 0 = the hub
+        cost = [math.inf]                              # min unigram cost of the words below the node
+        cnt = [0]                                      # words below the node
+        for w_ in range(V):
+            node = 0
+            cost[0] = min(cost[0], float(uni[w_])); cnt[0] += 1
+            for i in range(int(plen[w_])):
+                ph = int(phones[pron_off[w_] + i])
+                nxt_ = kids[node].get(ph)
+                if nxt_ is None:
+                    nxt_ = len(kids)
+                    kids[node][ph] = nxt_
+                    kids.append({}); cost.append(math.inf); cnt.append(0)
+                node = nxt_
+                cost[node] = min(cost[node], float(uni[w_])); cnt[node] += 1
+        cost[0] = 0.0                                  # nothing is pushed out of the hub
+        t_src: List[int] = []; t_dst: List[int] = []; t_il: List[int] = []; t_ol: List[int] = []; t_w: List[float] = []
+        tree_id: Dict[int, int] = {0: 0}               # trie node -> network state (shared nodes only)
+        pending_nodes: List[int] = []
+        for w_ in range(V):
+            node = 0
+            n_ph = int(plen[w_])
+            for i in range(n_ph):
+                ph = int(phones[pron_off[w_] + i])
+                child = kids[node][ph]
+                if cnt[child] > 1 and i < n_ph - 1:    # still shared: a tree arc, written once (by its first word)
+                    if child not in tree_id:
+                        tree_id[child] = -(len(pending_nodes) + 1)     # numbered below
+                        pending_nodes.append(child)
+                        t_src.append(tree_id[node]); t_dst.append(tree_id[child]); t_il.append(ph); t_ol.append(0)
+                        t_w.append(cost[child] - cost[node])
+                    node = child
+                    continue
+                # first arc unique to the word (or its last phone: homophones / prefixes of other words keep their
+                # own arc there): word label + what is left of the unigram cost, then into the shared tail
+                d_ = i + 1
+                to = int(tail_base[w_] + d_ - 1) if d_ < n_ph else int(hist0 + w_)
+                t_src.append(tree_id[node]); t_dst.append(to); t_il.append(ph); t_ol.append(w_ + 1)
+                t_w.append(float(uni[w_]) - cost[node])
+                break
+        n_tree = len(pending_nodes)
     # bigram states
     kb = min(k_bigram, V)
     bw = rng.integers(0, V, size=(V, kb))
@@ -476,6 +529,10 @@ def trigram_net(n_words: int, n_hmm: int, *, k_bigram: int = 40, n_trigram: int 
     tw = rng.integers(0, V, size=(n_trigram, kt))
     first_arcs(np.repeat(tri0 + k_idx, kt), tw.ravel(), rng.gamma(3.0, 1.0, size=n_trigram * kt))
     add(tri0 + k_idx, hist0 + tri_v, np.zeros(n_trigram), np.zeros(n_trigram), rng.gamma(2.0, 1.0, size=n_trigram))
+
+    if prefix_tree:
+        fix = lambda v: np.where(np.asarray(v) < 0, tree0 - 1 - np.asarray(v), np.asarray(v))   # noqa: E731  (-k-1 -> tree0 + k)
+        add(fix(t_src), fix(t_dst), t_il, t_ol, t_w)
 
     finals: Dict[int, float] = {0: 0.0}
     fw = rng.uniform(0.0, 1.0, size=V + n_trigram)
@@ -582,6 +639,7 @@ def named_config(name: str):
     c2      BASELINE configs[1]: 1k-vocab bigram, 2000 triphone HMMs x 16-mix, ~42k states
     c3      BASELINE configs[2]: 20k-vocab trigram-shaped network, ~440k states / ~1.8M arcs, beam 250
     c3s     c3 topology at 1/8 scale (parity at sizes the CPU oracle finishes in seconds)
+    c3p     c3 with a prefix-tree lexicon at the hub (shared first phones, pushed unigram weights); c3ps = 1/8 scale
     c5      BASELINE configs[4]: 64k-vocab trigram-shaped network, ~1.45M states / ~5.9M arcs (beam sweeps)
     """
     if name == "c1":
@@ -611,6 +669,14 @@ def named_config(name: str):
         return (make_models(4000, 16, sigma_mu=1.3, seed=21, n_gmm_pool=6000),
                 trigram_net(20000, 4000, k_bigram=40, n_trigram=60000, k_trigram=8, seed=22), (),
                 dict(main_beam=250.0))
+    if name == "c3p":                           # c3 with a prefix-tree lexicon at the hub
+        return (make_models(4000, 16, sigma_mu=1.3, seed=21, n_gmm_pool=6000),
+                trigram_net(20000, 4000, k_bigram=40, n_trigram=60000, k_trigram=8, seed=22, prefix_tree=True), (),
+                dict(main_beam=250.0))
+    if name == "c3ps":                          # the same at 1/8 scale (parity tests)
+        return (make_models(600, 8, sigma_mu=1.0, seed=23, n_gmm_pool=900),
+                trigram_net(2500, 600, k_bigram=20, n_trigram=6000, k_trigram=6, seed=24, prefix_tree=True), (),
+                dict(main_beam=220.0))
     if name == "c5":                            # BASELINE configs[4]: 64k-vocab trigram, ~1.45M states / ~5.9M arcs;
         #                                             the beam and histogram settings are swept by the caller
         return (make_models(4000, 16, sigma_mu=1.3, seed=21, n_gmm_pool=6000),

@@ -37,8 +37,8 @@ def test_overflowing_lane_is_decoded_again_with_a_larger_arena(oracle_port_lib, 
             g.check(u % 2, r, what=f"second pass, call {rep}")
     st = dec.stats(-1)
     assert st["n_frames"] == sum(x.shape[0] for x in feats)       # every utterance counted once
-    one = dec.decode(g.feats(1)[:20])                      # the streaming interface still sees the base view
-    assert one.status >= -2
+    one = dec.decode(g.feats(1)[:20])                      # the streaming interface still sees the (too small) base view
+    assert one.status <= -10 and ((-(one.status + 13)) >> 8) & 1
     dec.close()
 
 

@@ -293,12 +293,14 @@ def test_c2_batch_properties(c2_setup):
     d8.close(); d3.close()
 
 
-def test_c3_scaled_trigram_matches_oracle(tmp_path, port_lib):
+@pytest.mark.parametrize("name", ["c3s", "c3ps"])
+def test_c3_scaled_trigram_matches_oracle(name, tmp_path, port_lib):
     """c3 topology (hub + shared tails + bigram/trigram back-off, hub out-degree = vocabulary)
-    at 1/8 scale: exercises huge-state expansion and two-level epsilon back-off."""
+    at 1/8 scale: exercises huge-state expansion and two-level epsilon back-off.  c3ps = the same with a
+    prefix-tree lexicon at the hub (word labels and pushed unigram weights inside the tree)."""
     from oracle.binding import OraclePort
-    m, net, tee, kw = synth.named_config("c3s")
-    files = synth.make_fixture("c3s", str(tmp_path), m, net)
+    m, net, tee, kw = synth.named_config(name)
+    files = synth.make_fixture(name, str(tmp_path), m, net)
     tabs, netl, models = flat_tables_from_files(files)
     p = OraclePort(tabs, _abi.make_cfg(**kw))
     dec = make_decoder(netl, models, kw, n_lanes=2, frame_stats=True)
@@ -307,7 +309,7 @@ def test_c3_scaled_trigram_matches_oracle(tmp_path, port_lib):
     for u in range(2):
         x, words = ps.sample(150, rng)
         want, got = p.decode(x, counters=True), dec.decode(x, lane=u)
-        same_result(want, got, f"c3s/utt{u}")
+        same_result(want, got, f"{name}/utt{u}")
         cnt, best = dec.frame_stats(u)
         assert np.array_equal(want.frame_cnt[:, [0, 1, 2, 4]], cnt)
         assert np.array_equal(bits(want.frame_best), bits(best))
