@@ -191,6 +191,38 @@ int jgpu_decode_batch(jgpu_handle* h, const float* const* feats, const int32_t* 
 int jgpu_decode_batch_device(jgpu_handle* h, const float* d_feats, const int64_t* row_offset,
                              const int32_t* n_frames, int32_t n_utts, JgpuResult* out);
 
+/* ---- whole-utterance work stealing across the GPUs of one node (BASELINE configs[3]) ----------------
+ * The reference decodes a file list one utterance after the other (DecoderBatchTest::run,
+ * src/DecoderBatchTest.cpp:690-777); here one process per GPU decodes the SAME list, and a rank whose lanes
+ * run dry takes the next utterance of the list from a counter shared through POSIX shared memory (an
+ * atomic fetch-add per claim; no collective on the data path).
+ *   jgpu_queue_open   : `create` != 0 on ONE rank (creates the segment, counter = 0); the others open it
+ *                       after a barrier of the caller's process group.  name: [A-Za-z0-9_.-]+, node-local.
+ *   jgpu_queue_reset  : counter = 0 for the next list (one rank, between two barriers).
+ *   jgpu_queue_claim  : returns the first of `n` consecutive list positions now owned by the caller.
+ *   jgpu_queue_close  : unmaps; the creator also unlinks the segment.
+ *   jgpu_decode_queue : decodes what this rank can claim of the n_utts utterances, visiting them in
+ *                       `order` (n_utts indices, the same on every rank — e.g. longest first; NULL = by
+ *                       decreasing length).  feats[u] are HOST pointers; the features of an utterance are
+ *                       copied to the device when it is claimed.  out[u] is written for claimed utterances
+ *                       only; claimed[k], k < *n_claimed, lists them.  busy_ms (optional) = device time between
+ *                       this rank's first and last kernel.  The schedule is built at most ~2 x 64 frame steps
+ *                       ahead of the device, so a claim reflects how far this GPU really is.
+ *   jgpu_decode_queue_device : the same with all features resident on this rank's device as one packed
+ *                       buffer (see jgpu_decode_batch_device). */
+typedef struct jgpu_queue jgpu_queue;
+int     jgpu_queue_open(const char* name, int32_t create, jgpu_queue** out);
+int     jgpu_queue_reset(jgpu_queue* q);
+int64_t jgpu_queue_claim(jgpu_queue* q, int64_t n);
+int64_t jgpu_queue_position(jgpu_queue* q);
+int     jgpu_queue_close(jgpu_queue* q);
+int jgpu_decode_queue(jgpu_handle* h, jgpu_queue* q, const float* const* feats, const int32_t* n_frames,
+                      int32_t n_utts, const int32_t* order, JgpuResult* out, int32_t* claimed,
+                      int32_t* n_claimed, double* busy_ms);
+int jgpu_decode_queue_device(jgpu_handle* h, jgpu_queue* q, const float* d_feats, const int64_t* row_offset,
+                             const int32_t* n_frames, int32_t n_utts, const int32_t* order, JgpuResult* out,
+                             int32_t* claimed, int32_t* n_claimed, double* busy_ms);
+
 /* Counters of the most recent utterance decoded on `lane` (streaming) or summed over the
  * most recent batch call (lane = -1). */
 int jgpu_stats(jgpu_handle* h, int32_t lane, JgpuStats* out);
@@ -202,6 +234,10 @@ int jgpu_frame_stats(jgpu_handle* h, int32_t lane, int32_t* cnt, float* best, in
 
 /* Number of kernel launches issued by this handle since creation (bench bookkeeping). */
 int64_t jgpu_launch_count(jgpu_handle* h);
+
+/* Second passes run by the batch entry points so far: utterances whose lane overflowed an arena are decoded again
+ * with the pools viewed as fewer lanes with larger arenas (see JgpuResult.status). */
+int64_t jgpu_retry_count(jgpu_handle* h);
 
 /* Enqueue all work of this handle on a caller-owned CUDA stream (a cudaStream_t passed as
  * void*), e.g. so that the caller's CUDA events bracket the decoder's kernels. */

@@ -51,6 +51,10 @@ def load_library() -> C.CDLL:
     lib.jgpu_utt_end.argtypes = [vp, i32, vp]
     lib.jgpu_decode_batch.argtypes = [vp, vp, vp, i32, vp]
     lib.jgpu_decode_batch_device.argtypes = [vp, vp, vp, vp, i32, vp]
+    lib.jgpu_decode_queue.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.jgpu_decode_queue_device.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.jgpu_retry_count.argtypes = [vp]
+    lib.jgpu_retry_count.restype = i64
     lib.jgpu_stats.argtypes = [vp, i32, vp]
     lib.jgpu_frame_stats.argtypes = [vp, i32, vp, vp, i32]
     lib.jgpu_launch_count.argtypes = [vp]
@@ -283,6 +287,45 @@ class WFSTDecoderLite:
         _check(self.lib.jgpu_decode_batch_device(self.h, C.c_void_p(d_feats_ptr), row_offset.ctypes.data,
                                                  n_frames.ctypes.data, n, res), "jgpu_decode_batch_device")
         return [Result(res[u]) for u in range(n)] if want_results else []
+
+    # ---- whole-utterance work stealing (BASELINE configs[3]) ----
+    def decode_queue(self, queue, feats: Sequence[np.ndarray], order: Optional[np.ndarray] = None):
+        """Decodes what this rank can claim of `feats` from the shared `queue` (dist.SharedQueue), utterance by
+        utterance as lanes run dry.  Returns ({utterance index: Result}, busy_ms)."""
+        feats = [np.ascontiguousarray(f, dtype=np.float32).reshape(-1, self.dim) for f in feats]
+        n = len(feats)
+        ptrs = (C.c_void_p * max(n, 1))(*[f.ctypes.data for f in feats])
+        nfr = np.asarray([f.shape[0] for f in feats], dtype=np.int32)
+        return self._decode_queue(queue, n, nfr, order,
+                                  lambda res, cl, ncl, busy, op: self.lib.jgpu_decode_queue(
+                                      self.h, queue.q, ptrs, nfr.ctypes.data, n, op, res, cl, ncl, busy), "jgpu_decode_queue")
+
+    def decode_queue_device(self, queue, d_feats_ptr: int, row_offset: np.ndarray, n_frames: np.ndarray,
+                            order: Optional[np.ndarray] = None):
+        row_offset = np.ascontiguousarray(row_offset, dtype=np.int64)
+        nfr = np.ascontiguousarray(n_frames, dtype=np.int32)
+        n = int(nfr.shape[0])
+        return self._decode_queue(queue, n, nfr, order,
+                                  lambda res, cl, ncl, busy, op: self.lib.jgpu_decode_queue_device(
+                                      self.h, queue.q, C.c_void_p(d_feats_ptr), row_offset.ctypes.data, nfr.ctypes.data, n, op,
+                                      res, cl, ncl, busy), "jgpu_decode_queue_device")
+
+    def _decode_queue(self, queue, n, nfr, order, call, what):
+        words, res = self._result_buffers(n)
+        claimed = np.zeros(max(n, 1), dtype=np.int32)
+        n_claimed = C.c_int32(0)
+        busy = C.c_double(0.0)
+        op = None
+        if order is not None:
+            order = np.ascontiguousarray(order, dtype=np.int32)
+            op = order.ctypes.data
+        _check(call(res, claimed.ctypes.data, C.byref(n_claimed), C.byref(busy), op), what)
+        return {int(u): Result(res[int(u)]) for u in claimed[: n_claimed.value]}, float(busy.value)
+
+    @property
+    def retry_count(self) -> int:
+        """Second passes (larger per-lane arenas, fewer lanes) run by the batch entry points so far."""
+        return int(self.lib.jgpu_retry_count(self.h))
 
     # ---- counters ----
     def stats(self, lane: int = -1) -> Dict[str, int]:

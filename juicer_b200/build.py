@@ -8,12 +8,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjuicer_b200.so")
-SOURCES = ["jgpu_engine.cu", "host_loaders.cpp", "host_mmf.cpp"]
-DEPS = SOURCES + ["jgpu_device.cuh", "jgpu_gmm.cuh", "jgpu_search.cuh", "jgpu_err.h", "jgpu_softplus_table.h", "host_models.h",
+SOURCES = ["jgpu_engine.cu", "host_loaders.cpp", "host_mmf.cpp", "host_queue.cpp"]
+DEPS = SOURCES + ["jgpu_device.cuh", "jgpu_gmm.cuh", "jgpu_search.cuh", "jgpu_err.h", "jgpu_softplus_table.h", "host_models.h", "host_queue.h",
                   os.path.join("..", "..", "include", "juicer_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false",            # scores must never see a contracted FMA (parity with the CPU decoder)
-              "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared", "-lrt"]
 
 
 def needs_build() -> bool:

@@ -17,6 +17,7 @@
 
 #include "jgpu_device.cuh"
 #include "jgpu_err.h"
+#include "host_queue.h"
 #include "jgpu_gmm.cuh"
 #define JG_HUGE_DEG 1024   // rows with at least this many model arcs are walked by all CTAs of the lane
 #include "jgpu_search.cuh"
@@ -1062,8 +1063,11 @@ int decode_pass(jgpu_handle* h, UttSource* src, const float* d_feats, const int6
 // network) are then decoded again, from their first frame, with the pools viewed as fewer lanes with larger arenas,
 // until nothing fails or nothing can grow: the reference has no capacity at all (it keeps allocating,
 // src/WFSTDecoderLite.cpp:751-805), so a capacity failure must never be what the caller sees.
+// `first` = the source of the first pass (nullptr: all n_utts utterances, longest first); `claimed`, when given,
+// receives the utterances this call decoded (a shared queue hands every rank a different subset).
 int decode_common(jgpu_handle* h, const float* d_feats, const int64_t* row_offset, const int32_t* n_frames,
-                  int32_t n_utts, JgpuResult* out)
+                  int32_t n_utts, JgpuResult* out, UttSource* first = nullptr, std::vector<int>* claimed = nullptr,
+                  const std::function<int(int)>& on_claim = nullptr)
 {
     for (auto& l : h->lanes)
         if (l.begun) return fail(JGPU_E_STATE, "streaming utterance in flight: finish it before a batch call");
@@ -1074,17 +1078,22 @@ int decode_common(jgpu_handle* h, const float* d_feats, const int64_t* row_offse
     int rc = ensure_results(h, (size_t)n_utts, pool0);
     if (rc) return rc;
     memset(&h->batch_stats, 0, sizeof(h->batch_stats));
-    std::vector<int> ids(n_utts), err, need_words;
+    // longest first: a free lane takes the longest utterance left (LPT)
+    std::vector<int> ids(n_utts), slot_utt, err, need_words;
     for (int i = 0; i < n_utts; ++i) ids[i] = i;
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return n_frames[a] > n_frames[b]; });
     if ((rc = set_view(h, h->sticky ? h->sticky_view : h->base))) return rc;
-    for (int pass = 0; pass < 4 && !ids.empty(); ++pass) {
-        if ((rc = decode_pass(h, d_feats, row_offset, n_frames, ids, out, &err, &need_words))) break;
+    for (int pass = 0; pass < 4; ++pass) {
+        ListSource list(ids);
+        UttSource* src = (pass == 0 && first) ? first : &list;
+        if ((rc = decode_pass(h, src, d_feats, row_offset, n_frames, out, &slot_utt, &err, &need_words, on_claim))) break;
+        if (pass == 0 && claimed) *claimed = slot_utt;
         std::vector<int> failed;
         int errors = 0;
         size_t words = 0;
-        for (size_t k = 0; k < ids.size(); ++k)
+        for (size_t k = 0; k < slot_utt.size(); ++k)
             if (err[k] & JG_ERR_RETRYABLE) {
-                failed.push_back(ids[k]);
+                failed.push_back(slot_utt[k]);
                 errors |= err[k];
                 words += (size_t)std::max(need_words[k], 64);
             }
@@ -1093,15 +1102,30 @@ int decode_common(jgpu_handle* h, const float* d_feats, const int64_t* row_offse
         const bool grew = grow_view(h, errors, (int)failed.size(), &v);
         const bool more_words = (errors & JG_ERR_WORDS) != 0;
         if (!grew && !more_words) break;                      // nothing left to enlarge: the statuses stand
-        if (more_words && (rc = ensure_results(h, failed.size(), words + words / 2))) break;
+        if (more_words && (rc = ensure_results(h, (size_t)n_utts, words + words / 2))) break;
         if (grew && (rc = set_view(h, v))) break;
         // a batch that mostly overflowed starts the next call with the larger arenas straight away
-        if (grew && pass == 0 && failed.size() * 2 > ids.size()) { h->sticky = true; h->sticky_view = v; }
+        if (grew && pass == 0 && failed.size() * 2 > slot_utt.size()) { h->sticky = true; h->sticky_view = v; }
         ++h->retry_passes;
+        std::stable_sort(failed.begin(), failed.end(), [&](int a, int b) { return n_frames[a] > n_frames[b]; });
         ids.swap(failed);
     }
     const int rc2 = set_view(h, h->base);                     // the streaming interface always sees the base view
     return rc ? rc : rc2;
+}
+
+// device buffer for the packed features of a host-buffer batch call
+int ensure_feats(jgpu_handle* h, size_t rows)
+{
+    if (rows > h->feats_cap) {
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->d_feats) cudaFree(h->d_feats);
+        h->d_feats = nullptr;
+        h->feats_cap = 0;
+        CK(cudaMalloc(&h->d_feats, std::max<size_t>(rows, 1) * h->dim * sizeof(float)));
+        h->feats_cap = rows;
+    }
+    return JGPU_OK;
 }
 
 int lane_stats(jgpu_handle* h, int lane, JgpuStats* out)
@@ -1288,20 +1312,93 @@ int jgpu_decode_batch(jgpu_handle* h, const float* const* feats, const int32_t* 
         if (n_frames[u] < 0) return fail(JGPU_E_ARG, "utterance %d: negative frame count", u);
         off[u + 1] = off[u] + n_frames[u];
     }
-    const size_t rows = (size_t)off[n_utts];
-    if (rows > h->feats_cap) {
-        CK(cudaStreamSynchronize(h->stream));
-        if (h->d_feats) cudaFree(h->d_feats);
-        h->d_feats = nullptr;
-        h->feats_cap = 0;
-        CK(cudaMalloc(&h->d_feats, std::max<size_t>(rows, 1) * h->dim * sizeof(float)));
-        h->feats_cap = rows;
-    }
+    int rc0 = ensure_feats(h, (size_t)off[n_utts]);
+    if (rc0) return rc0;
     for (int u = 0; u < n_utts; ++u)
         if (n_frames[u] > 0)
             CK(cudaMemcpyAsync(h->d_feats + (size_t)off[u] * h->dim, feats[u], (size_t)n_frames[u] * h->dim * sizeof(float),
                                cudaMemcpyHostToDevice, h->stream));
     return decode_common(h, h->d_feats, off.data(), n_frames, n_utts, out);
+}
+
+namespace {
+struct QueueSource : UttSource {
+    jgpu_queue* q;
+    std::vector<int> order;
+    QueueSource(jgpu_queue* q_, const int32_t* ord, const int32_t* n_frames, int n) : q(q_), order(n)
+    {
+        for (int i = 0; i < n; ++i) order[i] = ord ? ord[i] : i;
+        if (!ord) std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n_frames[a] > n_frames[b]; });
+    }
+    int next() override
+    {
+        const int64_t i = jgpu_queue_claim(q, 1);
+        return (i >= 0 && i < (int64_t)order.size()) ? order[(size_t)i] : -1;
+    }
+    bool shared() const override { return true; }
+};
+
+int decode_queue_common(jgpu_handle* h, jgpu_queue* q, const float* d_feats, const int64_t* row_offset, const int32_t* n_frames,
+                        int32_t n_utts, const int32_t* order, JgpuResult* out, int32_t* claimed, int32_t* n_claimed,
+                        double* busy_ms, const std::function<int(int)>& on_claim)
+{
+    if (order)
+        for (int i = 0; i < n_utts; ++i)
+            if (order[i] < 0 || order[i] >= n_utts) return fail(JGPU_E_ARG, "order[%d] = %d out of range", i, order[i]);
+    QueueSource src(q, order, n_frames, n_utts);
+    std::vector<int> mine;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (busy_ms) {
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, h->stream));
+    }
+    int rc = decode_common(h, d_feats, row_offset, n_frames, n_utts, out, &src, &mine, on_claim);
+    if (busy_ms) {
+        cudaEventRecord(e1, h->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *busy_ms = ms;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    if (n_claimed) *n_claimed = (int32_t)mine.size();
+    if (claimed)
+        for (size_t k = 0; k < mine.size(); ++k) claimed[k] = mine[k];
+    return rc;
+}
+} // namespace
+
+int jgpu_decode_queue_device(jgpu_handle* h, jgpu_queue* q, const float* d_feats, const int64_t* row_offset,
+                             const int32_t* n_frames, int32_t n_utts, const int32_t* order, JgpuResult* out,
+                             int32_t* claimed, int32_t* n_claimed, double* busy_ms)
+{
+    if (!h || !q || n_utts < 0 || (n_utts > 0 && (!d_feats || !row_offset || !n_frames || !out))) return fail(JGPU_E_ARG, "bad argument");
+    CK(cudaSetDevice(h->device));
+    return decode_queue_common(h, q, d_feats, row_offset, n_frames, n_utts, order, out, claimed, n_claimed, busy_ms, nullptr);
+}
+
+int jgpu_decode_queue(jgpu_handle* h, jgpu_queue* q, const float* const* feats, const int32_t* n_frames, int32_t n_utts,
+                      const int32_t* order, JgpuResult* out, int32_t* claimed, int32_t* n_claimed, double* busy_ms)
+{
+    if (!h || !q || n_utts < 0 || (n_utts > 0 && (!feats || !n_frames || !out))) return fail(JGPU_E_ARG, "bad argument");
+    CK(cudaSetDevice(h->device));
+    std::vector<int64_t> off(n_utts + 1, 0);
+    for (int u = 0; u < n_utts; ++u) {
+        if (n_frames[u] < 0) return fail(JGPU_E_ARG, "utterance %d: negative frame count", u);
+        off[u + 1] = off[u] + n_frames[u];
+    }
+    int rc = ensure_feats(h, (size_t)off[n_utts]);
+    if (rc) return rc;
+    // the features of an utterance cross the bus when it is claimed, stream-ordered ahead of the steps that read them
+    auto on_claim = [&](int u) -> int {
+        if (n_frames[u] > 0)
+            CK(cudaMemcpyAsync(h->d_feats + (size_t)off[u] * h->dim, feats[u], (size_t)n_frames[u] * h->dim * sizeof(float),
+                               cudaMemcpyHostToDevice, h->stream));
+        return JGPU_OK;
+    };
+    return decode_queue_common(h, q, h->d_feats, off.data(), n_frames, n_utts, order, out, claimed, n_claimed, busy_ms, on_claim);
 }
 
 int jgpu_stats(jgpu_handle* h, int32_t lane, JgpuStats* out)
@@ -1330,6 +1427,7 @@ int jgpu_frame_stats(jgpu_handle* h, int32_t lane, int32_t* cnt, float* best, in
 }
 
 int64_t jgpu_launch_count(jgpu_handle* h) { return h ? h->launches : 0; }
+int64_t jgpu_retry_count(jgpu_handle* h) { return h ? h->retry_passes : 0; }
 
 int jgpu_set_stream(jgpu_handle* h, void* cuda_stream)
 {

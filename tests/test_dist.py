@@ -82,15 +82,20 @@ def _steal_worker(rank, world, port, q):
         time.sleep(0.05 if rank == 1 else 0.0)              # rank 1 is the slow GPU
         return {u: dict(rank=rank, frames=n_frames[u]) for u in idx}
 
-    local = jdist.decode_with_stealing(decode_wave, n_frames, wave=3, name="test/queue")
+    local = jdist.decode_with_stealing(decode_wave, n_frames, wave=3)
     allr = jdist.gather_results(local, len(n_frames))
+    # a second list through a second queue with the same (default) name: a fresh counter, nothing is skipped
+    # (the store key of the first version was never reset)
+    local2 = jdist.decode_with_stealing(lambda idx: {u: dict(rank=rank, frames=n_frames[u]) for u in idx}, n_frames, wave=5)
+    allr2 = jdist.gather_results(local2, len(n_frames))
+    assert [r["frames"] for r in allr2] == n_frames
     if rank == 0:
         q.put(allr)
     d.barrier()
     d.destroy_process_group()
 
 
-def test_work_stealing_queue_two_ranks():
+def test_work_stealing_queue_two_ranks(product_lib):
     """Every utterance is decoded exactly once, and the fast rank ends up with more of them."""
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
@@ -107,6 +112,46 @@ def test_work_stealing_queue_two_ranks():
     assert sum(by_rank) == 40 and by_rank[0] > by_rank[1]
 
 
-def test_queue_without_process_group_is_a_plain_loop():
+def test_queue_without_process_group_is_a_plain_loop(product_lib):
     q = jdist.UtteranceQueue([5, 9, 1, 7], wave=3)
     assert q.claim() == [1, 3, 0] and q.claim() == [2] and q.claim() == []
+    q.close()
+    q2 = jdist.UtteranceQueue([5, 9, 1, 7], wave=3)          # same default name, fresh counter
+    assert q2.claim() == [1, 3, 0]
+    q2.close()
+
+
+def _claim_worker(name, n, out_q):
+    q = jdist.SharedQueue(name, False)
+    mine = []
+    while True:
+        i = q.claim(1)
+        if i >= n:
+            break
+        mine.append(i)
+    out_q.put(mine)
+    q.close()
+
+
+def test_shared_queue_hands_out_every_position_once(product_lib):
+    """The C-ABI counter (jgpu_queue_*: POSIX shared memory + atomic fetch-add) under three concurrent processes."""
+    name = f"juicer_b200.test.{os.getpid()}"
+    owner = jdist.SharedQueue(name, True)
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    n = 20000
+    procs = [ctx.Process(target=_claim_worker, args=(name, n, out_q)) for _ in range(3)]
+    for p in procs:
+        p.start()
+    got = [out_q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    flat = sorted(i for g in got for i in g)
+    assert flat == list(range(n))
+    assert owner.position >= n
+    owner.reset()
+    assert owner.claim(4) == 0 and owner.claim(1) == 4
+    owner.close()
+    with pytest.raises(Exception):
+        jdist.SharedQueue(name, False)                       # the creator unlinked the segment
