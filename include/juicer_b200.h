@@ -232,6 +232,11 @@ int jgpu_stats(jgpu_handle* h, int32_t lane, JgpuStats* out);
  * after frame t; best[t] = bestEmitScore after frame t.  Returns frames written. */
 int jgpu_frame_stats(jgpu_handle* h, int32_t lane, int32_t* cnt, float* best, int32_t max_frames);
 
+/* Measurement utility for bench.py's secondary roofline: the FP32 issue peak of this device for code that may
+ * not contract multiplies and adds into FMAs (the scorer's exact operand order forbids it), in 10^12 scalar
+ * operations per second, measured now on the handle's stream. */
+int jgpu_ubench_fp32(jgpu_handle* h, double* tera_ops);
+
 /* Number of kernel launches issued by this handle since creation (bench bookkeeping). */
 int64_t jgpu_launch_count(jgpu_handle* h);
 

@@ -53,6 +53,7 @@ def load_library() -> C.CDLL:
     lib.jgpu_decode_batch_device.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.jgpu_decode_queue.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.jgpu_decode_queue_device.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.jgpu_ubench_fp32.argtypes = [vp, vp]
     lib.jgpu_retry_count.argtypes = [vp]
     lib.jgpu_retry_count.restype = i64
     lib.jgpu_stats.argtypes = [vp, i32, vp]
@@ -321,6 +322,12 @@ class WFSTDecoderLite:
             op = order.ctypes.data
         _check(call(res, claimed.ctypes.data, C.byref(n_claimed), C.byref(busy), op), what)
         return {int(u): Result(res[int(u)]) for u in claimed[: n_claimed.value]}, float(busy.value)
+
+    def fp32_peak_tops(self) -> float:
+        """Non-FMA FP32 issue peak of the device, 10^12 op/s (jgpu_ubench_fp32)."""
+        v = C.c_double(0.0)
+        _check(self.lib.jgpu_ubench_fp32(self.h, C.byref(v)), "jgpu_ubench_fp32")
+        return float(v.value)
 
     @property
     def retry_count(self) -> int:

@@ -97,7 +97,8 @@ struct LaneCtl {
     int n_free;               // records on the lane's free list (filled by k_gc_sweep)
     int gc_gen, gc_do;        // mark stamp of the collection in progress / whether this lane takes part in it
     int paths_recycled;       // records served from the free list in this utterance (statistics)
-    int pad_tail_[4];         // keeps sizeof(LaneCtl) off a multiple of 128 B: every CTA of every kernel reads the same
+    int c_gmm;                // (GMM, frame) scores computed for this lane in the current step (lazy scorer)
+    int pad_tail_[3];         // keeps sizeof(LaneCtl) off a multiple of 128 B: every CTA of every kernel reads the same
                               // fields of all lanes at start-up, and line-aligned control blocks put those hot lines on
                               // a subset of the L2 slices (measured: +4 us per kernel launch at a 384 B stride)
 };
@@ -144,6 +145,19 @@ struct Dev {
     int*      path_free;       // [n_lanes][cap_paths] free list: indices of dead word-boundary records
     int*      hist;
     const float* scores;       // [ring rows][n_gmms]
+    // lazy acoustic scoring (HTKFlatModels::calcOutput is only ever called for states a live token asks for,
+    // src/HTKFlatModels.cpp:226-262): whoever writes a token that can make a state ask for its score in the NEXT step
+    // stamps need[gmm][lane] with the low byte of the lane's next epoch; k_gmm_lazy scores the stamped pairs of a
+    // step between k_boundary and k_internal.  A stale stamp only costs an evaluation, so nothing is ever cleared.
+    int lazy;                  // 0: every GMM is scored for every frame, 16 frames ahead (k_gmm_scores)
+    unsigned char* need;       // [n_gmms][need_stride]
+    int need_stride;           // lanes rounded up to 32
+    const int* arc_g1;         // per arc: GMM of the first emitting state of its HMM, or -1 - hmm when the entry state
+                               // has other emitting successors (then every emitting state is stamped)
+    int* lane_stamp;           // [need_stride] stamp current in this step per lane, 0x100 when the lane scores nothing
+    float* xtile;              // [need_stride][DP] the lanes' feature rows of this step, zero padded (k_boundary)
+    int xtile_dp, feat_dim;
+    const float* const* feat_base;   // device cell holding the feature base pointer of the running schedule chunk
     const int4*  sched;        // [n_steps + 1][n_lanes] {feature row, score row, flags, utt}
     int*      lane_step;       // [n_lanes] next schedule row of the lane (k_boundary)
     ResHdr*   res_hdr;

@@ -28,6 +28,22 @@
 #define JG_TRACING(h) false
 #endif
 
+// non-FMA FP32 issue-rate microbenchmark (jgpu_ubench_fp32)
+__global__ void __launch_bounds__(256) k_ubench_fp32(float* out, int iters, float m)
+{
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = 1.0f + threadIdx.x * 1e-6f + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { a[i] = __fmul_rn(a[i], m); a[i] = __fmul_rn(a[i], 1.0009765625f); }
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 namespace {
 
 int fail(int code, const char* fmt, ...)
@@ -87,6 +103,11 @@ struct jgpu_handle {
     int stream_chunk = 256;
     float* d_scores = nullptr;
     float* d_gmm_out = nullptr;   // jgpu_gmm_scores scratch
+    // lazy scorer (k_gmm_lazy): per-component parameter rows, the per-step feature tile and the demand stamps
+    bool lazy = true;             // JUICER_B200_DENSE=1 (or more than 32 components per GMM): score everything, 16 frames ahead
+    int lazy_cluster = JG_LAZY_CLUSTER;   // CTAs sharing one multicast feature tile (JUICER_B200_LAZY_CLUSTER = 1 | 2 | 4)
+    LazyArgs lz{};
+    const float** d_feat_base = nullptr;
     int gmm_chunk = 1024;
     // results
     size_t res_cap = 0;                  // utterance headers
@@ -397,7 +418,27 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
         for (int s = 1; s < ns - 1; ++s) info[(size_t)i * 8 + (s <= 3 ? s : s + 1)] = m->gmm[i * M + s];
     }
 
+    // lazy scoring: the GMM an entry token makes ask for its score — the first emitting state when that is the entry
+    // state's only emitting successor, else (-1 - hmm): the commit then stamps every emitting state of the model
+    std::vector<int> arc_g1(A, 0);
+    {
+        std::vector<int> g1_of(H);
+        for (int i = 0; i < H; ++i) {
+            const int ns = m->n_states[i];
+            int n_succ = 0, only = -1;
+            for (int j = 1; j < ns - 1; ++j)
+                if (m->trp[((size_t)i * M + 0) * M + j] > JG_LZ) { ++n_succ; only = j; }
+            g1_of[i] = (n_succ == 1 && only == 1) ? m->gmm[i * M + 1] : (-1 - i);
+            if (ns <= 2) g1_of[i] = -1 - i;              // no emitting state at all: nothing to stamp
+        }
+        for (int a = 0; a < A; ++a) arc_g1[a] = arcs[a].z > 0 ? g1_of[arcs[a].z - 1] : 0;
+    }
     int rc;
+    {
+        int* d_g1 = nullptr;
+        if ((rc = upload(h, &d_g1, arc_g1))) return rc;
+        d.arc_g1 = d_g1;
+    }
     // The static network + HMM tables live in ONE allocation (an L2 access-policy window over it was measured:
     // pinning them costs more L2 than it saves; the streams carry evict-first hints instead).
     auto pad256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
@@ -458,11 +499,38 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
     if ((rc = upload(h, &d_det, det))) return rc;
     if ((rc = upload(h, &d_nc, nc))) return rc;
     G.mu = d_mu; G.iv = d_iv; G.det = d_det; G.ncomp = d_nc;
+    if (const char* e = getenv("JUICER_B200_DENSE")) h->lazy = atoi(e) == 0;
+    if (const char* e = getenv("JUICER_B200_LAZY_CLUSTER")) h->lazy_cluster = atoi(e);
+    if (h->lazy_cluster != 1 && h->lazy_cluster != 2 && h->lazy_cluster != 4) h->lazy_cluster = JG_LAZY_CLUSTER;
+    if (C > 32) h->lazy = false;                         // a component per thread of a warp at most
+    if (h->lazy) {
+        // the same parameters once more, one 16 B-aligned row of DP floats per component: [gmm][component][DP]
+        const int DPl = h->DP;
+        std::vector<float> mu2((size_t)g->n_gmms * C * DPl, 0.0f), iv2(mu2.size(), 0.0f), det2((size_t)g->n_gmms * C, JG_LZ);
+        for (int gi = 0; gi < g->n_gmms; ++gi)
+            for (int c = 0; c < g->n_comps[gi]; ++c) {
+                det2[(size_t)gi * C + c] = g->dets[(size_t)gi * C + c];
+                for (int dd = 0; dd < D; ++dd) {
+                    mu2[((size_t)gi * C + c) * DPl + dd] = g->means[((size_t)gi * C + c) * D + dd];
+                    iv2[((size_t)gi * C + c) * DPl + dd] = g->ivars[((size_t)gi * C + c) * D + dd];
+                }
+            }
+        float *d_mu2, *d_iv2, *d_det2;
+        if ((rc = upload(h, &d_mu2, mu2))) return rc;
+        if ((rc = upload(h, &d_iv2, iv2))) return rc;
+        if ((rc = upload(h, &d_det2, det2))) return rc;
+        LazyArgs& z = h->lz;
+        z.mu = d_mu2; z.iv = d_iv2; z.det = d_det2; z.ncomp = d_nc;
+        z.n_gmms = g->n_gmms; z.C = C;
+        z.cpw = 1;
+        while (z.cpw < C) z.cpw *= 2;
+    }
     {
         std::vector<double> sp(&JG_SOFTPLUS_TABLE[0][0], &JG_SOFTPLUS_TABLE[0][0] + JG_SP_INTERVALS * (JG_SP_DEG + 1));
         double* d_sp;
         if ((rc = upload(h, &d_sp, sp))) return rc;
         G.softplus = d_sp;
+        h->lz.softplus = d_sp;
     }
     return JGPU_OK;
 }
@@ -575,7 +643,24 @@ int build_state(jgpu_handle* h)
     if ((rc = h->alloc(&h->d_sched, (size_t)(h->sched_chunk + 1) * L, false))) return rc;
     if ((rc = h->alloc(&h->d_rows, (size_t)h->sched_chunk * L, false))) return rc;
     if ((rc = h->alloc(&d.lane_step, L))) return rc;
-    if ((rc = h->alloc(&h->d_scores, (size_t)2 * h->FB * L * d.n_gmms, false))) return rc;   // two halves
+    d.lazy = h->lazy ? 1 : 0;
+    d.need_stride = ((int)L + 31) & ~31;
+    d.xtile_dp = h->DP;
+    d.feat_dim = h->dim;
+    if ((rc = h->alloc(&h->d_feat_base, 1))) return rc;
+    d.feat_base = h->d_feat_base;
+    if (h->lazy) {
+        if ((rc = h->alloc(&d.need, (size_t)d.n_gmms * d.need_stride))) return rc;
+        if ((rc = h->alloc(&d.lane_stamp, (size_t)d.need_stride))) return rc;
+        if ((rc = h->alloc(&d.xtile, (size_t)d.need_stride * h->DP))) return rc;
+        std::vector<int> st0(d.need_stride, 0x100);
+        CK(cudaMemcpyAsync(d.lane_stamp, st0.data(), st0.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if ((rc = h->alloc(&h->d_scores, L * d.n_gmms, false))) return rc;                    // one row per lane
+        LazyArgs& z = h->lz;
+        z.need = d.need; z.need_stride = d.need_stride; z.n_lanes = (int)L; z.ctl = d.ctl; z.lane_stamp = d.lane_stamp;
+        z.xtile = d.xtile; z.scores = h->d_scores;
+    } else if ((rc = h->alloc(&h->d_scores, (size_t)2 * h->FB * L * d.n_gmms, false))) return rc;   // two halves
     if ((rc = h->alloc(&h->d_stream_feats, L * h->stream_chunk * h->dim, false))) return rc;
     if ((rc = h->alloc(&h->d_gmm_out, (size_t)h->gmm_chunk * d.n_gmms, false))) return rc;
     d.scores = h->d_scores;
@@ -660,6 +745,7 @@ int set_view(jgpu_handle* h, const jgpu_handle::View& v)
     CK(cudaStreamSynchronize(h->stream));
     drop_graphs(h);
     d.n_lanes = v.n_lanes; d.cap = v.cap; d.cap_arr = v.cap_arr; d.cap_paths = v.cap_paths;
+    h->lz.n_lanes = v.n_lanes;
     d.gc_threshold = d.cap_paths - d.cap_paths / 4;
     h->bpl = std::max(2, std::min(64, (1184 + v.n_lanes - 1) / v.n_lanes));
     return JGPU_OK;
@@ -717,6 +803,38 @@ int launch_gmm(jgpu_handle* h, const float* d_x, const int* d_rows, int n_rows, 
     return JGPU_OK;
 }
 
+// the stamped (GMM, lane) pairs of this step (see k_gmm_lazy); runs between k_boundary and k_internal
+int launch_lazy(jgpu_handle* h)
+{
+    const LazyArgs& z = h->lz;
+    const int CL = h->lazy_cluster;
+    int grid = (z.n_gmms + JG_LAZY_WARPS - 1) / JG_LAZY_WARPS;
+    grid = (grid + CL - 1) / CL * CL;
+    const size_t smem = (size_t)z.need_stride * h->DP * sizeof(float) + (size_t)JG_LAZY_WARPS * 32 * (z.cpw + 1) * sizeof(float) +
+                        (size_t)JG_LAZY_WARPS * z.need_stride * sizeof(unsigned short) + (size_t)2 * z.need_stride * sizeof(int);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(JG_LAZY_WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = CL > 1 ? 1 : 0;
+    h->prof_begin(JGPU_K_GMM);
+    cudaError_t e = cudaErrorInvalidValue;
+#define LAZY_LAUNCH(DPV, CLV)                                                                                              \
+    if (h->DP == DPV && CL == CLV) {                                                                                       \
+        e = cudaFuncSetAttribute(k_gmm_lazy<DPV, CLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+        if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, k_gmm_lazy<DPV, CLV>, z);                                       \
+    }
+#define LAZY_DP(DPV) LAZY_LAUNCH(DPV, 1) LAZY_LAUNCH(DPV, 2) LAZY_LAUNCH(DPV, 4)
+    LAZY_DP(16) LAZY_DP(28) LAZY_DP(40) LAZY_DP(52) LAZY_DP(64)
+#undef LAZY_DP
+#undef LAZY_LAUNCH
+    h->prof_end();
+    ++h->launches;
+    if (e != cudaSuccess) return fail(JGPU_E_CUDA, "k_gmm_lazy launch (DP %d, cluster %d, %zu B shared): %s", h->DP, CL, smem, cudaGetErrorString(e));
+    return JGPU_OK;
+}
+
 int launch_step(jgpu_handle* h)
 {
     const Dev& d = h->d;
@@ -733,6 +851,7 @@ int launch_step(jgpu_handle* h)
     h->prof_begin(JGPU_K_BOUNDARY);
     k_boundary<<<d.n_lanes, 32, 0, st>>>(d);
     h->prof_end();
+    if (h->lazy) { int rc = launch_lazy(h); if (rc) return rc; }
     h->prof_begin(JGPU_K_INTERNAL);
     {
         const size_t smem = (size_t)2 * h->S * JG_THREADS * sizeof(float4);   // two chunk buffers: record + S-1 token planes
@@ -791,7 +910,7 @@ int launch_steps_graph(jgpu_handle* h, int n)
         if (e != cudaSuccess) { exec = nullptr; return fail(JGPU_E_CUDA, "graph instantiate: %s", cudaGetErrorString(e)); }
     }
     CK(cudaGraphLaunch(exec, h->stream));
-    h->launches += (int64_t)n * (3 + h->d.n_rounds + (h->d.fuse_exits ? 0 : 1) + (h->has_huge ? 1 : 0));
+    h->launches += (int64_t)n * (3 + h->d.n_rounds + (h->d.fuse_exits ? 0 : 1) + (h->has_huge ? 1 : 0) + (h->lazy ? 1 : 0));
     return JGPU_OK;
 }
 
@@ -813,9 +932,11 @@ int submit_chunk(jgpu_handle* h, std::vector<int4>& chunk, int ns, bool last, co
         }
     CK(cudaMemcpyAsync(h->d_sched, chunk.data(), (size_t)(ns + (last ? 1 : 0)) * L * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->d.lane_step, 0, (size_t)L * sizeof(int), h->stream));
-    if (ns) CK(cudaMemcpyAsync(h->d_rows, rows.data(), (size_t)ns * L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    // the acoustic scores of frame block b+1 are enqueued ahead of the search of block b (two halves of the ring)
+    if (ns && !h->lazy) CK(cudaMemcpyAsync(h->d_rows, rows.data(), (size_t)ns * L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_feat_base, &d_x, sizeof(const float*), cudaMemcpyHostToDevice, h->stream));   // k_boundary gathers from it
+    // dense mode: the acoustic scores of frame block b+1 are enqueued ahead of the search of block b (two halves of the ring)
     auto issue_gmm = [&](int b) -> int {
+        if (h->lazy) return JGPU_OK;
         const int b0 = b * FB, nb = std::min(FB, ns - b0), half = b & 1;
         return launch_gmm(h, d_x, h->d_rows + (size_t)b0 * L, nb * L, h->d_scores, (long long)half * FB * L);
     };
@@ -1424,6 +1545,38 @@ int jgpu_frame_stats(jgpu_handle* h, int32_t lane, int32_t* cnt, float* best, in
     if (n > 0 && cnt) CK(cudaMemcpy(cnt, h->d.fstat_cnt + (size_t)lane * h->d.max_frames * 4, (size_t)n * 4 * sizeof(int), cudaMemcpyDeviceToHost));
     if (n > 0 && best) CK(cudaMemcpy(best, h->d.fstat_best + (size_t)lane * h->d.max_frames, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
     return n;
+}
+
+// Measurement utility (bench.py: roofline.secondary): the FP32 issue peak for code that may not use FMA — what bounds
+// the scorer, whose exact operand order forbids contraction.  16 independent multiply chains per
+// thread, 8 CTAs of 256 threads per SM; returns 10^12 scalar FP32 operations per second, best of 5 launches.
+int jgpu_ubench_fp32(jgpu_handle* h, double* tera_ops)
+{
+    if (!h || !tera_ops) return fail(JGPU_E_ARG, "bad argument");
+    CK(cudaSetDevice(h->device));
+    float* out = nullptr;
+    const int grid = h->n_sm * 8, iters = 1 << 14;
+    CK(cudaMalloc(&out, (size_t)grid * 256 * sizeof(float)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0, h->stream);
+        k_ubench_fp32<<<grid, 256, 0, h->stream>>>(out, iters, 0.999f);
+        cudaEventRecord(e1, h->stream);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double ops = (double)grid * 256 * (double)iters * 32.0;
+        if (rep > 0 && ms > 0.f) best = std::max(best, ops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    CK(cudaGetLastError());
+    *tera_ops = best;
+    return JGPU_OK;
 }
 
 int64_t jgpu_launch_count(jgpu_handle* h) { return h ? h->launches : 0; }

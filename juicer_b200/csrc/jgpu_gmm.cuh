@@ -220,3 +220,217 @@ k_gmm_scores(GmmDev g, int gpb, const float* __restrict__ x, const int* __restri
 {
     gmm_scores_body<DP, 256, false>(g, gpb, x, rows, n_rows, out, out_base, n_by);
 }
+
+// =========================================================================================
+// k_gmm_lazy: the scorer of the decode loop.  The reference evaluates a GMM only when a live state asks for it
+// (calcGMMOutput behind a per-frame cache, src/HTKFlatModels.cpp:226-262: ~3.1k of 6000 GMMs per frame on c3);
+// here the (GMM, lane) pairs stamped for this step (Dev::need, see jgpu_device.cuh) are scored once per step,
+// between k_boundary and k_internal — a superset of what k_internal will read, counted per lane (total_gmm_evals).
+//
+//   warp   <-> one GMM at a time (warp w of the grid takes GMMs w, w + n_warps, ...)
+//   thread <-> component c = lane % CPW of that GMM, its mean / inverse-variance rows in registers; the 32 / CPW
+//              groups of CPW threads work on different feature rows, JG_LAZY_U rows in flight per thread
+//   rows    = the lanes whose stamp is current, compacted by ballot into a per-warp list
+// so no SIMT slot is spent on a (GMM, lane) pair nobody asked for.  Arithmetic and operand order are those of
+// k_gmm_scores above (same helpers), so the two produce the same bits.
+//
+// Feature tile: k_boundary gathers the lanes' feature rows of the step into one dense zero-padded tile
+// [lanes][DP]; every CTA needs all of it.  It is staged with the TMA bulk-copy engine (cp.async.bulk, SASS UBLKCP)
+// completing on an mbarrier, and MULTICAST across a thread-block cluster: each CTA of the cluster fetches 1 / CL of
+// the tile once and the copy lands in the shared memory of all CL CTAs (JG_LAZY_CLUSTER = 1: plain per-CTA copy).
+// =========================================================================================
+#ifndef JG_LAZY_U
+#define JG_LAZY_U 2
+#endif
+#ifndef JG_LAZY_CLUSTER
+#define JG_LAZY_CLUSTER 2
+#endif
+#define JG_LAZY_WARPS 8
+
+__device__ __forceinline__ unsigned jg_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void jg_mbar_init(void* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(jg_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void jg_mbar_expect_tx(void* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(jg_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void jg_mbar_wait(void* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "JG_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra JG_DONE;\n"
+        "bra JG_WAIT;\n"
+        "JG_DONE:\n"
+        "}\n" ::"r"(jg_smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared memory of this CTA / of every CTA in `mask` of the cluster (same offsets in each)
+__device__ __forceinline__ void jg_bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(jg_smem_u32(dst)), "l"(src), "r"(bytes), "r"(jg_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void jg_bulk_g2s_multicast(void* dst, const void* src, unsigned bytes, void* bar, unsigned short mask)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(jg_smem_u32(dst)), "l"(src), "r"(bytes), "r"(jg_smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ unsigned jg_cluster_rank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void jg_cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                 "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+struct LazyArgs {
+    const float* mu;           // [n_gmms][C][DP]  (row of one component contiguous, 16 B aligned)
+    const float* iv;
+    const float* det;          // [n_gmms][C]
+    const int*   ncomp;
+    const double* softplus;
+    int n_gmms, C, cpw;        // cpw = threads per GMM group: smallest power of two >= C (<= 32)
+    const unsigned char* need; // [n_gmms][need_stride]
+    int need_stride, n_lanes;
+    LaneCtl* ctl;
+    const int* lane_stamp;     // [need_stride] the stamp that is current for each lane in this step (k_boundary); 0x100 = none
+    const float* xtile;        // [need_stride][DP]
+    float* scores;             // [n_lanes][n_gmms]
+};
+
+template <int DP, int CL>
+__global__ void __launch_bounds__(JG_LAZY_WARPS * 32, (DP <= 40 ? 2 : 1)) k_gmm_lazy(LazyArgs a)
+{
+    JG_TRACE_SCOPE(JGPU_K_GMM, 0);
+    extern __shared__ __align__(128) float lz_smem[];
+    __shared__ __align__(8) unsigned long long lz_bar;
+    const int Lp = a.need_stride, L = a.n_lanes;
+    float* xs = lz_smem;                                           // [Lp][DP]
+    float* vals = xs + (size_t)Lp * DP;                            // [warps][32][cpw + 1]
+    unsigned short* rowlist = reinterpret_cast<unsigned short*>(vals + JG_LAZY_WARPS * 32 * (a.cpw + 1));   // [warps][Lp]
+    int* s_stamp = reinterpret_cast<int*>(rowlist + JG_LAZY_WARPS * Lp);                                    // [Lp]
+    int* s_cnt = s_stamp + Lp;                                     // [Lp]
+
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const unsigned tile_bytes = (unsigned)((size_t)Lp * DP * sizeof(float));
+    if (tid == 0) jg_mbar_init(&lz_bar, 1);
+    __syncthreads();
+    if (CL > 1) jg_cluster_sync();                                 // every CTA of the cluster has its barrier ready
+    if (tid == 0) {
+        jg_mbar_expect_tx(&lz_bar, tile_bytes);
+        if (CL > 1) {
+            // my 1 / CL of the tile, delivered to all CTAs of the cluster
+            const unsigned share = ((tile_bytes / CL) + 15u) & ~15u;
+            const unsigned r = jg_cluster_rank();
+            const unsigned b0 = min(r * share, tile_bytes), b1 = min(b0 + share, tile_bytes);
+            if (b1 > b0)
+                jg_bulk_g2s_multicast(reinterpret_cast<char*>(xs) + b0, reinterpret_cast<const char*>(a.xtile) + b0, b1 - b0, &lz_bar,
+                                      (unsigned short)((1u << CL) - 1u));
+        } else {
+            jg_bulk_g2s(xs, a.xtile, tile_bytes, &lz_bar);
+        }
+    }
+    // meanwhile: which stamp is current for each lane (0x100 never equals a byte: idle and seeding lanes)
+    for (int l = tid; l < Lp; l += blockDim.x) {
+        s_stamp[l] = l < L ? a.lane_stamp[l] : 0x100;
+        s_cnt[l] = 0;
+    }
+    __syncthreads();
+
+    const int cpw = a.cpw, rpi = 32 / cpw;                         // rows per warp iteration
+    const int c = lane % cpw, hh = lane / cpw;
+    const int vstride = cpw + 1;
+    float* vw = vals + (size_t)wid * 32 * vstride;
+    unsigned short* rl = rowlist + (size_t)wid * Lp;
+    const int n_warps = gridDim.x * JG_LAZY_WARPS;
+    bool tile_ready = false;
+    for (int g = blockIdx.x * JG_LAZY_WARPS + wid; g < a.n_gmms; g += n_warps) {
+        // ---- rows that asked for GMM g ----
+        int n = 0;
+        const unsigned char* nd = a.need + (size_t)g * Lp;
+        for (int l0 = 0; l0 < Lp; l0 += 32) {
+            const int l = l0 + lane;
+            const bool want = (int)nd[l] == s_stamp[l];
+            const unsigned m = __ballot_sync(0xffffffffu, want);
+            if (want) {
+                rl[n + __popc(m & ((1u << lane) - 1u))] = (unsigned short)l;
+                atomicAdd(&s_cnt[l], 1);
+            }
+            n += __popc(m);
+        }
+        if (n == 0) continue;
+        // ---- this thread's Gaussian ----
+        const int nc = __ldg(a.ncomp + g);
+        const bool active = c < nc;
+        float mu[DP], iv[DP];
+        float det = JG_LZ;
+        {
+            const float4* pm = reinterpret_cast<const float4*>(a.mu + ((size_t)g * a.C + (active ? c : 0)) * DP);
+            const float4* pv = reinterpret_cast<const float4*>(a.iv + ((size_t)g * a.C + (active ? c : 0)) * DP);
+#pragma unroll
+            for (int q = 0; q < DP / 4; ++q) {
+                const float4 m4 = __ldg(pm + q), v4 = __ldg(pv + q);
+                mu[4 * q] = m4.x; mu[4 * q + 1] = m4.y; mu[4 * q + 2] = m4.z; mu[4 * q + 3] = m4.w;
+                iv[4 * q] = v4.x; iv[4 * q + 1] = v4.y; iv[4 * q + 2] = v4.z; iv[4 * q + 3] = v4.w;
+            }
+            if (active) det = __ldg(a.det + (size_t)g * a.C + c);
+        }
+        if (!tile_ready) { jg_mbar_wait(&lz_bar, 0); tile_ready = true; }
+        __syncwarp();                                              // the row list is complete
+        for (int b0 = 0; b0 < n; b0 += 32) {
+            const int nb = min(32, n - b0);
+            // phase 1: JG_LAZY_U rows in flight per thread; the d-sum of each is sequential (:247-251)
+            for (int i0 = 0; i0 < nb; i0 += rpi * JG_LAZY_U) {
+                float s[JG_LAZY_U];
+                int xo[JG_LAZY_U];                             // row offsets in float4 units
+                const float4* xs4 = reinterpret_cast<const float4*>(xs);
+#pragma unroll
+                for (int u = 0; u < JG_LAZY_U; ++u) {
+                    const int i = i0 + u * rpi + hh;
+                    xo[u] = (i < nb ? (int)rl[b0 + i] : 0) * (DP / 4);
+                    s[u] = 0.0f;
+                }
+#pragma unroll
+                for (int q = 0; q < DP / 4; ++q) {
+#pragma unroll
+                    for (int u = 0; u < JG_LAZY_U; ++u) {
+                        const float4 xv = xs4[xo[u] + q];
+                        const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float xmu = __fsub_rn(xa[e], mu[4 * q + e]);
+                            s[u] = __fadd_rn(s[u], __fmul_rn(__fmul_rn(xmu, xmu), iv[4 * q + e]));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < JG_LAZY_U; ++u) {
+                    const int i = i0 + u * rpi + hh;
+                    if (i < nb && active) vw[i * vstride + c] = __fadd_rn(__fmul_rn(-0.5f, s[u]), det);   // see k_gmm_scores
+                }
+            }
+            __syncwarp();
+            // phase 2: thread <-> (row, GMM): logAdd over the components IN ORDER (:252-255, :266-293)
+            if (lane < nb) {
+                float lp = JG_LZ;
+                for (int cc = 0; cc < nc; ++cc) lp = jg_log_add(a.softplus, lp, vw[lane * vstride + cc]);
+                a.scores[(size_t)rl[b0 + lane] * a.n_gmms + g] = lp;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int l = tid; l < L; l += blockDim.x)
+        if (s_cnt[l]) atomicAdd(&a.ctl[l].c_gmm, s_cnt[l]);
+    if (!tile_ready) jg_mbar_wait(&lz_bar, 0);                     // never leave with a copy into this CTA in flight
+    if (CL > 1) jg_cluster_sync();                                 // ... or while a peer still waits for my share
+}

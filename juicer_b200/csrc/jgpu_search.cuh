@@ -23,7 +23,8 @@
 #define JG_RUN 1                  // consecutive chunks of k_internal handed to one CTA (L1 reuse of per-lane tables)
 #endif
 #ifndef JG_WALK_CTAS
-#define JG_WALK_CTAS 6            // resident CTAs per SM of k_walk (40 registers per thread at 6)
+#define JG_WALK_CTAS 5            // resident CTAs per SM of k_walk (51 registers per thread; at 6 the commit spills since the
+                                  // arrival ids and the demand stamps were added, and 5 vs 6 measured the same in round 1)
 #endif
 #ifndef JG_HUGE_ILP
 #define JG_HUGE_ILP 2            // arcs in flight per thread in k_commit_huge (1: 32.8 us, 2: 29.0 us, 4: 31.1 us — 54 registers, two waves)
@@ -208,6 +209,15 @@ __device__ __forceinline__ u64 state_key_of(const Dev& d, unsigned epoch, float 
     return ((u64)(epoch & d.key_emask) << (32 + d.key_id_bits)) | ((u64)f2o(score) << d.key_id_bits) | (u64)id;
 }
 
+// Lazy acoustic scoring: "state with GMM g of this lane may ask for its score in the lane's next step".  A plain
+// byte store behind a read (most marks find the stamp already there); races only ever write the same value.
+__device__ __forceinline__ void mark_need(const Dev& d, int lane, int g, unsigned epoch)
+{
+    unsigned char* p = d.need + (size_t)g * d.need_stride + lane;
+    const unsigned char st = (unsigned char)((epoch + 1u) & 0xffu);
+    if (*p != st) *p = st;
+}
+
 // =========================================================================================
 // k_boundary: one warp per lane.  (A) closes the previous step: statistics, best final
 // token, back-trace when the schedule says the utterance is over (recognitionFinish,
@@ -362,7 +372,7 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
             c->s_proc_end += c->c_end_proc;
             c->s_arcs += c->c_arcs;
             c->s_entry += c->c_entry;
-            c->s_gmm += d.n_gmms;
+            c->s_gmm += d.lazy ? c->c_gmm : d.n_gmms;
             c->s_frames += 1;
             if (d.frame_stats) {
                 if (c->frame < d.max_frames) {
@@ -397,6 +407,7 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
         for (int i = 0; i <= JG_MAX_ROUNDS + 1; ++i) c->n_arr[i] = 0;
         c->best_final = 0;
         c->final_rec = -1;
+        c->c_gmm = 0;
         c->c_active_emit = c->c_active_end = c->c_end_proc = c->c_arcs = c->c_entry = 0;
         c->mode = mode;
         if (mode != JG_MODE_IDLE) c->epoch += 1;             // invalidates every arcdyn.slot of older steps
@@ -438,11 +449,19 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
             c->thr_start = (d.start_beam > 0.0f ? (be - d.start_beam) : JG_LZ);
             c->best_int = f2o(JG_LZ);                        // :905
             c->best_ext = f2o(JG_LZ);
-            c->srow = s.y;                                   // (per-frame statistics simply stop at max_frames)
+            c->srow = d.lazy ? lane : s.y;                   // row of this lane's scores (lazy: one row per lane)
         }
     }
     if (mode == JG_MODE_SEED && d.max_hyps > 0)
         for (int b = l; b < d.hist_nbins; b += 32) v.hist[b] = 0;
+    if (d.lazy) {
+        // the lane's feature row of this step goes into the dense tile the scorer stages with one bulk copy
+        if (mode == JG_MODE_FRAME) {
+            const float* x = *d.feat_base + (size_t)s.x * d.feat_dim;
+            for (int dd = l; dd < d.xtile_dp; dd += 32) d.xtile[(size_t)lane * d.xtile_dp + dd] = dd < d.feat_dim ? x[dd] : 0.0f;
+        }
+        if (l == 0) d.lane_stamp[lane] = mode == JG_MODE_FRAME ? (int)(c->epoch & 0xffu) : 0x100;
+    }
     __syncwarp();
     {
         const int* src = reinterpret_cast<const int*>(&sc);
@@ -699,6 +718,11 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
                     res.x = res.x - norm;                                          // :408
                     if (res.x > thr_emit) {
                         const float o = outp[j - 1];                               // calcOutput :411
+                        if (d.lazy && d.frame_stats) {                             // self-check: somebody asked for this score
+                            const int gm_chk[6] = {h0.y, h0.z, h0.w, h1.y, h1.z, h1.w};
+                            if (d.need[(size_t)gm_chk[j - 1] * d.need_stride + lane] != (unsigned char)(epoch & 0xffu))
+                                atomicOr(&c->error, JG_ERR_LAZY);
+                        }
                         res.x = res.x + o;
                         res.y = res.y + o;
                         if (hist_on) {                                             // Histogram::addScore
@@ -728,6 +752,20 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
                 }
                 if (res.x > JG_LZ) { ex = res; has_exit = true; ++cnt_end; }
             }
+        }
+        if (d.lazy && survive) {
+            // which states can ask for their score next step: state j when one of its predecessors holds a live token
+            // (left-to-right: j - 1 or j); other topologies stamp every emitting state of a surviving instance
+            const int gm_now[6] = {h0.y, h0.z, h0.w, h1.y, h1.z, h1.w};
+            const bool lr_c = S == 5 && (h0.x & JG_LR_CLASS);
+            bool prev_live = false;
+#pragma unroll
+            for (int j = 1; j < S - 1; ++j)
+                if (j < nst - 1) {
+                    const bool live = nt[j].x > JG_LZ;
+                    if (!lr_c || live || prev_live) mark_need(d, lane, gm_now[j - 1], epoch);
+                    prev_live = live;
+                }
         }
         JG_TRACE_AT(3);                                       // Viterbi done
         // ---- chunk i+1: its hmm_info has landed, start its acoustic-score gathers ----
@@ -940,6 +978,15 @@ __device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, 
             const float4 t = make_float4(s, tok.y, tok.z + w, tok.w);   // :568-570
             if (s > best) best = s;
             ++n_entry;
+            if (d.lazy) {                                     // the entry token makes the model's first state(s) ask
+                const int g1 = __ldg(d.arc_g1 + b);
+                if (g1 >= 0) mark_need(d, lane, g1, epoch);
+                else {
+                    const int* hi = d.hmm_info + (size_t)(-1 - g1) * 8;
+                    const int ns = __ldg(hi) & 0xff;
+                    for (int j = 1; j < ns - 1; ++j) mark_need(d, lane, __ldg(hi + (j <= 3 ? j : j + 1)), epoch);
+                }
+            }
             const size_t cap = (size_t)d.cap;
             float4* tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * (size_t)(d.S - 1) * cap;
             const int slot = slot_lookup(d, sm, epoch);

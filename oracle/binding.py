@@ -18,6 +18,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "liboracle_ref.so")
+REF_O3_SO = os.path.join(HERE, "_ref", "liboracle_ref_o3.so")       # speed-only build (-O3, AVX2 + FMA), never used for parity
 PORT_SO = os.path.join(HERE, "liboracle.so")
 DROPIN_BIN = os.path.join(HERE, "_ref", "dropin_test")
 LOG_ZERO = -np.finfo(np.float32).max
@@ -30,6 +31,7 @@ def build(ref: bool = True, port: bool = True) -> None:
         subprocess.check_call(["make", "-s", "-C", HERE, "port"])
     if ref and os.path.isdir(os.environ.get("JUICER_REF", "/root/reference")):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref_o3"])
         if os.path.exists(os.path.join(HERE, "..", "juicer_b200", "libjuicer_b200.so")):
             subprocess.check_call(["make", "-s", "-C", HERE, "dropin"])      # C++ adapter behind Juicer::IDecoder
 
@@ -78,12 +80,13 @@ class OracleRef:
     def __init__(self, files: Dict[str, str], *, main_beam: float, start_beam: float = 0.0,
                  end_beam: float = 0.0, word_beam: float = 0.0, max_hyps: int = 0,
                  lm_scale: float = 1.0, ins_penalty: float = 0.0, block_size: int = 5,
-                 remove_tee: bool = False):
+                 remove_tee: bool = False, so_path: Optional[str] = None):
         """files["jmbi"] (HTKFlatModels::readBinary) or, when only files["mmf"] is given, the MMF text form
         (HTKFlatModels::Load(mmf, remove_tee), on top of oracle/shim/htkparse_rd.cpp)."""
-        if not os.path.exists(REF_SO):
-            raise RuntimeError(f"{REF_SO} missing: run `make -C oracle ref` where /root/reference exists")
-        self.lib = C.CDLL(REF_SO)
+        so_path = so_path or REF_SO
+        if not os.path.exists(so_path):
+            raise RuntimeError(f"{so_path} missing: run `make -C oracle ref` where /root/reference exists")
+        self.lib = C.CDLL(so_path)
         self.lib.oref_create.restype = C.c_void_p
         self.lib.oref_create.argtypes = [C.c_char_p] * 4 + [C.c_float] * 6 + [C.c_int, C.c_int]
         self.lib.oref_decode.restype = C.c_int

@@ -340,3 +340,30 @@ def test_word_boundary_arena_is_garbage_collected(c2_setup):
         assert int(dec.stats(-1)["total_paths"]) == made
     same_result(want[0], dec.decode(feats[0], lane=1, chunk=37), "gc streaming")
     dec.close()
+
+
+def test_lazy_scoring_evaluates_a_tight_superset(c2_setup):
+    """HTKFlatModels::calcOutput is only called for states a live token asks for (src/HTKFlatModels.cpp:226-262).
+    The CUDA path scores, once per step, the (GMM, lane) pairs stamped one step ahead — a superset of what
+    k_internal reads (its self-check, active with frame_stats, turns a missing stamp into a failed utterance) that
+    must stay close to the exact set the oracle port counts, and well below scoring everything."""
+    import ctypes as C
+    from oracle.binding import OraclePort
+    m, net, kw, tabs, netl, models = c2_setup
+    ps = synth.PathSampler(net, m)
+    x, _ = ps.sample(200, np.random.default_rng(81))
+    p = OraclePort(tabs, _abi.make_cfg(**kw))
+    p.lib.jor_debug_gmm_superset.restype = C.c_longlong
+    p.lib.jor_debug_gmm_superset_reset()
+    want = p.decode(x)
+    exact = p.stats()["total_gmm_evals"]
+    superset = int(p.lib.jor_debug_gmm_superset())
+    dec = make_decoder(netl, models, kw, n_lanes=2, frame_stats=True)
+    got = dec.decode(x, lane=1)
+    same_result(want, got, "lazy scoring")
+    evals = dec.stats(1)["total_gmm_evals"]
+    dense = x.shape[0] * models.n_gmm
+    assert exact <= evals <= dense
+    assert evals <= 1.02 * superset + 64, (exact, superset, evals, dense)
+    assert evals < 0.9 * dense, (exact, superset, evals, dense)
+    dec.close(); p.close()
