@@ -121,7 +121,9 @@ struct jgpu_handle {
     int retry_passes = 0;                // second passes run so far (statistics)
     bool sticky = false;                 // the last batch mostly overflowed the base view: start with sticky_view
     View sticky_view{};
-    unsigned epoch_wrap = 0x7ffu;        // a lane's stamped tables are wiped when (epoch & epoch_wrap) == 0
+    unsigned epoch_wrap = 0x7ffu;        // a lane's state keys are wiped when (epoch & epoch_wrap) == 0
+    unsigned gen_wrap = 0x7ffu;          // ... and its slotmap when (utterance stamp & gen_wrap) == 0
+    std::vector<unsigned> host_gen;      // mirror of LaneCtl::utt_gen
     std::vector<LaneHost> lanes;
     int64_t launches = 0;
     JgpuStats batch_stats{};
@@ -542,9 +544,9 @@ static int bits_for(unsigned long long v)     // smallest b with v < 2^b
     return b;
 }
 
-// bytes of per-lane state per instance of capacity: two list buffers (record + S-1 token planes each), the arrival
-// records (two planes) and the round-0 work list at 2 per instance
-static double bytes_per_instance(int S) { return 16.0 * 2 + 16.0 * 2 * (S - 1) + 2 * (32.0 + 4.0); }
+// bytes of per-lane state per instance of capacity: the slot (record + S-1 token planes + free-stack entry), the
+// arrival records (two planes) and the round-0 work list at 2 per instance
+static double bytes_per_instance(int S) { return 16.0 + 16.0 * (S - 1) + 4.0 + 2 * (32.0 + 4.0); }
 
 int build_state(jgpu_handle* h)
 {
@@ -588,8 +590,9 @@ int build_state(jgpu_handle* h)
     d.key_id_bits = bits_for(2ull * ((unsigned long long)d.n_arcs + 1ull) + 1ull);
     d.slot_emask = (1u << std::min(32 - d.slot_bits, 16)) - 1u;
     d.key_emask = (1u << std::min(32 - d.key_id_bits, 16)) - 1u;
-    h->epoch_wrap = std::min(d.slot_emask, d.key_emask);    // both tables are wiped when the narrower stamp wraps
-    if (h->epoch_wrap < 7u) return fail(JGPU_E_ARG, "network too large for the stamped tables: %d arcs", d.n_arcs);
+    h->epoch_wrap = d.key_emask;                            // state keys: stamped per step, wiped when the stamp wraps
+    h->gen_wrap = d.slot_emask;                             // slotmap: stamped per utterance
+    if (h->epoch_wrap < 7u || h->gen_wrap < 7u) return fail(JGPU_E_ARG, "network too large for the stamped tables: %d arcs", d.n_arcs);
     h->has_huge = h->n_huge_states > 0;
     h->bpl = std::max(2, std::min(64, (1184 + c.n_lanes - 1) / c.n_lanes));   // k_commit_huge only
     {
@@ -601,7 +604,7 @@ int build_state(jgpu_handle* h)
     }
 
     const size_t cap = d.cap, P = d.S - 1;
-    size_t need = L * (2 * cap * 16 + 2 * P * cap * 16 + (size_t)d.n_arcs * 4 + (size_t)d.n_multi * 8 +
+    size_t need = L * (cap * 20 + P * cap * 16 + (size_t)d.n_arcs * 4 + (size_t)d.n_multi * 8 +
                        (size_t)d.cap_arr * 36 + (size_t)d.cap_paths * 36);
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
@@ -622,8 +625,9 @@ int build_state(jgpu_handle* h)
     h->pool_inst = L * cap; h->pool_arr = L * (size_t)d.cap_arr; h->pool_paths = L * (size_t)d.cap_paths;
     int rc;
     if ((rc = h->alloc(&d.ctl, L))) return rc;
-    if ((rc = h->alloc(&d.inst_meta, 2 * h->pool_inst, false))) return rc;
-    if ((rc = h->alloc(&d.tok, 2 * P * h->pool_inst, false))) return rc;
+    if ((rc = h->alloc(&d.inst_meta, h->pool_inst, false))) return rc;
+    if ((rc = h->alloc(&d.tok, P * h->pool_inst, false))) return rc;
+    if ((rc = h->alloc(&d.slot_free, h->pool_inst, false))) return rc;
     if ((rc = h->alloc(&d.slotmap, L * d.n_arcs))) return rc;
     if ((rc = h->alloc(&d.state_key, L * d.n_multi))) return rc;
     if ((rc = h->alloc(&d.arr_tok, h->pool_arr, false))) return rc;
@@ -645,12 +649,15 @@ int build_state(jgpu_handle* h)
     if ((rc = h->alloc(&d.lane_step, L))) return rc;
     d.lazy = h->lazy ? 1 : 0;
     d.need_stride = ((int)L + 31) & ~31;
+    d.need_gp = (d.n_gmms + 31) & ~31;
     d.xtile_dp = h->DP;
     d.feat_dim = h->dim;
     if ((rc = h->alloc(&h->d_feat_base, 1))) return rc;
     d.feat_base = h->d_feat_base;
     if (h->lazy) {
-        if ((rc = h->alloc(&d.need, (size_t)d.n_gmms * d.need_stride))) return rc;
+        if ((rc = h->alloc(&d.need, (size_t)d.need_gp * d.need_stride))) return rc;
+        if (d.frame_stats && (rc = h->alloc(&d.scored, (size_t)d.need_gp * d.need_stride))) return rc;
+        if ((rc = h->alloc(&d.gmm_next, 1))) return rc;
         if ((rc = h->alloc(&d.lane_stamp, (size_t)d.need_stride))) return rc;
         if ((rc = h->alloc(&d.xtile, (size_t)d.need_stride * h->DP))) return rc;
         std::vector<int> st0(d.need_stride, 0x100);
@@ -658,7 +665,8 @@ int build_state(jgpu_handle* h)
         CK(cudaStreamSynchronize(h->stream));
         if ((rc = h->alloc(&h->d_scores, L * d.n_gmms, false))) return rc;                    // one row per lane
         LazyArgs& z = h->lz;
-        z.need = d.need; z.need_stride = d.need_stride; z.n_lanes = (int)L; z.ctl = d.ctl; z.lane_stamp = d.lane_stamp;
+        z.need = d.need; z.scored = d.scored; z.gmm_next = d.gmm_next; z.need_stride = d.need_stride; z.need_gp = d.need_gp;
+        z.n_lanes = (int)L; z.ctl = d.ctl; z.lane_stamp = d.lane_stamp;
         z.xtile = d.xtile; z.scores = h->d_scores;
     } else if ((rc = h->alloc(&h->d_scores, (size_t)2 * h->FB * L * d.n_gmms, false))) return rc;   // two halves
     if ((rc = h->alloc(&h->d_stream_feats, L * h->stream_chunk * h->dim, false))) return rc;
@@ -700,6 +708,7 @@ int build_state(jgpu_handle* h)
     }
     h->lanes.assign(L, LaneHost());
     h->host_epoch.assign(L, 0u);
+    h->host_gen.assign(L, 0u);
     return JGPU_OK;
 }
 
@@ -808,8 +817,9 @@ int launch_lazy(jgpu_handle* h)
 {
     const LazyArgs& z = h->lz;
     const int CL = h->lazy_cluster;
-    int grid = (z.n_gmms + JG_LAZY_WARPS - 1) / JG_LAZY_WARPS;
-    grid = (grid + CL - 1) / CL * CL;
+    // persistent: as many CTAs as are resident (2 per SM up to DP 40), warps take GMMs from a counter
+    int grid = std::min((z.n_gmms + JG_LAZY_WARPS - 1) / JG_LAZY_WARPS, h->n_sm * (h->DP <= 40 ? 2 : 1));
+    grid = std::max(CL, grid / CL * CL);
     const size_t smem = (size_t)z.need_stride * h->DP * sizeof(float) + (size_t)JG_LAZY_WARPS * 32 * (z.cpw + 1) * sizeof(float) +
                         (size_t)JG_LAZY_WARPS * z.need_stride * sizeof(unsigned short) + (size_t)2 * z.need_stride * sizeof(int);
     cudaLaunchConfig_t cfg = {};
@@ -946,29 +956,37 @@ int submit_chunk(jgpu_handle* h, std::vector<int4>& chunk, int ns, bool last, co
         int rc;
         if (b + 1 < n_blocks && (rc = issue_gmm(b + 1))) return rc;
         const int b0 = b * FB, nb = std::min(FB, ns - b0);
-        // a lane whose epoch stamp wraps inside this block gets its stamped tables wiped right before that
-        // step (every epoch_wrap + 1 steps: 2048 on a 2M-arc network); such a block is launched step by step
+        // a lane whose step stamp (state keys) or utterance stamp (slotmap) wraps inside this block gets that table
+        // wiped right before the step (every epoch_wrap + 1 steps / gen_wrap + 1 utterances of the lane); such a
+        // block is launched step by step
         bool wipe_in_block = false;
         {
-            std::vector<unsigned> ep(h->host_epoch);
+            std::vector<unsigned> ep(h->host_epoch), gn(h->host_gen);
             for (int i = b0; i < b0 + nb && !wipe_in_block; ++i)
-                for (int l = 0; l < L; ++l)
-                    if ((chunk[(size_t)i * L + l].z & 3) != JG_MODE_IDLE && ((++ep[l]) & h->epoch_wrap) == 0u) { wipe_in_block = true; break; }
+                for (int l = 0; l < L; ++l) {
+                    const int md = chunk[(size_t)i * L + l].z & 3;
+                    if (md != JG_MODE_IDLE && ((++ep[l]) & h->epoch_wrap) == 0u) { wipe_in_block = true; break; }
+                    if (md == JG_MODE_SEED && ((++gn[l]) & h->gen_wrap) == 0u) { wipe_in_block = true; break; }
+                }
         }
         const bool graphs = h->use_graphs && !h->prof_on && !JG_TRACING(h);
         if (graphs && nb == FB && !wipe_in_block) {
             for (int i = b0; i < b0 + nb; ++i)
-                for (int l = 0; l < L; ++l)
-                    if ((chunk[(size_t)i * L + l].z & 3) != JG_MODE_IDLE) ++h->host_epoch[l];
+                for (int l = 0; l < L; ++l) {
+                    const int md = chunk[(size_t)i * L + l].z & 3;
+                    if (md != JG_MODE_IDLE) ++h->host_epoch[l];
+                    if (md == JG_MODE_SEED) ++h->host_gen[l];
+                }
             if ((rc = launch_steps_graph(h, nb))) return rc;
         } else {
             for (int i = b0; i < b0 + nb; ++i) {
                 for (int l = 0; l < L; ++l) {
-                    if ((chunk[(size_t)i * L + l].z & 3) == JG_MODE_IDLE) continue;
-                    if (((++h->host_epoch[l]) & h->epoch_wrap) == 0u) {
+                    const int md = chunk[(size_t)i * L + l].z & 3;
+                    if (md == JG_MODE_IDLE) continue;
+                    if (((++h->host_epoch[l]) & h->epoch_wrap) == 0u)
                         CK(cudaMemsetAsync(h->d.state_key + (size_t)l * d.n_multi, 0, (size_t)d.n_multi * sizeof(u64), h->stream));
+                    if (md == JG_MODE_SEED && ((++h->host_gen[l]) & h->gen_wrap) == 0u)
                         CK(cudaMemsetAsync(h->d.slotmap + (size_t)l * d.n_arcs, 0, (size_t)d.n_arcs * sizeof(unsigned), h->stream));
-                    }
                 }
                 if ((rc = graphs ? launch_steps_graph(h, 1) : launch_step(h))) return rc;
             }

@@ -227,7 +227,8 @@ k_gmm_scores(GmmDev g, int gpb, const float* __restrict__ x, const int* __restri
 // here the (GMM, lane) pairs stamped for this step (Dev::need, see jgpu_device.cuh) are scored once per step,
 // between k_boundary and k_internal — a superset of what k_internal will read, counted per lane (total_gmm_evals).
 //
-//   warp   <-> one GMM at a time (warp w of the grid takes GMMs w, w + n_warps, ...)
+//   warp   <-> one GMM at a time, taken from a device-wide counter: the rows per GMM differ by the dozen, and a static
+//              split leaves a third of an SM's warps idle at the tail of every CTA (measured)
 //   thread <-> component c = lane % CPW of that GMM, its mean / inverse-variance rows in registers; the 32 / CPW
 //              groups of CPW threads work on different feature rows, JG_LAZY_U rows in flight per thread
 //   rows    = the lanes whose stamp is current, compacted by ballot into a per-warp list
@@ -299,8 +300,10 @@ struct LazyArgs {
     const int*   ncomp;
     const double* softplus;
     int n_gmms, C, cpw;        // cpw = threads per GMM group: smallest power of two >= C (<= 32)
-    const unsigned char* need; // [n_gmms][need_stride]
-    int need_stride, n_lanes;
+    const unsigned char* need; // [need_stride][need_gp]
+    unsigned char* scored;     // same shape, or nullptr: stamp of the step in which the pair was scored (self-check)
+    int* gmm_next;             // work counter, zeroed by k_boundary
+    int need_stride, need_gp, n_lanes;
     LaneCtl* ctl;
     const int* lane_stamp;     // [need_stride] the stamp that is current for each lane in this step (k_boundary); 0x100 = none
     const float* xtile;        // [need_stride][DP]
@@ -351,15 +354,18 @@ __global__ void __launch_bounds__(JG_LAZY_WARPS * 32, (DP <= 40 ? 2 : 1)) k_gmm_
     const int vstride = cpw + 1;
     float* vw = vals + (size_t)wid * 32 * vstride;
     unsigned short* rl = rowlist + (size_t)wid * Lp;
-    const int n_warps = gridDim.x * JG_LAZY_WARPS;
     bool tile_ready = false;
-    for (int g = blockIdx.x * JG_LAZY_WARPS + wid; g < a.n_gmms; g += n_warps) {
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = atomicAdd(a.gmm_next, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= a.n_gmms) break;
         // ---- rows that asked for GMM g ----
         int n = 0;
-        const unsigned char* nd = a.need + (size_t)g * Lp;
+        const unsigned char* nd = a.need + g;
         for (int l0 = 0; l0 < Lp; l0 += 32) {
             const int l = l0 + lane;
-            const bool want = (int)nd[l] == s_stamp[l];
+            const bool want = (int)nd[(size_t)l * a.need_gp] == s_stamp[l];
             const unsigned m = __ballot_sync(0xffffffffu, want);
             if (want) {
                 rl[n + __popc(m & ((1u << lane) - 1u))] = (unsigned short)l;
@@ -423,7 +429,9 @@ __global__ void __launch_bounds__(JG_LAZY_WARPS * 32, (DP <= 40 ? 2 : 1)) k_gmm_
             if (lane < nb) {
                 float lp = JG_LZ;
                 for (int cc = 0; cc < nc; ++cc) lp = jg_log_add(a.softplus, lp, vw[lane * vstride + cc]);
-                a.scores[(size_t)rl[b0 + lane] * a.n_gmms + g] = lp;
+                const int row = (int)rl[b0 + lane];
+                a.scores[(size_t)row * a.n_gmms + g] = lp;
+                if (a.scored) a.scored[(size_t)row * a.need_gp + g] = (unsigned char)s_stamp[row];
             }
             __syncwarp();
         }

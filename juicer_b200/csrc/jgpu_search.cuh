@@ -40,8 +40,8 @@
 // Per-lane views -------------------------------------------------------------------------
 struct LaneView {
     LaneCtl* c;
-    int4* meta_cur; int4* meta_nxt;
-    float4* tok_cur; float4* tok_nxt;
+    int4* meta;
+    float4* tok;
     unsigned* slotmap;
     u64* skey;
     float4* arr_tok; int4* arr_meta;
@@ -54,12 +54,9 @@ __device__ __forceinline__ LaneView lane_view(const Dev& d, int lane, LaneCtl* c
 {
     LaneView v;
     v.c = ctl ? ctl : d.ctl + lane;
-    const int flip = v.c->flip;
     const size_t cap = (size_t)d.cap, P = (size_t)(d.S - 1);
-    v.meta_cur = d.inst_meta + ((size_t)lane * 2 + flip) * cap;
-    v.meta_nxt = d.inst_meta + ((size_t)lane * 2 + (flip ^ 1)) * cap;
-    v.tok_cur = d.tok + ((size_t)lane * 2 + flip) * P * cap;
-    v.tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * P * cap;
+    v.meta = d.inst_meta + (size_t)lane * cap;
+    v.tok = d.tok + (size_t)lane * P * cap;
     v.slotmap = d.slotmap + (size_t)lane * d.n_arcs;
     v.skey = d.state_key + (size_t)lane * d.n_multi;
     v.arr_tok = d.arr_tok + (size_t)lane * d.cap_arr;
@@ -146,6 +143,7 @@ struct LaneSh {                   // per-CTA shared copy of what a chunk needs t
 // bit 31 of LaneSh::epoch (only the low 11 bits of the epoch are ever used as a stamp): the lane's
 // word-boundary free list was not empty when the kernel started
 #define JG_SH_HAS_FREE 0x80000000u
+#define JG_SH_HAS_SFREE 0x40000000u   // bit 30: the lane's stack of free instance slots was not empty when the kernel started
 
 // sh.cnt[] must be filled (and __syncthreads() NOT yet called); returns the number of chunks
 __device__ __forceinline__ int chunk_scan(LaneSh& sh, int L, int items = JG_CH)
@@ -213,7 +211,7 @@ __device__ __forceinline__ u64 state_key_of(const Dev& d, unsigned epoch, float 
 // byte store behind a read (most marks find the stamp already there); races only ever write the same value.
 __device__ __forceinline__ void mark_need(const Dev& d, int lane, int g, unsigned epoch)
 {
-    unsigned char* p = d.need + (size_t)g * d.need_stride + lane;
+    unsigned char* p = d.need + (size_t)lane * d.need_gp + g;
     const unsigned char st = (unsigned char)((epoch + 1u) & 0xffu);
     if (*p != st) *p = st;
 }
@@ -347,9 +345,9 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
 
     // ---- (A) close the previous step ----------------------------------------------------
     if (l == 0 && prev_mode != JG_MODE_IDLE) {
-        const int n_after = min(c->n_next, d.cap);
+        const int n_after = c->n_live;
         const int n_arr_total = arr_base(c, d.n_rounds + 1);
-        if (c->n_next > d.cap) c->error |= JG_ERR_ACTIVE;
+        if (c->n_hw > d.cap) c->error |= JG_ERR_ACTIVE;
         if (n_arr_total > d.cap_arr) c->error |= JG_ERR_ARRIVALS;
         if (c->n_paths > d.cap_paths) c->error |= JG_ERR_PATHS;
         const u64 key = c->best_final;
@@ -399,23 +397,20 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
     }
     __syncwarp();
     if (l == 0) {
-        if (prev_mode != JG_MODE_IDLE) {                     // the list built last step becomes current
-            c->flip ^= 1;
-            c->n_cur = min(c->n_next, d.cap);
-        }
-        c->n_next = 0; c->n_huge = 0; c->n_r0 = 0;
+        c->n_huge = 0; c->n_r0 = 0;
         for (int i = 0; i <= JG_MAX_ROUNDS + 1; ++i) c->n_arr[i] = 0;
         c->best_final = 0;
         c->final_rec = -1;
         c->c_gmm = 0;
         c->c_active_emit = c->c_active_end = c->c_end_proc = c->c_arcs = c->c_entry = 0;
         c->mode = mode;
-        if (mode != JG_MODE_IDLE) c->epoch += 1;             // invalidates every arcdyn.slot of older steps
+        if (mode != JG_MODE_IDLE) c->epoch += 1;             // invalidates the state keys of older steps
         if (mode == JG_MODE_SEED) {                          // recognitionStart :139-228
             c->utt = s.w;
             c->frame = 0;
             c->error = 0;
-            c->n_cur = 0;                                    // previous utterance's instances are dropped (:148-158)
+            c->n_hw = 0; c->n_live = 0; c->n_sfree = 0;      // previous utterance's instances are dropped (:148-158):
+            c->utt_gen += 1;                                 // their slotmap entries carry the old utterance stamp
             c->n_paths = 0; c->n_free = 0; c->paths_recycled = 0;
             c->best_int = f2o(JG_LZ);
             c->best_ext = f2o(JG_LZ);
@@ -461,6 +456,7 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
             for (int dd = l; dd < d.xtile_dp; dd += 32) d.xtile[(size_t)lane * d.xtile_dp + dd] = dd < d.feat_dim ? x[dd] : 0.0f;
         }
         if (l == 0) d.lane_stamp[lane] = mode == JG_MODE_FRAME ? (int)(c->epoch & 0xffu) : 0x100;
+        if (l == 0 && lane == 0) *d.gmm_next = 0;
     }
     __syncwarp();
     {
@@ -557,10 +553,10 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
     if (tid < min(d.n_lr, JG_LR_SH)) s_lr[tid] = __ldg(d.lr + tid);
     for (int l = tid; l < L; l += blockDim.x) {
         const LaneCtl* c = d.ctl + l;
-        sh.cnt[l] = c->mode == JG_MODE_FRAME ? c->n_cur : 0;
+        sh.cnt[l] = c->mode == JG_MODE_FRAME ? min(c->n_hw, d.cap) : 0;      // slots, free ones included
         sh.f0[l] = c->norm; sh.f1[l] = c->thr_emit; sh.f2[l] = c->thr_start;
-        sh.i0[l] = c->srow; sh.i1[l] = c->flip; sh.i2[l] = c->frame;
-        sh.epoch[l] = (c->epoch & ~JG_SH_HAS_FREE) | (c->n_free > 0 ? JG_SH_HAS_FREE : 0u);
+        sh.i0[l] = c->srow; sh.i1[l] = 0; sh.i2[l] = c->frame;
+        sh.epoch[l] = (c->epoch & ~(JG_SH_HAS_FREE | JG_SH_HAS_SFREE)) | (c->n_free > 0 ? JG_SH_HAS_FREE : 0u);
     }
     const int total = chunk_scan(sh, L);
     const size_t cap = (size_t)d.cap;
@@ -575,9 +571,8 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
             const int k = (ch - sh.pref[ln]) * JG_CH + tid;
             if (k < sh.cnt[ln]) {
                 v = true;
-                const int flip = sh.i1[ln];
-                const int4* meta_cur = d.inst_meta + ((size_t)ln * 2 + flip) * cap;
-                const float4* tok_cur = d.tok + ((size_t)ln * 2 + flip) * P * cap;
+                const int4* meta_cur = d.inst_meta + (size_t)ln * cap;
+                const float4* tok_cur = d.tok + (size_t)ln * P * cap;
                 float4* dst = stage + (size_t)buf * (P + 1) * JG_THREADS + tid;
                 cp_async16(dst, meta_cur + k, l2_stream);
 #pragma unroll
@@ -641,20 +636,25 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         const int buf = it & 1;
         const float norm = sh.f0[lane], thr_emit = sh.f1[lane], thr_start = sh.f2[lane];
         const unsigned epoch = sh.epoch[lane];
-        const int flip = sh.i1[lane];
         LaneCtl* c = d.ctl + lane;
+        const int slot = (ch - sh.pref[lane]) * JG_CH + tid;  // this thread's instance slot
         // ---- registers <- buffer (chunk i) ----
-        int4 meta = make_int4(0, 0, 0, 0);
+        int4 meta = make_int4(-1, 0, 0, 0);
         float4 old[S];
 #pragma unroll
         for (int i = 0; i < S; ++i) old[i] = null_tok();
+        unsigned old_live = 0u;                               // bit i: plane i held a live token when the step began
         if (valid) {
             const float4* src = stage + (size_t)buf * (P + 1) * JG_THREADS + tid;
             meta = *reinterpret_cast<const int4*>(src);
-            old[0] = src[JG_THREADS];
-            if (!(meta.y & JG_FRESH)) {                        // a FRESH instance only has its entry token
+            valid = meta.x >= 0;                              // a free slot (its instance died earlier) is skipped
+            if (valid) {
+                old[0] = src[JG_THREADS];
+                old_live = old[0].x > JG_LZ ? 1u : 0u;
+                if (!(meta.y & JG_FRESH)) {                    // a FRESH instance only has its entry token
 #pragma unroll
-                for (int i = 1; i < P; ++i) old[i] = src[(i + 1) * JG_THREADS];
+                    for (int i = 1; i < P; ++i) { old[i] = src[(i + 1) * JG_THREADS]; old_live |= old[i].x > JG_LZ ? (1u << i) : 0u; }
+                }
             }
         }
         // ---- chunk i+2 -> the buffer just read; chunk i+1 has landed: start its hmm_info gathers ----
@@ -718,9 +718,9 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
                     res.x = res.x - norm;                                          // :408
                     if (res.x > thr_emit) {
                         const float o = outp[j - 1];                               // calcOutput :411
-                        if (d.lazy && d.frame_stats) {                             // self-check: somebody asked for this score
+                        if (d.lazy && d.frame_stats) {                             // self-check: the scorer did score this pair
                             const int gm_chk[6] = {h0.y, h0.z, h0.w, h1.y, h1.z, h1.w};
-                            if (d.need[(size_t)gm_chk[j - 1] * d.need_stride + lane] != (unsigned char)(epoch & 0xffu))
+                            if (d.scored[(size_t)lane * d.need_gp + gm_chk[j - 1]] != (unsigned char)(epoch & 0xffu))
                                 atomicOr(&c->error, JG_ERR_LAZY);
                         }
                         res.x = res.x + o;
@@ -785,7 +785,8 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         // (:497-509) is written now and the arrival record only meets the commit.  The others are listed for round 0.
         const bool to_round = FUSE && has_exit && (meta.z & (int)JG_ROUND) != 0;
         const bool need_path = FUSE && has_exit && !to_round && meta.z >= 0 && meta.w != 0;   // (MULTI: the commit writes it)
-        const unsigned m_s = __ballot_sync(0xffffffffu, survive), m_e = __ballot_sync(0xffffffffu, has_exit);
+        const bool dies = valid && !survive;                  // returnNetInst (:777-797): the slot goes back on the stack
+        const unsigned m_s = __ballot_sync(0xffffffffu, dies), m_e = __ballot_sync(0xffffffffu, has_exit);
         const unsigned m_p = __ballot_sync(0xffffffffu, need_path), m_r = __ballot_sync(0xffffffffu, to_round);
         const unsigned best_o = __reduce_max_sync(0xffffffffu, f2o(best));
         const unsigned packed = __reduce_add_sync(0xffffffffu, (unsigned)cnt_emit | ((unsigned)cnt_hist << 16));
@@ -799,14 +800,15 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         // i.e. up to five dependent round trips per chunk with the whole CTA parked at the barrier below.
         if (wid == 0) {
             const int li = lane_id();
-            if (li < 3) {                                     // lanes 0..2: next list, round-0 arrivals, round-0 work list
+            if (li < 3) {                                     // lanes 0..2: free-slot stack, round-0 arrivals, round-0 work list
                 const int col = li == 2 ? 5 : li;
                 int tot = 0;
                 for (int w = 0; w < NW; ++w) { const int a = sh_w[w][col]; sh_w[w][col] = tot; tot += a; }   // exclusive offsets of the warps
-                int* ctr = li == 0 ? &c->n_next : li == 1 ? &c->n_arr[0] : &c->n_r0;
+                int* ctr = li == 0 ? &c->n_sfree : li == 1 ? &c->n_arr[0] : &c->n_r0;
                 int base = 0;
                 if (tot) base = atomicAdd(ctr, tot);          // one predicated ATOMG for the three lanes
                 sh_base[li == 2 ? 3 : li] = base;
+                if (li == 0 && tot) atomicSub(&c->n_live, tot);
             }
         } else if (tid == 32) {                               // word-boundary records
             int np = 0;
@@ -829,17 +831,22 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         __syncthreads();
         JG_TRACE_AT(5);                                       // allocation known
         const unsigned lt = (1u << lane_id()) - 1u;
-        const int pos = sh_base[0] + sh_w[wid][0] + __popc(m_s & lt);
         const int e = sh_base[1] + sh_w[wid][1] + __popc(m_e & lt);
-        if (survive && pos < d.cap) {
-            int4* meta_nxt = d.inst_meta + ((size_t)lane * 2 + (flip ^ 1)) * cap;
-            float4* tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * P * cap;
-            st_stream(meta_nxt + pos, make_int4(meta.x, meta.y & ~JG_FRESH, meta.z, meta.w));
-            tok_nxt[pos] = null_tok();                    // entry token consumed (:426-435); k_walk<1> may overwrite it
+        if (survive) {
+            // the instance stays where it is: only what changed is written
+            int4* meta_l = d.inst_meta + (size_t)lane * cap;
+            float4* tok_l = d.tok + (size_t)lane * P * cap;
+            const bool fresh = (meta.y & JG_FRESH) != 0;
+            if (fresh) reinterpret_cast<int*>(meta_l + slot)[1] = meta.y & ~JG_FRESH;   // its emitting planes become valid now
+            if (old_live & 1u) tok_l[slot] = null_tok();      // entry token consumed (:426-435); k_walk<1> may write a new one
 #pragma unroll
             for (int i = 1; i < P; ++i)
-                if (i < nst - 1) st_stream(tok_nxt + (size_t)i * cap + pos, nt[i]);
-            d.slotmap[(size_t)lane * d.n_arcs + meta.x] = slot_entry(d, epoch, pos);
+                if (i < nst - 1 && (fresh || ((old_live >> i) & 1u) || nt[i].x > JG_LZ)) st_stream(tok_l + (size_t)i * cap + slot, nt[i]);
+        } else if (dies) {
+            reinterpret_cast<int*>(d.inst_meta + (size_t)lane * cap + slot)[0] = -1;
+            d.slotmap[(size_t)lane * d.n_arcs + meta.x] = 0u;                            // trans->hook = NULL
+            const int fpos = sh_base[0] + sh_w[wid][0] + __popc(m_s & lt);
+            d.slot_free[(size_t)lane * cap + fpos] = slot;
         }
         if (has_exit && e < d.cap_arr) {
             int via = meta.x;
@@ -938,9 +945,34 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_filter(Dev d)
 //              new FRESH instance, attachNetInst :751-774); a row's slotmap entries are
 //              contiguous, so the lookup costs one sequential read per state.
 // =========================================================================================
+// one instance slot for every thread of the warp that is here (all of the same lane): first from the stack of
+// slots freed by k_internal (it only shrinks during the commit), then from the high-water mark
+__device__ __forceinline__ int slot_alloc_here(const Dev& d, LaneCtl* c, int lane, bool has_free)
+{
+    const unsigned peers = __activemask();
+    const int leader = __ffs(peers) - 1, n = __popc(peers);
+    int from_free = 0, free_top = 0, bump = 0;
+    if (lane_id() == leader) {
+        if (has_free) {
+            const int old = atomicSub(&c->n_sfree, n);
+            from_free = min(max(old, 0), n);
+            if (from_free < n) atomicAdd(&c->n_sfree, n - from_free);      // give back what was not there
+            free_top = old;
+        }
+        if (from_free < n) bump = atomicAdd(&c->n_hw, n - from_free);
+        atomicAdd(&c->n_live, n);
+    }
+    from_free = __shfl_sync(peers, from_free, leader);
+    free_top = __shfl_sync(peers, free_top, leader);
+    bump = __shfl_sync(peers, bump, leader);
+    const int j = __popc(peers & ((1u << lane_id()) - 1u));
+    return j < from_free ? d.slot_free[(size_t)lane * d.cap + free_top - 1 - j] : bump + (j - from_free);
+}
+
+// `epoch`: the lane's step epoch with the JG_SH_* flag bits; `gen`: the lane's utterance stamp (slotmap entries)
 template <int PASS>
-__device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, unsigned epoch, float thr_end, float thr_word,
-                                            int out_round, int out_base, int flip, const float4 tok, int b, const int4 a,
+__device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, unsigned epoch, unsigned gen, float thr_end, float thr_word,
+                                            int out_round, int out_base, const float4 tok, int b, const int4 a,
                                             unsigned sm, float& best, int& n_entry)
 {
     const float w = __int_as_float(a.y);
@@ -988,17 +1020,17 @@ __device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, 
                 }
             }
             const size_t cap = (size_t)d.cap;
-            float4* tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * (size_t)(d.S - 1) * cap;
-            const int slot = slot_lookup(d, sm, epoch);
+            float4* tok_l = d.tok + (size_t)lane * (size_t)(d.S - 1) * cap;
+            const int slot = slot_lookup(d, sm, gen);
             if (slot >= 0) {
-                tok_nxt[slot] = t;                            // the instance survived the internal phase: plane 0 = entry token
+                tok_l[slot] = t;                              // the arc has a live instance: plane 0 = entry token
             } else {
-                const int pos = agg_inc(&c->n_next);
+                // attachNetInst (:751-774): a slot from the lane's stack of free slots, else a new one
+                const int pos = slot_alloc_here(d, c, lane, (epoch & JG_SH_HAS_SFREE) != 0);
                 if (pos < d.cap) {                            // overflow is flagged by k_boundary
-                    int4* meta_nxt = d.inst_meta + ((size_t)lane * 2 + (flip ^ 1)) * cap;
-                    st_stream(meta_nxt + pos, make_int4(b, (a.z - 1) | JG_FRESH, a.x, a.w));
-                    tok_nxt[pos] = t;
-                    d.slotmap[(size_t)lane * d.n_arcs + b] = slot_entry(d, epoch, pos);
+                    d.inst_meta[(size_t)lane * cap + pos] = make_int4(b, (a.z - 1) | JG_FRESH, a.x, a.w);
+                    tok_l[pos] = t;
+                    d.slotmap[(size_t)lane * d.n_arcs + b] = slot_entry(d, gen, pos);
                 }
             }
         }
@@ -1033,7 +1065,7 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
             }
         }
         sh.cnt[l] = n;
-        sh.i0[l] = rec0; sh.i1[l] = out_base; sh.i2[l] = PASS == 0 ? c->frame : c->flip;
+        sh.i0[l] = rec0; sh.i1[l] = out_base; sh.i2[l] = PASS == 0 ? c->frame : (int)c->utt_gen;
         float te = JG_LZ, tw = JG_LZ;
         if (mode == JG_MODE_FRAME) {
             const float be = o2f(c->best_int);
@@ -1046,7 +1078,8 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
             sh.f0[l] = __uint_as_float((unsigned)(bf >> 32));
             sh.f1[l] = __uint_as_float((unsigned)bf);
         }
-        sh.epoch[l] = (c->epoch & ~JG_SH_HAS_FREE) | (c->n_free > 0 ? JG_SH_HAS_FREE : 0u);
+        sh.epoch[l] = (c->epoch & ~(JG_SH_HAS_FREE | JG_SH_HAS_SFREE)) | (c->n_free > 0 ? JG_SH_HAS_FREE : 0u) |
+                      (c->n_sfree > 0 ? JG_SH_HAS_SFREE : 0u);
     }
     const int total_chunks = chunk_scan(sh, L);
     JG_TRACE_AT(0);                                           // setup done
@@ -1179,7 +1212,7 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
 #pragma unroll
             for (int u = 0; u < 2; ++u)
                 if (b[u] >= 0)
-                    process_arc<PASS>(d, lane, c, epoch, thr_end, thr_word, round + 1, out_base, sh.i2[lane], s_tok[src[u]], b[u],
+                    process_arc<PASS>(d, lane, c, epoch, (unsigned)sh.i2[lane], thr_end, thr_word, round + 1, out_base, s_tok[src[u]], b[u],
                                       a[u], sm[u], best, n_entry);
         }
         if (PASS == 1) {
@@ -1206,8 +1239,8 @@ __global__ void __launch_bounds__(JG_THREADS) k_commit_huge(Dev d)
     if (c->mode == JG_MODE_IDLE) return;
     const int n = min(c->n_huge, d.cap_huge);
     if (n == 0) return;
-    const unsigned epoch = c->epoch;
-    const int flip = c->flip;
+    const unsigned epoch = (c->epoch & ~(JG_SH_HAS_FREE | JG_SH_HAS_SFREE)) | (c->n_sfree > 0 ? JG_SH_HAS_SFREE : 0u);
+    const unsigned gen = c->utt_gen;
     int n_entry = 0;
     float best = JG_LZ;
     for (int h = 0; h < n; ++h) {
@@ -1232,7 +1265,7 @@ __global__ void __launch_bounds__(JG_THREADS) k_commit_huge(Dev d)
 #pragma unroll
             for (int u = 0; u < JG_HUGE_ILP; ++u) {
                 const int b = b0 + u * stride;
-                if (b < end) process_arc<1>(d, lane, c, epoch, JG_LZ, JG_LZ, 0, 0, flip, tok, b, a[u], sm[u], best, n_entry);
+                if (b < end) process_arc<1>(d, lane, c, epoch, gen, JG_LZ, JG_LZ, 0, 0, tok, b, a[u], sm[u], best, n_entry);
             }
         }
     }
@@ -1277,8 +1310,7 @@ __device__ __forceinline__ void gc_mark_chain(PathRec* paths, int p, int gen)
     }
 }
 
-// grid (CTAs per lane, n_lanes).  Roots: every live token of the list built by the last step (the lane's NEXT
-// buffer: k_boundary has not flipped yet) and the pending best final arrival.
+// grid (CTAs per lane, n_lanes).  Roots: every live token of the lane's instances and the pending best final arrival.
 __global__ void __launch_bounds__(JG_THREADS) k_gc_mark(Dev d)
 {
     const int lane = blockIdx.y;
@@ -1287,13 +1319,13 @@ __global__ void __launch_bounds__(JG_THREADS) k_gc_mark(Dev d)
     const int gen = c->gc_gen;
     const size_t cap = (size_t)d.cap;
     const int P = d.S - 1;
-    const int flip = c->flip ^ 1;
-    const int4* meta = d.inst_meta + ((size_t)lane * 2 + flip) * cap;
-    const float4* tok = d.tok + ((size_t)lane * 2 + flip) * P * cap;
+    const int4* meta = d.inst_meta + (size_t)lane * cap;
+    const float4* tok = d.tok + (size_t)lane * P * cap;
     PathRec* paths = d.paths + (size_t)lane * d.cap_paths;
-    const int n = min(c->n_next, d.cap);
+    const int n = min(c->n_hw, d.cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int4 m = meta[i];
+        if (m.x < 0) continue;                                // free slot
         const float4 t0 = tok[i];
         if (t0.x > JG_LZ) gc_mark_chain(paths, __float_as_int(t0.w), gen);
         if (!(m.y & JG_FRESH)) {
