@@ -104,6 +104,9 @@ struct LaneCtl {
     int paths_recycled;       // records served from the free list in this utterance (statistics)
     int c_gmm;                // (GMM, frame) scores computed for this lane in the current step (lazy scorer)
     int n_sfree;              // free instance slots on the lane's stack
+    // slot compaction (k_compact_*): after the burst of the first frames of an utterance most slots below the high-water
+    // mark are free; the live instances above the live count are then moved into the free slots below it
+    int cp_do, cp_new_hw, cp_n_mov, cp_n_hole;
     int pad_tail_[2];         // keeps sizeof(LaneCtl) off a multiple of 128 B: every CTA of every kernel reads the same
                               // fields of all lanes at start-up, and line-aligned control blocks put those hot lines on
                               // a subset of the L2 slices (measured: +4 us per kernel launch at a 384 B stride)

@@ -845,7 +845,8 @@ int launch_lazy(jgpu_handle* h)
     return JGPU_OK;
 }
 
-int launch_step(jgpu_handle* h)
+// `compact`: the slot compaction kernels run after this step's commit (every fourth step)
+int launch_step(jgpu_handle* h, bool compact)
 {
     const Dev& d = h->d;
     const dim3 grid_huge(h->bpl, d.n_lanes);
@@ -894,6 +895,13 @@ int launch_step(jgpu_handle* h)
         h->prof_end();
         ++h->launches;
     }
+    if (compact) {
+        const dim3 grid_cp(std::max(2, std::min(16, 1184 / d.n_lanes)), d.n_lanes);
+        k_compact_decide<<<(d.n_lanes + 127) / 128, 128, 0, st>>>(d);
+        k_compact_collect<<<grid_cp, JG_THREADS, 0, st>>>(d);
+        k_compact_move<<<grid_cp, JG_THREADS, 0, st>>>(d);
+        h->launches += 3;
+    }
     h->launches += 3 + d.n_rounds;
     CK(cudaGetLastError());
     return JGPU_OK;
@@ -910,7 +918,7 @@ int launch_steps_graph(jgpu_handle* h, int n)
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         const int64_t before = h->launches;
         int rc = JGPU_OK;
-        for (int i = 0; i < n && !rc; ++i) rc = launch_step(h);
+        for (int i = 0; i < n && !rc; ++i) rc = launch_step(h, n == 1 || (i & 3) == 3);
         h->launches = before;
         cudaError_t e = cudaStreamEndCapture(h->stream, &g);
         if (rc) { if (g) cudaGraphDestroy(g); return rc; }
@@ -920,7 +928,8 @@ int launch_steps_graph(jgpu_handle* h, int n)
         if (e != cudaSuccess) { exec = nullptr; return fail(JGPU_E_CUDA, "graph instantiate: %s", cudaGetErrorString(e)); }
     }
     CK(cudaGraphLaunch(exec, h->stream));
-    h->launches += (int64_t)n * (3 + h->d.n_rounds + (h->d.fuse_exits ? 0 : 1) + (h->has_huge ? 1 : 0) + (h->lazy ? 1 : 0));
+    h->launches += (int64_t)n * (3 + h->d.n_rounds + (h->d.fuse_exits ? 0 : 1) + (h->has_huge ? 1 : 0) + (h->lazy ? 1 : 0)) +
+                   3 * (n == 1 ? 1 : n / 4);
     return JGPU_OK;
 }
 
@@ -988,7 +997,7 @@ int submit_chunk(jgpu_handle* h, std::vector<int4>& chunk, int ns, bool last, co
                     if (md == JG_MODE_SEED && ((++h->host_gen[l]) & h->gen_wrap) == 0u)
                         CK(cudaMemsetAsync(h->d.slotmap + (size_t)l * d.n_arcs, 0, (size_t)d.n_arcs * sizeof(unsigned), h->stream));
                 }
-                if ((rc = graphs ? launch_steps_graph(h, 1) : launch_step(h))) return rc;
+                if ((rc = graphs ? launch_steps_graph(h, 1) : launch_step(h, true))) return rc;
             }
         }
         // word-boundary arena: mark + sweep between two frame steps, every gc_period steps (lanes whose arena

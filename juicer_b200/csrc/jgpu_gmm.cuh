@@ -363,15 +363,24 @@ __global__ void __launch_bounds__(JG_LAZY_WARPS * 32, (DP <= 40 ? 2 : 1)) k_gmm_
         // ---- rows that asked for GMM g ----
         int n = 0;
         const unsigned char* nd = a.need + g;
-        for (int l0 = 0; l0 < Lp; l0 += 32) {
-            const int l = l0 + lane;
-            const bool want = (int)nd[(size_t)l * a.need_gp] == s_stamp[l];
-            const unsigned m = __ballot_sync(0xffffffffu, want);
-            if (want) {
-                rl[n + __popc(m & ((1u << lane) - 1u))] = (unsigned short)l;
-                atomicAdd(&s_cnt[l], 1);
+        for (int lb = 0; lb < Lp; lb += 256) {                     // 8 stamp loads in flight, then the ballots
+            int st8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int l = lb + k * 32 + lane;
+                st8[k] = l < Lp ? (int)nd[(size_t)l * a.need_gp] : -1;
             }
-            n += __popc(m);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int l = lb + k * 32 + lane;
+                const bool want = l < Lp && st8[k] == s_stamp[l];
+                const unsigned m = __ballot_sync(0xffffffffu, want);
+                if (want) {
+                    rl[n + __popc(m & ((1u << lane) - 1u))] = (unsigned short)l;
+                    atomicAdd(&s_cnt[l], 1);
+                }
+                n += __popc(m);
+            }
         }
         if (n == 0) continue;
         // ---- this thread's Gaussian ----

@@ -207,13 +207,13 @@ __device__ __forceinline__ u64 state_key_of(const Dev& d, unsigned epoch, float 
     return ((u64)(epoch & d.key_emask) << (32 + d.key_id_bits)) | ((u64)f2o(score) << d.key_id_bits) | (u64)id;
 }
 
-// Lazy acoustic scoring: "state with GMM g of this lane may ask for its score in the lane's next step".  A plain
-// byte store behind a read (most marks find the stamp already there); races only ever write the same value.
+// Lazy acoustic scoring: "state with GMM g of this lane may ask for its score in the lane's next step"; races only
+// ever write the same value.
 __device__ __forceinline__ void mark_need(const Dev& d, int lane, int g, unsigned epoch)
 {
-    unsigned char* p = d.need + (size_t)lane * d.need_gp + g;
-    const unsigned char st = (unsigned char)((epoch + 1u) & 0xffu);
-    if (*p != st) *p = st;
+    // a plain fire-and-forget byte store: reading the stamp first (most are already there) put a dependent L2 round
+    // trip in front of every chunk's barrier and cost far more than the stores (measured)
+    d.need[(size_t)lane * d.need_gp + g] = (unsigned char)((epoch + 1u) & 0xffu);
 }
 
 // =========================================================================================
@@ -397,6 +397,11 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
     }
     __syncwarp();
     if (l == 0) {
+        if (c->cp_do) {                                      // a compaction ran after the last step: the slots above the live
+            c->n_hw = c->cp_new_hw;                          // count are empty now and every slot below it is live
+            c->n_sfree = 0;
+            c->cp_do = 0;
+        }
         c->n_huge = 0; c->n_r0 = 0;
         for (int i = 0; i <= JG_MAX_ROUNDS + 1; ++i) c->n_arr[i] = 0;
         c->best_final = 0;
@@ -410,6 +415,7 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
             c->frame = 0;
             c->error = 0;
             c->n_hw = 0; c->n_live = 0; c->n_sfree = 0;      // previous utterance's instances are dropped (:148-158):
+            c->cp_do = 0;
             c->utt_gen += 1;                                 // their slotmap entries carry the old utterance stamp
             c->n_paths = 0; c->n_free = 0; c->paths_recycled = 0;
             c->best_int = f2o(JG_LZ);
@@ -1369,5 +1375,76 @@ __global__ void __launch_bounds__(JG_THREADS) k_gc_sweep(Dev d)
                 paths[i].mark = JG_PATH_FREE;
             }
         }
+    }
+}
+
+// =========================================================================================
+// Slot compaction.  Instances keep their slot for life, so the slots in use only shrink when somebody moves
+// instances: the first frames of an utterance light up several times the steady-state number of instances (every
+// arc of the hub and of the first history states), and k_internal walks the slots up to the high-water mark.  When
+// the mark exceeds 1.5 x the live count (+1024), the live instances ABOVE the live count are moved into the free
+// slots BELOW it (there are exactly as many), their slotmap entries re-pointed, and the mark drops to the live
+// count.  Three small kernels after a step's commit, every fourth step; lanes that do not need it return at once.
+// Scratch: the lane's round-0 work list (free between two steps): movers at [0, cap), holes at [cap, 2 cap).
+// =========================================================================================
+__global__ void k_compact_decide(Dev d)
+{
+    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= d.n_lanes) return;
+    LaneCtl* c = d.ctl + lane;
+    const int hw = c->n_hw, live = c->n_live;
+    const bool go = c->mode != JG_MODE_IDLE && hw <= d.cap && live >= 0 && hw > live + live / 2 + 1024;
+    c->cp_do = go ? 1 : 0;
+    if (go) { c->cp_new_hw = live; c->cp_n_mov = 0; c->cp_n_hole = 0; }
+}
+
+__global__ void __launch_bounds__(JG_THREADS) k_compact_collect(Dev d)
+{
+    const int lane = blockIdx.y;
+    LaneCtl* c = d.ctl + lane;
+    if (!c->cp_do) return;
+    const int new_hw = c->cp_new_hw, hw = c->n_hw, n_free = min(c->n_sfree, d.cap);
+    const size_t cap = (size_t)d.cap;
+    const int4* meta = d.inst_meta + (size_t)lane * cap;
+    const int* stack = d.slot_free + (size_t)lane * cap;
+    int* movers = d.r0_list + (size_t)lane * d.cap_arr;
+    int* holes = movers + cap;
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i0 = new_hw; i0 < hw; i0 += stride) {            // (whole warps iterate together: warp_alloc needs them all)
+        const int i = i0 + t0;
+        const bool live = i < hw && meta[i].x >= 0;
+        const int pos = warp_alloc(&c->cp_n_mov, live);
+        if (live) movers[pos] = i;
+    }
+    for (int k0 = 0; k0 < n_free; k0 += stride) {
+        const int k = k0 + t0;
+        const int s = k < n_free ? stack[k] : 0x7fffffff;
+        const bool low = s < new_hw;
+        const int pos = warp_alloc(&c->cp_n_hole, low);
+        if (low) holes[pos] = s;
+    }
+}
+
+__global__ void __launch_bounds__(JG_THREADS) k_compact_move(Dev d)
+{
+    const int lane = blockIdx.y;
+    LaneCtl* c = d.ctl + lane;
+    if (!c->cp_do) return;
+    const size_t cap = (size_t)d.cap;
+    const int P = d.S - 1;
+    int4* meta = d.inst_meta + (size_t)lane * cap;
+    float4* tok = d.tok + (size_t)lane * P * cap;
+    const int* movers = d.r0_list + (size_t)lane * d.cap_arr;
+    const int* holes = movers + cap;
+    const int n = min(c->cp_n_mov, c->cp_n_hole);               // equal by construction
+    const unsigned gen = c->utt_gen;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int from = movers[i], to = holes[i];
+        const int4 m = meta[from];
+        meta[to] = m;
+        tok[to] = tok[from];
+        if (!(m.y & JG_FRESH))
+            for (int p = 1; p < P; ++p) tok[(size_t)p * cap + to] = tok[(size_t)p * cap + from];
+        d.slotmap[(size_t)lane * d.n_arcs + m.x] = slot_entry(d, gen, to);
     }
 }
