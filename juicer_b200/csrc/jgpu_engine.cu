@@ -501,6 +501,9 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
     if ((rc = upload(h, &d_det, det))) return rc;
     if ((rc = upload(h, &d_nc, nc))) return rc;
     G.mu = d_mu; G.iv = d_iv; G.det = d_det; G.ncomp = d_nc;
+    // one lane (the latency mode of BASELINE configs[1]): a step's stamped pairs are one feature row per GMM, which
+    // leaves the per-step scorer nothing to amortise its launch over; scoring every GMM 16 frames ahead is cheaper
+    if (h->cfg.n_lanes == 1) h->lazy = false;
     if (const char* e = getenv("JUICER_B200_DENSE")) h->lazy = atoi(e) == 0;
     if (const char* e = getenv("JUICER_B200_LAZY_CLUSTER")) h->lazy_cluster = atoi(e);
     if (h->lazy_cluster != 1 && h->lazy_cluster != 2 && h->lazy_cluster != 4) h->lazy_cluster = JG_LAZY_CLUSTER;

@@ -141,6 +141,27 @@ class OracleRef:
         self.lib.oref_gmm_scores(self.h, _fp(feats), feats.shape[0], _fp(out))
         return out
 
+    def decode_partials(self, feats: np.ndarray, every: int):
+        """Streaming partial results of the reference (tracePartialPath, src/WFSTDecoderLite.cpp:822-871) asked for
+        after every `every`-th frame: [(frame, labels, word-end frames) or (frame, None, None) when not traceable]."""
+        feats = np.ascontiguousarray(feats, dtype=np.float32)
+        T = feats.shape[0]
+        max_tr = T // max(every, 1) + 1
+        tf = np.zeros(max_tr, dtype=np.int32); tl = np.zeros(max_tr, dtype=np.int32)
+        cap = max_tr * 512
+        fl = np.zeros(cap, dtype=np.int32); ff = np.zeros(cap, dtype=np.int32)
+        self.lib.oref_decode_partial.restype = C.c_int
+        self.lib.oref_decode_partial.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int]
+        n = self.lib.oref_decode_partial(self.h, _fp(feats), T, every, max_tr, _fp(tf), _fp(tl), _fp(fl), _fp(ff), cap)
+        out, off = [], 0
+        for k in range(n):
+            if tl[k] < 0:
+                out.append((int(tf[k]), None, None))
+            else:
+                out.append((int(tf[k]), fl[off:off + tl[k]].tolist(), ff[off:off + tl[k]].tolist()))
+                off += int(tl[k])
+        return out
+
     def dump_models(self) -> Dict[str, np.ndarray]:
         H, S, G, Cc, D = self.n_hmm, self.max_states, self.n_gmm, self.max_comps, self.dim
         r = dict(hmm_nstates=np.zeros(H, np.int32), hmm_gmm=np.zeros((H, S), np.int32),

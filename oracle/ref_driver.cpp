@@ -36,6 +36,23 @@ public:
     int   cntEndProcessed()   const { return nEndHypsProcessed; }
     float best()              const { return bestEmitScore; }
     int   cntPaths()          const { return nPath; }
+#ifdef PARTIAL_DECODING
+    /* tracePartialPath (src/WFSTDecoderLite.cpp:822-871) on demand.  The reference picks, per instance, the first token
+     * with a non-NULL path by walking states[] WITHOUT a bound (:846-850): an instance none of whose tokens has a
+     * word in its history sends it past the array.  Returns -1 (and traces nothing) when such an instance exists. */
+    int partialTrace(std::vector<int>* labels, std::vector<int>* frames)
+    {
+        for (NetInst* inst = activeNetInstList; inst; inst = inst->next) {
+            bool any = false;
+            for (int i = 0; i < inst->nStates && !any; ++i) any = inst->states[i].path != NULL;
+            if (!any) return -1;
+        }
+        tracePartialPath();
+        labels->clear(); frames->clear();
+        for (size_t i = 0; i < partialPaths.size(); ++i) { labels->push_back(partialPaths[i]->label); frames->push_back(partialPaths[i]->frame); }
+        return (int)partialPaths.size();
+    }
+#endif
 };
 
 /* protected-member access: HTKFlatModels.h:43-63, HTKModels.h:139-170 */
@@ -305,6 +322,40 @@ int oref_decode(void* hv, const float* feats, int T, OrefWord* words, int maxWor
         }
     }
     return n;
+}
+
+/* Streaming partial results: decode `feats`, and after every `every`-th frame ask the reference for the path records
+ * all live hypotheses have converged on (partialPaths, src/WFSTDecoderLite.h:200).  Trace k (k < return value) was
+ * taken after frame trace_frame[k] and found trace_len[k] records (-1: not traceable, see RefDecoder::partialTrace),
+ * whose labels / frames are flat[off .. off + len) with off = sum of the earlier non-negative lengths. */
+int oref_decode_partial(void* hv, const float* feats, int T, int every, int max_traces, int* trace_frame, int* trace_len,
+                        int* flat_labels, int* flat_frames, int flat_cap)
+{
+    Handle* h = (Handle*)hv;
+    const int D = h->models->dimVec();
+    std::vector<float*> ptr(T);
+    for (int t = 0; t < T; ++t) ptr[t] = const_cast<float*>(feats) + (size_t)t * D;
+    h->dec->setPartialDecodeOptions(1 << 30);           /* the decoder keeps its list, but never traces on its own */
+    h->dec->init();
+    int n_tr = 0, off = 0;
+    std::vector<int> labels, frames;
+    for (int t = 0; t < T; ++t) {
+        h->dec->processFrame(&ptr[t], t, std::min(20, T - t));
+        if (every > 0 && (t + 1) % every == 0 && n_tr < max_traces) {
+            const int n = h->dec->partialTrace(&labels, &frames);
+            trace_frame[n_tr] = t;
+            trace_len[n_tr] = n;
+            if (n > 0) {
+                if (off + n > flat_cap) break;
+                for (int i = 0; i < n; ++i) { flat_labels[off + i] = labels[i]; flat_frames[off + i] = frames[i]; }
+                off += n;
+            }
+            ++n_tr;
+        }
+    }
+    h->dec->finish();
+    h->dec->setPartialDecodeOptions(0);
+    return n_tr;
 }
 
 } // extern "C"
