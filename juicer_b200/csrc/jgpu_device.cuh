@@ -13,13 +13,10 @@
 //                                 | states int4{first, n arcs, final weight, n_eps | n_tee << 16}
 //                                 | hmm_info 8 x i32 per HMM | trP/SE per transition-matrix class
 //                                 | GMM parameters transposed [d][comp][gmm]
-//   per lane, updated IN PLACE  : instance slots        inst_meta[cap] int4{arc (-1 = free slot), hmm | FRESH, to | MULTI, out label}
-//                                 token planes          tok[S-1][cap] float4{score,ac,lm,path}
-//                                 free slots            slot_free[cap] (a stack: deaths push, births pop)
-//                                 An instance keeps its slot from attachNetInst to returnNetInst (src/WFSTDecoderLite.cpp:
-//                                 751-797): a survivor costs one read and one write of its live tokens, nothing is re-listed.
-//   per lane, dense             : slotmap[nArcs] u32 = utterance stamp | slot + 1 — the GPU form of WFSTTransition::hook,
-//                                   written at birth, zeroed at death, void when the stamp is not the lane's utterance
+//   per lane, double buffered   : active-instance list  inst_meta[2][cap] int4{arc, hmm | FRESH, to | MULTI, out label}
+//                                 token planes          tok[2][S-1][cap] float4{score,ac,lm,path}
+//   per lane, dense             : slotmap[nArcs] u32 = epoch stamp << 20 | list position + 1 — the GPU form of
+//                                   WFSTTransition::hook, valid iff the stamp is the current epoch
 //                                 state_key[nMulti] u64 (per-state max of arriving tokens, self-cleaning), for the
 //                                   states that can see more than one arrival per frame (numbered first)
 //   per lane, per frame scratch : arrival records (token plane + {via, state, label} plane, stored round after round)
@@ -78,12 +75,10 @@ struct ResHdr {           // 32 B per utterance
 #define JG_FRESH 0x40000000   // inst_meta.y flag: only the entry token of this instance is valid
 
 struct LaneCtl {
-    int n_hw;                 // instance slots in use: slots [0, n_hw) are live or on the free list
-    int n_huge, n_paths;
-    unsigned utt_gen;         // advances with every utterance seeded on this lane: the stamp of its slotmap entries
+    int n_cur, n_huge, n_paths, flip;
     int n_r0;                 // records of round 0 that need the expansion round (fused mode: indices in r0_list)
     unsigned epoch;           // advances every non-idle step of this lane, never repeats
-    int n_live;               // live instances (births - deaths): nActiveInsts of the reference's statistics
+    int n_next;               // (n_next, n_arr[0]) sit in one aligned 64-bit word: k_internal bumps both with one atomic
     int n_arr[JG_MAX_ROUNDS + 2];    // arrivals feeding expansion round k (records are stored back to back)
     unsigned best_int;        // orderable max of emitting scores of this frame   (WFSTDecoderLite.cpp:417-418)
     unsigned best_ext;        // orderable max of entry scores of this frame      (:572-573)
@@ -103,11 +98,7 @@ struct LaneCtl {
     int gc_gen, gc_do;        // mark stamp of the collection in progress / whether this lane takes part in it
     int paths_recycled;       // records served from the free list in this utterance (statistics)
     int c_gmm;                // (GMM, frame) scores computed for this lane in the current step (lazy scorer)
-    int n_sfree;              // free instance slots on the lane's stack
-    // slot compaction (k_compact_*): after the burst of the first frames of an utterance most slots below the high-water
-    // mark are free; the live instances above the live count are then moved into the free slots below it
-    int cp_do, cp_new_hw, cp_n_mov, cp_n_hole;
-    int pad_tail_[2];         // keeps sizeof(LaneCtl) off a multiple of 128 B: every CTA of every kernel reads the same
+    int pad_tail_[3];         // keeps sizeof(LaneCtl) off a multiple of 128 B: every CTA of every kernel reads the same
                               // fields of all lanes at start-up, and line-aligned control blocks put those hot lines on
                               // a subset of the L2 slices (measured: +4 us per kernel launch at a 384 B stride)
 };
@@ -152,16 +143,14 @@ struct Dev {
     int2*     huge;            // [n_lanes][cap_huge] {state, arrival record} of hub-like rows met by k_commit
     PathRec*  paths;
     int*      path_free;       // [n_lanes][cap_paths] free list: indices of dead word-boundary records
-    int*      slot_free;       // [n_lanes][cap] stack of free instance slots
     int*      hist;
     const float* scores;       // [ring rows][n_gmms]
     // lazy acoustic scoring (HTKFlatModels::calcOutput is only ever called for states a live token asks for,
     // src/HTKFlatModels.cpp:226-262): whoever writes a token that can make a state ask for its score in the NEXT step
     // stamps need[lane][gmm] with the low byte of the lane's next epoch; k_gmm_lazy scores the stamped pairs of a
     // step between k_boundary and k_internal.  A stale stamp only costs an evaluation, so nothing is ever cleared.
-    int lazy;                  // 0: every GMM is scored for every frame, 16 frames ahead (k_gmm_scores)
-    unsigned char* need;       // [need_stride][need_gp]: a lane's stamps are one contiguous row, which the kernels that
-                               // write them (one lane per chunk) keep in L1
+    int lazy;                  // 0 (default): every GMM is scored for every frame, 16 frames ahead (k_gmm_scores)
+    unsigned char* need;       // [need_stride][need_gp]: a lane's stamps are one contiguous row
     unsigned char* scored;     // [need_stride][need_gp] (frame_stats handles only) stamp of the last step the pair was scored
     int need_stride;           // lanes rounded up to 32
     int need_gp;               // GMMs rounded up to 32
@@ -246,14 +235,14 @@ __device__ __forceinline__ float4 null_tok()
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 // slotmap entries: the GPU form of WFSTTransition::hook (src/WFSTNetwork.h:50-51), valid iff stamped with the lane's epoch
-__device__ __forceinline__ unsigned slot_entry(const Dev& d, unsigned gen, int slot)
+__device__ __forceinline__ unsigned slot_entry(const Dev& d, unsigned epoch, int pos)
 {
-    return ((gen & d.slot_emask) << d.slot_bits) | ((unsigned)slot + 1u);
+    return ((epoch & d.slot_emask) << d.slot_bits) | ((unsigned)pos + 1u);
 }
-__device__ __forceinline__ int slot_lookup(const Dev& d, unsigned sm, unsigned gen)        // slot or -1
+__device__ __forceinline__ int slot_lookup(const Dev& d, unsigned sm, unsigned epoch)     // list position or -1
 {
     const unsigned p = sm & ((1u << d.slot_bits) - 1u);
-    return ((sm >> d.slot_bits) == (gen & d.slot_emask) && p != 0u) ? (int)p - 1 : -1;
+    return ((sm >> d.slot_bits) == (epoch & d.slot_emask) && p != 0u) ? (int)p - 1 : -1;
 }
 
 // warp-aggregated slot allocation: every thread of the warp must call it

@@ -104,7 +104,8 @@ struct jgpu_handle {
     float* d_scores = nullptr;
     float* d_gmm_out = nullptr;   // jgpu_gmm_scores scratch
     // lazy scorer (k_gmm_lazy): per-component parameter rows, the per-step feature tile and the demand stamps
-    bool lazy = true;             // JUICER_B200_DENSE=1 (or more than 32 components per GMM): score everything, 16 frames ahead
+    bool lazy = false;            // JUICER_B200_LAZY=1: score only the stamped (GMM, lane) pairs, once per step (see DESIGN.md:
+                                  // measured slower than scoring everything 16 frames ahead on the BASELINE workloads)
     int lazy_cluster = JG_LAZY_CLUSTER;   // CTAs sharing one multicast feature tile (JUICER_B200_LAZY_CLUSTER = 1 | 2 | 4)
     LazyArgs lz{};
     const float** d_feat_base = nullptr;
@@ -121,9 +122,7 @@ struct jgpu_handle {
     int retry_passes = 0;                // second passes run so far (statistics)
     bool sticky = false;                 // the last batch mostly overflowed the base view: start with sticky_view
     View sticky_view{};
-    unsigned epoch_wrap = 0x7ffu;        // a lane's state keys are wiped when (epoch & epoch_wrap) == 0
-    unsigned gen_wrap = 0x7ffu;          // ... and its slotmap when (utterance stamp & gen_wrap) == 0
-    std::vector<unsigned> host_gen;      // mirror of LaneCtl::utt_gen
+    unsigned epoch_wrap = 0x7ffu;        // a lane's stamped tables are wiped when (epoch & epoch_wrap) == 0
     std::vector<LaneHost> lanes;
     int64_t launches = 0;
     JgpuStats batch_stats{};
@@ -501,10 +500,7 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
     if ((rc = upload(h, &d_det, det))) return rc;
     if ((rc = upload(h, &d_nc, nc))) return rc;
     G.mu = d_mu; G.iv = d_iv; G.det = d_det; G.ncomp = d_nc;
-    // one lane (the latency mode of BASELINE configs[1]): a step's stamped pairs are one feature row per GMM, which
-    // leaves the per-step scorer nothing to amortise its launch over; scoring every GMM 16 frames ahead is cheaper
-    if (h->cfg.n_lanes == 1) h->lazy = false;
-    if (const char* e = getenv("JUICER_B200_DENSE")) h->lazy = atoi(e) == 0;
+    if (const char* e = getenv("JUICER_B200_LAZY")) h->lazy = atoi(e) != 0;
     if (const char* e = getenv("JUICER_B200_LAZY_CLUSTER")) h->lazy_cluster = atoi(e);
     if (h->lazy_cluster != 1 && h->lazy_cluster != 2 && h->lazy_cluster != 4) h->lazy_cluster = JG_LAZY_CLUSTER;
     if (C > 32) h->lazy = false;                         // a component per thread of a warp at most
@@ -547,9 +543,9 @@ static int bits_for(unsigned long long v)     // smallest b with v < 2^b
     return b;
 }
 
-// bytes of per-lane state per instance of capacity: the slot (record + S-1 token planes + free-stack entry), the
-// arrival records (two planes) and the round-0 work list at 2 per instance
-static double bytes_per_instance(int S) { return 16.0 + 16.0 * (S - 1) + 4.0 + 2 * (32.0 + 4.0); }
+// bytes of per-lane state per instance of capacity: two list buffers (record + S-1 token planes each), the arrival
+// records (two planes) and the round-0 work list at 2 per instance
+static double bytes_per_instance(int S) { return 16.0 * 2 + 16.0 * 2 * (S - 1) + 2 * (32.0 + 4.0); }
 
 int build_state(jgpu_handle* h)
 {
@@ -593,9 +589,8 @@ int build_state(jgpu_handle* h)
     d.key_id_bits = bits_for(2ull * ((unsigned long long)d.n_arcs + 1ull) + 1ull);
     d.slot_emask = (1u << std::min(32 - d.slot_bits, 16)) - 1u;
     d.key_emask = (1u << std::min(32 - d.key_id_bits, 16)) - 1u;
-    h->epoch_wrap = d.key_emask;                            // state keys: stamped per step, wiped when the stamp wraps
-    h->gen_wrap = d.slot_emask;                             // slotmap: stamped per utterance
-    if (h->epoch_wrap < 7u || h->gen_wrap < 7u) return fail(JGPU_E_ARG, "network too large for the stamped tables: %d arcs", d.n_arcs);
+    h->epoch_wrap = std::min(d.slot_emask, d.key_emask);    // both tables are wiped when the narrower stamp wraps
+    if (h->epoch_wrap < 7u) return fail(JGPU_E_ARG, "network too large for the stamped tables: %d arcs", d.n_arcs);
     h->has_huge = h->n_huge_states > 0;
     h->bpl = std::max(2, std::min(64, (1184 + c.n_lanes - 1) / c.n_lanes));   // k_commit_huge only
     {
@@ -607,7 +602,7 @@ int build_state(jgpu_handle* h)
     }
 
     const size_t cap = d.cap, P = d.S - 1;
-    size_t need = L * (cap * 20 + P * cap * 16 + (size_t)d.n_arcs * 4 + (size_t)d.n_multi * 8 +
+    size_t need = L * (2 * cap * 16 + 2 * P * cap * 16 + (size_t)d.n_arcs * 4 + (size_t)d.n_multi * 8 +
                        (size_t)d.cap_arr * 36 + (size_t)d.cap_paths * 36);
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
@@ -628,9 +623,8 @@ int build_state(jgpu_handle* h)
     h->pool_inst = L * cap; h->pool_arr = L * (size_t)d.cap_arr; h->pool_paths = L * (size_t)d.cap_paths;
     int rc;
     if ((rc = h->alloc(&d.ctl, L))) return rc;
-    if ((rc = h->alloc(&d.inst_meta, h->pool_inst, false))) return rc;
-    if ((rc = h->alloc(&d.tok, P * h->pool_inst, false))) return rc;
-    if ((rc = h->alloc(&d.slot_free, h->pool_inst, false))) return rc;
+    if ((rc = h->alloc(&d.inst_meta, 2 * h->pool_inst, false))) return rc;
+    if ((rc = h->alloc(&d.tok, 2 * P * h->pool_inst, false))) return rc;
     if ((rc = h->alloc(&d.slotmap, L * d.n_arcs))) return rc;
     if ((rc = h->alloc(&d.state_key, L * d.n_multi))) return rc;
     if ((rc = h->alloc(&d.arr_tok, h->pool_arr, false))) return rc;
@@ -711,7 +705,6 @@ int build_state(jgpu_handle* h)
     }
     h->lanes.assign(L, LaneHost());
     h->host_epoch.assign(L, 0u);
-    h->host_gen.assign(L, 0u);
     return JGPU_OK;
 }
 
@@ -848,8 +841,7 @@ int launch_lazy(jgpu_handle* h)
     return JGPU_OK;
 }
 
-// `compact`: the slot compaction kernels run after this step's commit (every fourth step)
-int launch_step(jgpu_handle* h, bool compact)
+int launch_step(jgpu_handle* h)
 {
     const Dev& d = h->d;
     const dim3 grid_huge(h->bpl, d.n_lanes);
@@ -898,13 +890,6 @@ int launch_step(jgpu_handle* h, bool compact)
         h->prof_end();
         ++h->launches;
     }
-    if (compact) {
-        const dim3 grid_cp(std::max(2, std::min(16, 1184 / d.n_lanes)), d.n_lanes);
-        k_compact_decide<<<(d.n_lanes + 127) / 128, 128, 0, st>>>(d);
-        k_compact_collect<<<grid_cp, JG_THREADS, 0, st>>>(d);
-        k_compact_move<<<grid_cp, JG_THREADS, 0, st>>>(d);
-        h->launches += 3;
-    }
     h->launches += 3 + d.n_rounds;
     CK(cudaGetLastError());
     return JGPU_OK;
@@ -921,7 +906,7 @@ int launch_steps_graph(jgpu_handle* h, int n)
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         const int64_t before = h->launches;
         int rc = JGPU_OK;
-        for (int i = 0; i < n && !rc; ++i) rc = launch_step(h, n == 1 || (i & 3) == 3);
+        for (int i = 0; i < n && !rc; ++i) rc = launch_step(h);
         h->launches = before;
         cudaError_t e = cudaStreamEndCapture(h->stream, &g);
         if (rc) { if (g) cudaGraphDestroy(g); return rc; }
@@ -931,8 +916,7 @@ int launch_steps_graph(jgpu_handle* h, int n)
         if (e != cudaSuccess) { exec = nullptr; return fail(JGPU_E_CUDA, "graph instantiate: %s", cudaGetErrorString(e)); }
     }
     CK(cudaGraphLaunch(exec, h->stream));
-    h->launches += (int64_t)n * (3 + h->d.n_rounds + (h->d.fuse_exits ? 0 : 1) + (h->has_huge ? 1 : 0) + (h->lazy ? 1 : 0)) +
-                   3 * (n == 1 ? 1 : n / 4);
+    h->launches += (int64_t)n * (3 + h->d.n_rounds + (h->d.fuse_exits ? 0 : 1) + (h->has_huge ? 1 : 0) + (h->lazy ? 1 : 0));
     return JGPU_OK;
 }
 
@@ -968,39 +952,31 @@ int submit_chunk(jgpu_handle* h, std::vector<int4>& chunk, int ns, bool last, co
         int rc;
         if (b + 1 < n_blocks && (rc = issue_gmm(b + 1))) return rc;
         const int b0 = b * FB, nb = std::min(FB, ns - b0);
-        // a lane whose step stamp (state keys) or utterance stamp (slotmap) wraps inside this block gets that table
-        // wiped right before the step (every epoch_wrap + 1 steps / gen_wrap + 1 utterances of the lane); such a
-        // block is launched step by step
+        // a lane whose epoch stamp wraps inside this block gets its stamped tables wiped right before that
+        // step (every epoch_wrap + 1 steps: 2048 on a 2M-arc network); such a block is launched step by step
         bool wipe_in_block = false;
         {
-            std::vector<unsigned> ep(h->host_epoch), gn(h->host_gen);
+            std::vector<unsigned> ep(h->host_epoch);
             for (int i = b0; i < b0 + nb && !wipe_in_block; ++i)
-                for (int l = 0; l < L; ++l) {
-                    const int md = chunk[(size_t)i * L + l].z & 3;
-                    if (md != JG_MODE_IDLE && ((++ep[l]) & h->epoch_wrap) == 0u) { wipe_in_block = true; break; }
-                    if (md == JG_MODE_SEED && ((++gn[l]) & h->gen_wrap) == 0u) { wipe_in_block = true; break; }
-                }
+                for (int l = 0; l < L; ++l)
+                    if ((chunk[(size_t)i * L + l].z & 3) != JG_MODE_IDLE && ((++ep[l]) & h->epoch_wrap) == 0u) { wipe_in_block = true; break; }
         }
         const bool graphs = h->use_graphs && !h->prof_on && !JG_TRACING(h);
         if (graphs && nb == FB && !wipe_in_block) {
             for (int i = b0; i < b0 + nb; ++i)
-                for (int l = 0; l < L; ++l) {
-                    const int md = chunk[(size_t)i * L + l].z & 3;
-                    if (md != JG_MODE_IDLE) ++h->host_epoch[l];
-                    if (md == JG_MODE_SEED) ++h->host_gen[l];
-                }
+                for (int l = 0; l < L; ++l)
+                    if ((chunk[(size_t)i * L + l].z & 3) != JG_MODE_IDLE) ++h->host_epoch[l];
             if ((rc = launch_steps_graph(h, nb))) return rc;
         } else {
             for (int i = b0; i < b0 + nb; ++i) {
                 for (int l = 0; l < L; ++l) {
-                    const int md = chunk[(size_t)i * L + l].z & 3;
-                    if (md == JG_MODE_IDLE) continue;
-                    if (((++h->host_epoch[l]) & h->epoch_wrap) == 0u)
+                    if ((chunk[(size_t)i * L + l].z & 3) == JG_MODE_IDLE) continue;
+                    if (((++h->host_epoch[l]) & h->epoch_wrap) == 0u) {
                         CK(cudaMemsetAsync(h->d.state_key + (size_t)l * d.n_multi, 0, (size_t)d.n_multi * sizeof(u64), h->stream));
-                    if (md == JG_MODE_SEED && ((++h->host_gen[l]) & h->gen_wrap) == 0u)
                         CK(cudaMemsetAsync(h->d.slotmap + (size_t)l * d.n_arcs, 0, (size_t)d.n_arcs * sizeof(unsigned), h->stream));
+                    }
                 }
-                if ((rc = graphs ? launch_steps_graph(h, 1) : launch_step(h, true))) return rc;
+                if ((rc = graphs ? launch_steps_graph(h, 1) : launch_step(h))) return rc;
             }
         }
         // word-boundary arena: mark + sweep between two frame steps, every gc_period steps (lanes whose arena

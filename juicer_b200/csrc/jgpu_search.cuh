@@ -40,8 +40,8 @@
 // Per-lane views -------------------------------------------------------------------------
 struct LaneView {
     LaneCtl* c;
-    int4* meta;
-    float4* tok;
+    int4* meta_cur; int4* meta_nxt;
+    float4* tok_cur; float4* tok_nxt;
     unsigned* slotmap;
     u64* skey;
     float4* arr_tok; int4* arr_meta;
@@ -54,9 +54,12 @@ __device__ __forceinline__ LaneView lane_view(const Dev& d, int lane, LaneCtl* c
 {
     LaneView v;
     v.c = ctl ? ctl : d.ctl + lane;
+    const int flip = v.c->flip;
     const size_t cap = (size_t)d.cap, P = (size_t)(d.S - 1);
-    v.meta = d.inst_meta + (size_t)lane * cap;
-    v.tok = d.tok + (size_t)lane * P * cap;
+    v.meta_cur = d.inst_meta + ((size_t)lane * 2 + flip) * cap;
+    v.meta_nxt = d.inst_meta + ((size_t)lane * 2 + (flip ^ 1)) * cap;
+    v.tok_cur = d.tok + ((size_t)lane * 2 + flip) * P * cap;
+    v.tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * P * cap;
     v.slotmap = d.slotmap + (size_t)lane * d.n_arcs;
     v.skey = d.state_key + (size_t)lane * d.n_multi;
     v.arr_tok = d.arr_tok + (size_t)lane * d.cap_arr;
@@ -143,7 +146,6 @@ struct LaneSh {                   // per-CTA shared copy of what a chunk needs t
 // bit 31 of LaneSh::epoch (only the low 11 bits of the epoch are ever used as a stamp): the lane's
 // word-boundary free list was not empty when the kernel started
 #define JG_SH_HAS_FREE 0x80000000u
-#define JG_SH_HAS_SFREE 0x40000000u   // bit 30: the lane's stack of free instance slots was not empty when the kernel started
 
 // sh.cnt[] must be filled (and __syncthreads() NOT yet called); returns the number of chunks
 __device__ __forceinline__ int chunk_scan(LaneSh& sh, int L, int items = JG_CH)
@@ -208,11 +210,10 @@ __device__ __forceinline__ u64 state_key_of(const Dev& d, unsigned epoch, float 
 }
 
 // Lazy acoustic scoring: "state with GMM g of this lane may ask for its score in the lane's next step"; races only
-// ever write the same value.
+// ever write the same value.  A plain fire-and-forget byte store: reading the stamp first (most are already there)
+// put a dependent L2 round trip in front of every chunk's barrier and cost far more than the stores (measured).
 __device__ __forceinline__ void mark_need(const Dev& d, int lane, int g, unsigned epoch)
 {
-    // a plain fire-and-forget byte store: reading the stamp first (most are already there) put a dependent L2 round
-    // trip in front of every chunk's barrier and cost far more than the stores (measured)
     d.need[(size_t)lane * d.need_gp + g] = (unsigned char)((epoch + 1u) & 0xffu);
 }
 
@@ -345,9 +346,9 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
 
     // ---- (A) close the previous step ----------------------------------------------------
     if (l == 0 && prev_mode != JG_MODE_IDLE) {
-        const int n_after = c->n_live;
+        const int n_after = min(c->n_next, d.cap);
         const int n_arr_total = arr_base(c, d.n_rounds + 1);
-        if (c->n_hw > d.cap) c->error |= JG_ERR_ACTIVE;
+        if (c->n_next > d.cap) c->error |= JG_ERR_ACTIVE;
         if (n_arr_total > d.cap_arr) c->error |= JG_ERR_ARRIVALS;
         if (c->n_paths > d.cap_paths) c->error |= JG_ERR_PATHS;
         const u64 key = c->best_final;
@@ -397,26 +398,23 @@ __global__ void __launch_bounds__(32) k_boundary(Dev d)
     }
     __syncwarp();
     if (l == 0) {
-        if (c->cp_do) {                                      // a compaction ran after the last step: the slots above the live
-            c->n_hw = c->cp_new_hw;                          // count are empty now and every slot below it is live
-            c->n_sfree = 0;
-            c->cp_do = 0;
+        if (prev_mode != JG_MODE_IDLE) {                     // the list built last step becomes current
+            c->flip ^= 1;
+            c->n_cur = min(c->n_next, d.cap);
         }
-        c->n_huge = 0; c->n_r0 = 0;
+        c->n_next = 0; c->n_huge = 0; c->n_r0 = 0;
         for (int i = 0; i <= JG_MAX_ROUNDS + 1; ++i) c->n_arr[i] = 0;
         c->best_final = 0;
         c->final_rec = -1;
         c->c_gmm = 0;
         c->c_active_emit = c->c_active_end = c->c_end_proc = c->c_arcs = c->c_entry = 0;
         c->mode = mode;
-        if (mode != JG_MODE_IDLE) c->epoch += 1;             // invalidates the state keys of older steps
+        if (mode != JG_MODE_IDLE) c->epoch += 1;             // invalidates every arcdyn.slot of older steps
         if (mode == JG_MODE_SEED) {                          // recognitionStart :139-228
             c->utt = s.w;
             c->frame = 0;
             c->error = 0;
-            c->n_hw = 0; c->n_live = 0; c->n_sfree = 0;      // previous utterance's instances are dropped (:148-158):
-            c->cp_do = 0;
-            c->utt_gen += 1;                                 // their slotmap entries carry the old utterance stamp
+            c->n_cur = 0;                                    // previous utterance's instances are dropped (:148-158)
             c->n_paths = 0; c->n_free = 0; c->paths_recycled = 0;
             c->best_int = f2o(JG_LZ);
             c->best_ext = f2o(JG_LZ);
@@ -559,10 +557,10 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
     if (tid < min(d.n_lr, JG_LR_SH)) s_lr[tid] = __ldg(d.lr + tid);
     for (int l = tid; l < L; l += blockDim.x) {
         const LaneCtl* c = d.ctl + l;
-        sh.cnt[l] = c->mode == JG_MODE_FRAME ? min(c->n_hw, d.cap) : 0;      // slots, free ones included
+        sh.cnt[l] = c->mode == JG_MODE_FRAME ? c->n_cur : 0;
         sh.f0[l] = c->norm; sh.f1[l] = c->thr_emit; sh.f2[l] = c->thr_start;
-        sh.i0[l] = c->srow; sh.i1[l] = 0; sh.i2[l] = c->frame;
-        sh.epoch[l] = (c->epoch & ~(JG_SH_HAS_FREE | JG_SH_HAS_SFREE)) | (c->n_free > 0 ? JG_SH_HAS_FREE : 0u);
+        sh.i0[l] = c->srow; sh.i1[l] = c->flip; sh.i2[l] = c->frame;
+        sh.epoch[l] = (c->epoch & ~JG_SH_HAS_FREE) | (c->n_free > 0 ? JG_SH_HAS_FREE : 0u);
     }
     const int total = chunk_scan(sh, L);
     const size_t cap = (size_t)d.cap;
@@ -577,8 +575,9 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
             const int k = (ch - sh.pref[ln]) * JG_CH + tid;
             if (k < sh.cnt[ln]) {
                 v = true;
-                const int4* meta_cur = d.inst_meta + (size_t)ln * cap;
-                const float4* tok_cur = d.tok + (size_t)ln * P * cap;
+                const int flip = sh.i1[ln];
+                const int4* meta_cur = d.inst_meta + ((size_t)ln * 2 + flip) * cap;
+                const float4* tok_cur = d.tok + ((size_t)ln * 2 + flip) * P * cap;
                 float4* dst = stage + (size_t)buf * (P + 1) * JG_THREADS + tid;
                 cp_async16(dst, meta_cur + k, l2_stream);
 #pragma unroll
@@ -642,25 +641,20 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         const int buf = it & 1;
         const float norm = sh.f0[lane], thr_emit = sh.f1[lane], thr_start = sh.f2[lane];
         const unsigned epoch = sh.epoch[lane];
+        const int flip = sh.i1[lane];
         LaneCtl* c = d.ctl + lane;
-        const int slot = (ch - sh.pref[lane]) * JG_CH + tid;  // this thread's instance slot
         // ---- registers <- buffer (chunk i) ----
-        int4 meta = make_int4(-1, 0, 0, 0);
+        int4 meta = make_int4(0, 0, 0, 0);
         float4 old[S];
 #pragma unroll
         for (int i = 0; i < S; ++i) old[i] = null_tok();
-        unsigned old_live = 0u;                               // bit i: plane i held a live token when the step began
         if (valid) {
             const float4* src = stage + (size_t)buf * (P + 1) * JG_THREADS + tid;
             meta = *reinterpret_cast<const int4*>(src);
-            valid = meta.x >= 0;                              // a free slot (its instance died earlier) is skipped
-            if (valid) {
-                old[0] = src[JG_THREADS];
-                old_live = old[0].x > JG_LZ ? 1u : 0u;
-                if (!(meta.y & JG_FRESH)) {                    // a FRESH instance only has its entry token
+            old[0] = src[JG_THREADS];
+            if (!(meta.y & JG_FRESH)) {                        // a FRESH instance only has its entry token
 #pragma unroll
-                    for (int i = 1; i < P; ++i) { old[i] = src[(i + 1) * JG_THREADS]; old_live |= old[i].x > JG_LZ ? (1u << i) : 0u; }
-                }
+                for (int i = 1; i < P; ++i) old[i] = src[(i + 1) * JG_THREADS];
             }
         }
         // ---- chunk i+2 -> the buffer just read; chunk i+1 has landed: start its hmm_info gathers ----
@@ -791,8 +785,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         // (:497-509) is written now and the arrival record only meets the commit.  The others are listed for round 0.
         const bool to_round = FUSE && has_exit && (meta.z & (int)JG_ROUND) != 0;
         const bool need_path = FUSE && has_exit && !to_round && meta.z >= 0 && meta.w != 0;   // (MULTI: the commit writes it)
-        const bool dies = valid && !survive;                  // returnNetInst (:777-797): the slot goes back on the stack
-        const unsigned m_s = __ballot_sync(0xffffffffu, dies), m_e = __ballot_sync(0xffffffffu, has_exit);
+        const unsigned m_s = __ballot_sync(0xffffffffu, survive), m_e = __ballot_sync(0xffffffffu, has_exit);
         const unsigned m_p = __ballot_sync(0xffffffffu, need_path), m_r = __ballot_sync(0xffffffffu, to_round);
         const unsigned best_o = __reduce_max_sync(0xffffffffu, f2o(best));
         const unsigned packed = __reduce_add_sync(0xffffffffu, (unsigned)cnt_emit | ((unsigned)cnt_hist << 16));
@@ -806,15 +799,14 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         // i.e. up to five dependent round trips per chunk with the whole CTA parked at the barrier below.
         if (wid == 0) {
             const int li = lane_id();
-            if (li < 3) {                                     // lanes 0..2: free-slot stack, round-0 arrivals, round-0 work list
+            if (li < 3) {                                     // lanes 0..2: next list, round-0 arrivals, round-0 work list
                 const int col = li == 2 ? 5 : li;
                 int tot = 0;
                 for (int w = 0; w < NW; ++w) { const int a = sh_w[w][col]; sh_w[w][col] = tot; tot += a; }   // exclusive offsets of the warps
-                int* ctr = li == 0 ? &c->n_sfree : li == 1 ? &c->n_arr[0] : &c->n_r0;
+                int* ctr = li == 0 ? &c->n_next : li == 1 ? &c->n_arr[0] : &c->n_r0;
                 int base = 0;
                 if (tot) base = atomicAdd(ctr, tot);          // one predicated ATOMG for the three lanes
                 sh_base[li == 2 ? 3 : li] = base;
-                if (li == 0 && tot) atomicSub(&c->n_live, tot);
             }
         } else if (tid == 32) {                               // word-boundary records
             int np = 0;
@@ -837,22 +829,17 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         __syncthreads();
         JG_TRACE_AT(5);                                       // allocation known
         const unsigned lt = (1u << lane_id()) - 1u;
+        const int pos = sh_base[0] + sh_w[wid][0] + __popc(m_s & lt);
         const int e = sh_base[1] + sh_w[wid][1] + __popc(m_e & lt);
-        if (survive) {
-            // the instance stays where it is: only what changed is written
-            int4* meta_l = d.inst_meta + (size_t)lane * cap;
-            float4* tok_l = d.tok + (size_t)lane * P * cap;
-            const bool fresh = (meta.y & JG_FRESH) != 0;
-            if (fresh) reinterpret_cast<int*>(meta_l + slot)[1] = meta.y & ~JG_FRESH;   // its emitting planes become valid now
-            if (old_live & 1u) tok_l[slot] = null_tok();      // entry token consumed (:426-435); k_walk<1> may write a new one
+        if (survive && pos < d.cap) {
+            int4* meta_nxt = d.inst_meta + ((size_t)lane * 2 + (flip ^ 1)) * cap;
+            float4* tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * P * cap;
+            st_stream(meta_nxt + pos, make_int4(meta.x, meta.y & ~JG_FRESH, meta.z, meta.w));
+            tok_nxt[pos] = null_tok();                    // entry token consumed (:426-435); k_walk<1> may overwrite it
 #pragma unroll
             for (int i = 1; i < P; ++i)
-                if (i < nst - 1 && (fresh || ((old_live >> i) & 1u) || nt[i].x > JG_LZ)) st_stream(tok_l + (size_t)i * cap + slot, nt[i]);
-        } else if (dies) {
-            reinterpret_cast<int*>(d.inst_meta + (size_t)lane * cap + slot)[0] = -1;
-            d.slotmap[(size_t)lane * d.n_arcs + meta.x] = 0u;                            // trans->hook = NULL
-            const int fpos = sh_base[0] + sh_w[wid][0] + __popc(m_s & lt);
-            d.slot_free[(size_t)lane * cap + fpos] = slot;
+                if (i < nst - 1) st_stream(tok_nxt + (size_t)i * cap + pos, nt[i]);
+            d.slotmap[(size_t)lane * d.n_arcs + meta.x] = slot_entry(d, epoch, pos);
         }
         if (has_exit && e < d.cap_arr) {
             int via = meta.x;
@@ -951,34 +938,9 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_filter(Dev d)
 //              new FRESH instance, attachNetInst :751-774); a row's slotmap entries are
 //              contiguous, so the lookup costs one sequential read per state.
 // =========================================================================================
-// one instance slot for every thread of the warp that is here (all of the same lane): first from the stack of
-// slots freed by k_internal (it only shrinks during the commit), then from the high-water mark
-__device__ __forceinline__ int slot_alloc_here(const Dev& d, LaneCtl* c, int lane, bool has_free)
-{
-    const unsigned peers = __activemask();
-    const int leader = __ffs(peers) - 1, n = __popc(peers);
-    int from_free = 0, free_top = 0, bump = 0;
-    if (lane_id() == leader) {
-        if (has_free) {
-            const int old = atomicSub(&c->n_sfree, n);
-            from_free = min(max(old, 0), n);
-            if (from_free < n) atomicAdd(&c->n_sfree, n - from_free);      // give back what was not there
-            free_top = old;
-        }
-        if (from_free < n) bump = atomicAdd(&c->n_hw, n - from_free);
-        atomicAdd(&c->n_live, n);
-    }
-    from_free = __shfl_sync(peers, from_free, leader);
-    free_top = __shfl_sync(peers, free_top, leader);
-    bump = __shfl_sync(peers, bump, leader);
-    const int j = __popc(peers & ((1u << lane_id()) - 1u));
-    return j < from_free ? d.slot_free[(size_t)lane * d.cap + free_top - 1 - j] : bump + (j - from_free);
-}
-
-// `epoch`: the lane's step epoch with the JG_SH_* flag bits; `gen`: the lane's utterance stamp (slotmap entries)
 template <int PASS>
-__device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, unsigned epoch, unsigned gen, float thr_end, float thr_word,
-                                            int out_round, int out_base, const float4 tok, int b, const int4 a,
+__device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, unsigned epoch, float thr_end, float thr_word,
+                                            int out_round, int out_base, int flip, const float4 tok, int b, const int4 a,
                                             unsigned sm, float& best, int& n_entry)
 {
     const float w = __int_as_float(a.y);
@@ -1026,17 +988,17 @@ __device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, 
                 }
             }
             const size_t cap = (size_t)d.cap;
-            float4* tok_l = d.tok + (size_t)lane * (size_t)(d.S - 1) * cap;
-            const int slot = slot_lookup(d, sm, gen);
+            float4* tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * (size_t)(d.S - 1) * cap;
+            const int slot = slot_lookup(d, sm, epoch);
             if (slot >= 0) {
-                tok_l[slot] = t;                              // the arc has a live instance: plane 0 = entry token
+                tok_nxt[slot] = t;                            // the instance survived the internal phase: plane 0 = entry token
             } else {
-                // attachNetInst (:751-774): a slot from the lane's stack of free slots, else a new one
-                const int pos = slot_alloc_here(d, c, lane, (epoch & JG_SH_HAS_SFREE) != 0);
+                const int pos = agg_inc(&c->n_next);
                 if (pos < d.cap) {                            // overflow is flagged by k_boundary
-                    d.inst_meta[(size_t)lane * cap + pos] = make_int4(b, (a.z - 1) | JG_FRESH, a.x, a.w);
-                    tok_l[pos] = t;
-                    d.slotmap[(size_t)lane * d.n_arcs + b] = slot_entry(d, gen, pos);
+                    int4* meta_nxt = d.inst_meta + ((size_t)lane * 2 + (flip ^ 1)) * cap;
+                    st_stream(meta_nxt + pos, make_int4(b, (a.z - 1) | JG_FRESH, a.x, a.w));
+                    tok_nxt[pos] = t;
+                    d.slotmap[(size_t)lane * d.n_arcs + b] = slot_entry(d, epoch, pos);
                 }
             }
         }
@@ -1071,7 +1033,7 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
             }
         }
         sh.cnt[l] = n;
-        sh.i0[l] = rec0; sh.i1[l] = out_base; sh.i2[l] = PASS == 0 ? c->frame : (int)c->utt_gen;
+        sh.i0[l] = rec0; sh.i1[l] = out_base; sh.i2[l] = PASS == 0 ? c->frame : c->flip;
         float te = JG_LZ, tw = JG_LZ;
         if (mode == JG_MODE_FRAME) {
             const float be = o2f(c->best_int);
@@ -1084,8 +1046,7 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
             sh.f0[l] = __uint_as_float((unsigned)(bf >> 32));
             sh.f1[l] = __uint_as_float((unsigned)bf);
         }
-        sh.epoch[l] = (c->epoch & ~(JG_SH_HAS_FREE | JG_SH_HAS_SFREE)) | (c->n_free > 0 ? JG_SH_HAS_FREE : 0u) |
-                      (c->n_sfree > 0 ? JG_SH_HAS_SFREE : 0u);
+        sh.epoch[l] = (c->epoch & ~JG_SH_HAS_FREE) | (c->n_free > 0 ? JG_SH_HAS_FREE : 0u);
     }
     const int total_chunks = chunk_scan(sh, L);
     JG_TRACE_AT(0);                                           // setup done
@@ -1218,7 +1179,7 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
 #pragma unroll
             for (int u = 0; u < 2; ++u)
                 if (b[u] >= 0)
-                    process_arc<PASS>(d, lane, c, epoch, (unsigned)sh.i2[lane], thr_end, thr_word, round + 1, out_base, s_tok[src[u]], b[u],
+                    process_arc<PASS>(d, lane, c, epoch, thr_end, thr_word, round + 1, out_base, sh.i2[lane], s_tok[src[u]], b[u],
                                       a[u], sm[u], best, n_entry);
         }
         if (PASS == 1) {
@@ -1245,8 +1206,8 @@ __global__ void __launch_bounds__(JG_THREADS) k_commit_huge(Dev d)
     if (c->mode == JG_MODE_IDLE) return;
     const int n = min(c->n_huge, d.cap_huge);
     if (n == 0) return;
-    const unsigned epoch = (c->epoch & ~(JG_SH_HAS_FREE | JG_SH_HAS_SFREE)) | (c->n_sfree > 0 ? JG_SH_HAS_SFREE : 0u);
-    const unsigned gen = c->utt_gen;
+    const unsigned epoch = c->epoch;
+    const int flip = c->flip;
     int n_entry = 0;
     float best = JG_LZ;
     for (int h = 0; h < n; ++h) {
@@ -1271,7 +1232,7 @@ __global__ void __launch_bounds__(JG_THREADS) k_commit_huge(Dev d)
 #pragma unroll
             for (int u = 0; u < JG_HUGE_ILP; ++u) {
                 const int b = b0 + u * stride;
-                if (b < end) process_arc<1>(d, lane, c, epoch, gen, JG_LZ, JG_LZ, 0, 0, tok, b, a[u], sm[u], best, n_entry);
+                if (b < end) process_arc<1>(d, lane, c, epoch, JG_LZ, JG_LZ, 0, 0, flip, tok, b, a[u], sm[u], best, n_entry);
             }
         }
     }
@@ -1316,7 +1277,8 @@ __device__ __forceinline__ void gc_mark_chain(PathRec* paths, int p, int gen)
     }
 }
 
-// grid (CTAs per lane, n_lanes).  Roots: every live token of the lane's instances and the pending best final arrival.
+// grid (CTAs per lane, n_lanes).  Roots: every live token of the list built by the last step (the lane's NEXT
+// buffer: k_boundary has not flipped yet) and the pending best final arrival.
 __global__ void __launch_bounds__(JG_THREADS) k_gc_mark(Dev d)
 {
     const int lane = blockIdx.y;
@@ -1325,13 +1287,13 @@ __global__ void __launch_bounds__(JG_THREADS) k_gc_mark(Dev d)
     const int gen = c->gc_gen;
     const size_t cap = (size_t)d.cap;
     const int P = d.S - 1;
-    const int4* meta = d.inst_meta + (size_t)lane * cap;
-    const float4* tok = d.tok + (size_t)lane * P * cap;
+    const int flip = c->flip ^ 1;
+    const int4* meta = d.inst_meta + ((size_t)lane * 2 + flip) * cap;
+    const float4* tok = d.tok + ((size_t)lane * 2 + flip) * P * cap;
     PathRec* paths = d.paths + (size_t)lane * d.cap_paths;
-    const int n = min(c->n_hw, d.cap);
+    const int n = min(c->n_next, d.cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int4 m = meta[i];
-        if (m.x < 0) continue;                                // free slot
         const float4 t0 = tok[i];
         if (t0.x > JG_LZ) gc_mark_chain(paths, __float_as_int(t0.w), gen);
         if (!(m.y & JG_FRESH)) {
@@ -1375,76 +1337,5 @@ __global__ void __launch_bounds__(JG_THREADS) k_gc_sweep(Dev d)
                 paths[i].mark = JG_PATH_FREE;
             }
         }
-    }
-}
-
-// =========================================================================================
-// Slot compaction.  Instances keep their slot for life, so the slots in use only shrink when somebody moves
-// instances: the first frames of an utterance light up several times the steady-state number of instances (every
-// arc of the hub and of the first history states), and k_internal walks the slots up to the high-water mark.  When
-// the mark exceeds 1.5 x the live count (+1024), the live instances ABOVE the live count are moved into the free
-// slots BELOW it (there are exactly as many), their slotmap entries re-pointed, and the mark drops to the live
-// count.  Three small kernels after a step's commit, every fourth step; lanes that do not need it return at once.
-// Scratch: the lane's round-0 work list (free between two steps): movers at [0, cap), holes at [cap, 2 cap).
-// =========================================================================================
-__global__ void k_compact_decide(Dev d)
-{
-    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lane >= d.n_lanes) return;
-    LaneCtl* c = d.ctl + lane;
-    const int hw = c->n_hw, live = c->n_live;
-    const bool go = c->mode != JG_MODE_IDLE && hw <= d.cap && live >= 0 && hw > live + live / 2 + 1024;
-    c->cp_do = go ? 1 : 0;
-    if (go) { c->cp_new_hw = live; c->cp_n_mov = 0; c->cp_n_hole = 0; }
-}
-
-__global__ void __launch_bounds__(JG_THREADS) k_compact_collect(Dev d)
-{
-    const int lane = blockIdx.y;
-    LaneCtl* c = d.ctl + lane;
-    if (!c->cp_do) return;
-    const int new_hw = c->cp_new_hw, hw = c->n_hw, n_free = min(c->n_sfree, d.cap);
-    const size_t cap = (size_t)d.cap;
-    const int4* meta = d.inst_meta + (size_t)lane * cap;
-    const int* stack = d.slot_free + (size_t)lane * cap;
-    int* movers = d.r0_list + (size_t)lane * d.cap_arr;
-    int* holes = movers + cap;
-    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int i0 = new_hw; i0 < hw; i0 += stride) {            // (whole warps iterate together: warp_alloc needs them all)
-        const int i = i0 + t0;
-        const bool live = i < hw && meta[i].x >= 0;
-        const int pos = warp_alloc(&c->cp_n_mov, live);
-        if (live) movers[pos] = i;
-    }
-    for (int k0 = 0; k0 < n_free; k0 += stride) {
-        const int k = k0 + t0;
-        const int s = k < n_free ? stack[k] : 0x7fffffff;
-        const bool low = s < new_hw;
-        const int pos = warp_alloc(&c->cp_n_hole, low);
-        if (low) holes[pos] = s;
-    }
-}
-
-__global__ void __launch_bounds__(JG_THREADS) k_compact_move(Dev d)
-{
-    const int lane = blockIdx.y;
-    LaneCtl* c = d.ctl + lane;
-    if (!c->cp_do) return;
-    const size_t cap = (size_t)d.cap;
-    const int P = d.S - 1;
-    int4* meta = d.inst_meta + (size_t)lane * cap;
-    float4* tok = d.tok + (size_t)lane * P * cap;
-    const int* movers = d.r0_list + (size_t)lane * d.cap_arr;
-    const int* holes = movers + cap;
-    const int n = min(c->cp_n_mov, c->cp_n_hole);               // equal by construction
-    const unsigned gen = c->utt_gen;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int from = movers[i], to = holes[i];
-        const int4 m = meta[from];
-        meta[to] = m;
-        tok[to] = tok[from];
-        if (!(m.y & JG_FRESH))
-            for (int p = 1; p < P; ++p) tok[(size_t)p * cap + to] = tok[(size_t)p * cap + from];
-        d.slotmap[(size_t)lane * d.n_arcs + m.x] = slot_entry(d, gen, to);
     }
 }

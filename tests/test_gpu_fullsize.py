@@ -50,7 +50,9 @@ class _Ref:
 
 
 @pytest.mark.parametrize("name", ["c3", "c5"])
-def test_fullsize_config_matches_reference(name, tmp_path_factory, oracle_port_lib, product_lib):
+def test_fullsize_config_matches_reference(name, tmp_path_factory, oracle_port_lib, product_lib, monkeypatch):
+    if name == "c3":
+        monkeypatch.setenv("JUICER_B200_LAZY", "1")       # c3 also exercises the opt-in per-step scorer at full size
     m, net, tee, _ = synth.named_config(name)
     files = synth.make_fixture(name, str(tmp_path_factory.mktemp(name)), m, net)
     tabs, netl, models = flat_tables_from_files(files)

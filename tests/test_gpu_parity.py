@@ -43,8 +43,12 @@ def test_gmm_scores_match_reference_golden(case, port_lib):
     dec.close()
 
 
+@pytest.mark.parametrize("lazy", [0, 1])
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-def test_decode_matches_reference_golden(case, port_lib):
+def test_decode_matches_reference_golden(case, lazy, port_lib, monkeypatch):
+    """lazy = 1: the opt-in per-step scorer of the stamped (GMM, lane) pairs (JUICER_B200_LAZY) instead of scoring
+    every GMM 16 frames ahead; frame_stats arms its self-check."""
+    monkeypatch.setenv("JUICER_B200_LAZY", str(lazy))
     g = Golden(case)
     tabs, net, models = flat_tables_from_files(g.files)
     dec = make_decoder(net, models, g.kw, n_lanes=2, frame_stats=True)
@@ -342,13 +346,14 @@ def test_word_boundary_arena_is_garbage_collected(c2_setup):
     dec.close()
 
 
-def test_lazy_scoring_evaluates_a_tight_superset(c2_setup):
+def test_lazy_scoring_evaluates_a_tight_superset(c2_setup, monkeypatch):
     """HTKFlatModels::calcOutput is only called for states a live token asks for (src/HTKFlatModels.cpp:226-262).
-    The CUDA path scores, once per step, the (GMM, lane) pairs stamped one step ahead — a superset of what
+    With JUICER_B200_LAZY=1 the CUDA path scores, once per step, the (GMM, lane) pairs stamped one step ahead — a superset of what
     k_internal reads (its self-check, active with frame_stats, turns a missing stamp into a failed utterance) that
     must stay close to the exact set the oracle port counts, and well below scoring everything."""
     import ctypes as C
     from oracle.binding import OraclePort
+    monkeypatch.setenv("JUICER_B200_LAZY", "1")
     m, net, kw, tabs, netl, models = c2_setup
     ps = synth.PathSampler(net, m)
     x, _ = ps.sample(200, np.random.default_rng(81))
