@@ -592,7 +592,7 @@ int build_state(jgpu_handle* h)
     h->epoch_wrap = std::min(d.slot_emask, d.key_emask);    // both tables are wiped when the narrower stamp wraps
     if (h->epoch_wrap < 7u) return fail(JGPU_E_ARG, "network too large for the stamped tables: %d arcs", d.n_arcs);
     h->has_huge = h->n_huge_states > 0;
-    h->bpl = std::max(2, std::min(64, (1184 + c.n_lanes - 1) / c.n_lanes));   // k_commit_huge only
+    h->bpl = std::max(2, std::min(64, (1184 * (256 / JG_THREADS) + c.n_lanes - 1) / c.n_lanes));   // k_commit_huge only
     {
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
@@ -752,7 +752,7 @@ int set_view(jgpu_handle* h, const jgpu_handle::View& v)
     d.n_lanes = v.n_lanes; d.cap = v.cap; d.cap_arr = v.cap_arr; d.cap_paths = v.cap_paths;
     h->lz.n_lanes = v.n_lanes;
     d.gc_threshold = d.cap_paths - d.cap_paths / 4;
-    h->bpl = std::max(2, std::min(64, (1184 + v.n_lanes - 1) / v.n_lanes));
+    h->bpl = std::max(2, std::min(64, (1184 * (256 / JG_THREADS) + v.n_lanes - 1) / v.n_lanes));
     return JGPU_OK;
 }
 

@@ -18,7 +18,9 @@
 
 #include "jgpu_device.cuh"
 
+#ifndef JG_MAX_LANES
 #define JG_MAX_LANES 512
+#endif
 #ifndef JG_RUN
 #define JG_RUN 1                  // consecutive chunks of k_internal handed to one CTA (L1 reuse of per-lane tables)
 #endif

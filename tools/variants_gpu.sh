@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick A/B of library variants: tools/variants_gpu.sh "A B C" [bench args]
 for v in $1; do
-  JUICER_B200_LIB=juicer_b200/libjuicer_b200_$v.so python bench.py --workload c3 --steps 1 --warmup 1 --no-cpu-baseline ${@:2} > gpurun_out/bench_var_$v.json 2> gpurun_out/bench_var_$v.err
+  JUICER_B200_LIB=juicer_b200/libjuicer_b200_$v.so python bench.py --workload c3 --steps 2 --warmup 1 --no-cpu-baseline --no-side ${@:2} > gpurun_out/bench_var_$v.json 2> gpurun_out/bench_var_$v.err
   python - <<PY
 import json
 j = json.load(open("gpurun_out/bench_var_$v.json")); r = j["roofline"]
