@@ -178,6 +178,16 @@ int jgpu_utt_begin(jgpu_handle* h, int32_t lane);
 int jgpu_push_frames(jgpu_handle* h, int32_t lane, const float* x, int32_t n_frames);
 int jgpu_utt_end(jgpu_handle* h, int32_t lane, JgpuResult* out);
 
+/* Streaming partial result of the utterance running on `lane`, between two jgpu_push_frames calls: the
+ * word-boundary records EVERY live hypothesis has in its history — they can no longer change.  Replaces
+ * tracePartialPath / traceWinningPaths / partialPaths (src/WFSTDecoderLite.cpp:822-897, src/WFSTDecoderLite.h:200),
+ * which the reference only runs behind its path collector (:358-370) and only prints at the end (:247-257).
+ *   status >= 0 : number of converged words (words[] as in jgpu_utt_end, without final weights);
+ *   status == -1: no live hypothesis / nothing decoded yet;
+ *   status == -3: some live instance has no word in its history yet (the reference's trace walks off that
+ *                 instance's token array there, :846-850), so there is no common record. */
+int jgpu_partial_result(jgpu_handle* h, int32_t lane, JgpuResult* out);
+
 /* Whole-utterance batch: decodes n_utts independent utterances, n_lanes at a time in
  * lock-step, refilling lanes as utterances finish.  feats[u] is a HOST pointer to
  * n_frames[u]*dim floats.  Replaces the per-file loop of DecoderBatchTest::run

@@ -49,6 +49,7 @@ def load_library() -> C.CDLL:
     lib.jgpu_utt_begin.argtypes = [vp, i32]
     lib.jgpu_push_frames.argtypes = [vp, i32, vp, i32]
     lib.jgpu_utt_end.argtypes = [vp, i32, vp]
+    lib.jgpu_partial_result.argtypes = [vp, i32, vp]
     lib.jgpu_decode_batch.argtypes = [vp, vp, vp, i32, vp]
     lib.jgpu_decode_batch_device.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.jgpu_decode_queue.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
@@ -244,6 +245,13 @@ class WFSTDecoderLite:
     def process_frames(self, x: np.ndarray, lane: int = 0) -> None:
         x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, self.dim)
         _check(self.lib.jgpu_push_frames(self.h, lane, x.ctypes.data, x.shape[0]), "jgpu_push_frames")
+
+    def partial_result(self, lane: int = 0) -> Result:
+        """The words every live hypothesis of the running utterance agrees on (jgpu_partial_result)."""
+        words = (JgpuWord * self.max_words)()
+        res = JgpuResult(0, 0, 0.0, 0.0, 0.0, self.max_words, C.cast(words, C.POINTER(JgpuWord)))
+        _check(self.lib.jgpu_partial_result(self.h, lane, C.byref(res)), "jgpu_partial_result")
+        return Result(res)
 
     def finish(self, lane: int = 0) -> Result:
         words = (JgpuWord * self.max_words)()

@@ -109,6 +109,7 @@ struct jgpu_handle {
     int lazy_cluster = JG_LAZY_CLUSTER;   // CTAs sharing one multicast feature tile (JUICER_B200_LAZY_CLUSTER = 1 | 2 | 4)
     LazyArgs lz{};
     const float** d_feat_base = nullptr;
+    int* d_partial = nullptr;     // scratch of jgpu_partial_result
     int gmm_chunk = 1024;
     // results
     size_t res_cap = 0;                  // utterance headers
@@ -681,13 +682,9 @@ int build_state(jgpu_handle* h)
     {
         const int smem = 2 * h->S * JG_THREADS * (int)sizeof(float4);
         cudaError_t e = cudaSuccess;
-        if (h->S == 5) {
-            e = cudaFuncSetAttribute(k_internal<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_internal<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        } else {
-            e = cudaFuncSetAttribute(k_internal<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_internal<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        }
+        void (*kerns[8])(Dev) = {k_internal<5, true, false>, k_internal<5, false, false>, k_internal<5, true, true>, k_internal<5, false, true>,
+                                 k_internal<8, true, false>, k_internal<8, false, false>, k_internal<8, true, true>, k_internal<8, false, true>};
+        for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return fail(JGPU_E_CUDA, "k_internal shared memory opt-in: %s", cudaGetErrorString(e));
     }
     {
@@ -696,10 +693,11 @@ int build_state(jgpu_handle* h)
         int n_sm = 148, occ = 0;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
         const size_t smem_int = (size_t)2 * h->S * JG_THREADS * sizeof(float4);
-        cudaError_t e = h->S == 5 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_internal<5, true>, JG_THREADS, smem_int)
-                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_internal<8, true>, JG_THREADS, smem_int);
+        cudaError_t e = h->S == 5 ? (h->lazy ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_internal<5, true, true>, JG_THREADS, smem_int)
+                                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_internal<5, true, false>, JG_THREADS, smem_int))
+                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_internal<8, true, false>, JG_THREADS, smem_int);
         if (e == cudaSuccess && occ > 0) d.grid_internal = n_sm * occ;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_walk<1>, JG_THREADS, 0) == cudaSuccess && occ > 0) d.grid_walk = n_sm * occ;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_walk<1, false>, JG_THREADS, 0) == cudaSuccess && occ > 0) d.grid_walk = n_sm * occ;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_filter, JG_THREADS, 0) == cudaSuccess && occ > 0) d.grid_other = n_sm * occ;
         cudaGetLastError();
     }
@@ -861,13 +859,12 @@ int launch_step(jgpu_handle* h)
     h->prof_begin(JGPU_K_INTERNAL);
     {
         const size_t smem = (size_t)2 * h->S * JG_THREADS * sizeof(float4);   // two chunk buffers: record + S-1 token planes
-        if (h->S == 5) {
-            if (d.fuse_exits) k_internal<5, true><<<d.grid_internal, JG_THREADS, smem, st>>>(d);
-            else k_internal<5, false><<<d.grid_internal, JG_THREADS, smem, st>>>(d);
-        } else {
-            if (d.fuse_exits) k_internal<8, true><<<d.grid_internal, JG_THREADS, smem, st>>>(d);
-            else k_internal<8, false><<<d.grid_internal, JG_THREADS, smem, st>>>(d);
-        }
+        void (*kern)(Dev);
+        if (h->S == 5) kern = h->lazy ? (d.fuse_exits ? k_internal<5, true, true> : k_internal<5, false, true>)
+                                      : (d.fuse_exits ? k_internal<5, true, false> : k_internal<5, false, false>);
+        else kern = h->lazy ? (d.fuse_exits ? k_internal<8, true, true> : k_internal<8, false, true>)
+                            : (d.fuse_exits ? k_internal<8, true, false> : k_internal<8, false, false>);
+        kern<<<d.grid_internal, JG_THREADS, smem, st>>>(d);
     }
     h->prof_end();
     if (!d.fuse_exits) {
@@ -878,15 +875,17 @@ int launch_step(jgpu_handle* h)
     }
     for (int r = 0; r < d.n_rounds; ++r) {
         h->prof_begin(r == 0 ? JGPU_K_EXPAND : r == 1 ? JGPU_K_EXPAND_R1 : JGPU_K_EXPAND_R2);
-        k_walk<0><<<d.grid_walk, JG_THREADS, 0, st>>>(d, r);
+        k_walk<0, false><<<d.grid_walk, JG_THREADS, 0, st>>>(d, r);
         h->prof_end();
     }
     h->prof_begin(JGPU_K_COMMIT);
-    k_walk<1><<<d.grid_walk, JG_THREADS, 0, st>>>(d, 0);
+    if (h->lazy) k_walk<1, true><<<d.grid_walk, JG_THREADS, 0, st>>>(d, 0);
+    else k_walk<1, false><<<d.grid_walk, JG_THREADS, 0, st>>>(d, 0);
     h->prof_end();
     if (h->has_huge) {
         h->prof_begin(JGPU_K_EXPAND_HUGE);
-        k_commit_huge<<<grid_huge, JG_THREADS, 0, st>>>(d);
+        if (h->lazy) k_commit_huge<true><<<grid_huge, JG_THREADS, 0, st>>>(d);
+        else k_commit_huge<false><<<grid_huge, JG_THREADS, 0, st>>>(d);
         h->prof_end();
         ++h->launches;
     }
@@ -1419,6 +1418,32 @@ int jgpu_utt_end(jgpu_handle* h, int32_t lane, JgpuResult* out)
     if ((rc = run_schedule(h, sched, 0, h->d_stream_feats))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     lh.begun = false;
+    return fetch_result(h, lane, out);
+}
+
+int jgpu_partial_result(jgpu_handle* h, int32_t lane, JgpuResult* out)
+{
+    if (!h || lane < 0 || lane >= h->d.n_lanes || !out) return fail(JGPU_E_ARG, "bad argument");
+    LaneHost& lh = h->lanes[lane];
+    if (!lh.begun) return fail(JGPU_E_STATE, "partial_result on lane %d without utt_begin", lane);
+    CK(cudaSetDevice(h->device));
+    if (!lh.seeded) {                                          // nothing decoded yet
+        out->status = -1; out->n_frames = 0; out->score = out->ac = out->lm = JGPU_LOG_ZERO;
+        return JGPU_OK;
+    }
+    int rc;
+    if (!h->d_partial && (rc = h->alloc(&h->d_partial, 4))) return rc;
+    const Dev& d = h->d;
+    CK(cudaMemsetAsync(h->d_partial, 0, 4 * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(d.res_used, 0, sizeof(int), h->stream));
+    k_partial_reset<<<128, JG_THREADS, 0, h->stream>>>(d, lane, h->d_partial);
+    k_partial_count<<<128, JG_THREADS, 0, h->stream>>>(d, lane, h->d_partial);
+    k_partial_flag<<<128, JG_THREADS, 0, h->stream>>>(d, lane, h->d_partial);
+    k_partial_head<<<128, JG_THREADS, 0, h->stream>>>(d, lane, h->d_partial);
+    k_partial_emit<<<1, 1, 0, h->stream>>>(d, lane, lane, h->d_partial);
+    h->launches += 5;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
     return fetch_result(h, lane, out);
 }
 

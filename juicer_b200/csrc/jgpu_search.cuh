@@ -541,7 +541,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //                 issue chunk i+1's acoustic-score gathers (its hmm_info has landed by now)
 //                 block-wide slot allocation (2 atomics per chunk) + counters, stores of chunk i
 // so the only memory latency a chunk still waits for is that of its own two allocation atomics.
-template <int S, bool FUSE>
+// LAZY: the opt-in per-step scorer is on (demand stamps + self-check); compiled out of the default kernels, whose
+// register budget (80 at three CTAs per SM) has no room for it
+template <int S, bool FUSE, bool LAZY>
 __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_internal(Dev d)
 {
     JG_TRACE_SCOPE(JGPU_K_INTERNAL, 0);
@@ -720,7 +722,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
                     res.x = res.x - norm;                                          // :408
                     if (res.x > thr_emit) {
                         const float o = outp[j - 1];                               // calcOutput :411
-                        if (d.lazy && d.frame_stats) {                             // self-check: the scorer did score this pair
+                        if (LAZY && d.frame_stats) {                               // self-check: the scorer did score this pair
                             const int gm_chk[6] = {h0.y, h0.z, h0.w, h1.y, h1.z, h1.w};
                             if (d.scored[(size_t)lane * d.need_gp + gm_chk[j - 1]] != (unsigned char)(epoch & 0xffu))
                                 atomicOr(&c->error, JG_ERR_LAZY);
@@ -755,7 +757,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
                 if (res.x > JG_LZ) { ex = res; has_exit = true; ++cnt_end; }
             }
         }
-        if (d.lazy && survive) {
+        if (LAZY && survive) {
             // which states can ask for their score next step: state j when one of its predecessors holds a live token
             // (left-to-right: j - 1 or j); other topologies stamp every emitting state of a surviving instance
             const int gm_now[6] = {h0.y, h0.z, h0.w, h1.y, h1.z, h1.w};
@@ -940,7 +942,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_filter(Dev d)
 //              new FRESH instance, attachNetInst :751-774); a row's slotmap entries are
 //              contiguous, so the lookup costs one sequential read per state.
 // =========================================================================================
-template <int PASS>
+template <int PASS, bool LAZY>
 __device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, unsigned epoch, float thr_end, float thr_word,
                                             int out_round, int out_base, int flip, const float4 tok, int b, const int4 a,
                                             unsigned sm, float& best, int& n_entry)
@@ -980,7 +982,7 @@ __device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, 
             const float4 t = make_float4(s, tok.y, tok.z + w, tok.w);   // :568-570
             if (s > best) best = s;
             ++n_entry;
-            if (d.lazy) {                                     // the entry token makes the model's first state(s) ask
+            if (LAZY) {                                       // the entry token makes the model's first state(s) ask
                 const int g1 = __ldg(d.arc_g1 + b);
                 if (g1 >= 0) mark_need(d, lane, g1, epoch);
                 else {
@@ -1007,7 +1009,7 @@ __device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, 
     }
 }
 
-template <int PASS>
+template <int PASS, bool LAZY>
 __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int round)
 {
     JG_TRACE_SCOPE(PASS ? JGPU_K_COMMIT : JGPU_K_EXPAND, round);
@@ -1181,7 +1183,7 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
 #pragma unroll
             for (int u = 0; u < 2; ++u)
                 if (b[u] >= 0)
-                    process_arc<PASS>(d, lane, c, epoch, thr_end, thr_word, round + 1, out_base, sh.i2[lane], s_tok[src[u]], b[u],
+                    process_arc<PASS, LAZY>(d, lane, c, epoch, thr_end, thr_word, round + 1, out_base, sh.i2[lane], s_tok[src[u]], b[u],
                                       a[u], sm[u], best, n_entry);
         }
         if (PASS == 1) {
@@ -1200,6 +1202,7 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
 }
 
 // hub-like rows met by the commit: all CTAs of the lane stride over the row.
+template <bool LAZY>
 __global__ void __launch_bounds__(JG_THREADS) k_commit_huge(Dev d)
 {
     JG_TRACE_SCOPE(JGPU_K_EXPAND_HUGE, 0);
@@ -1234,7 +1237,7 @@ __global__ void __launch_bounds__(JG_THREADS) k_commit_huge(Dev d)
 #pragma unroll
             for (int u = 0; u < JG_HUGE_ILP; ++u) {
                 const int b = b0 + u * stride;
-                if (b < end) process_arc<1>(d, lane, c, epoch, JG_LZ, JG_LZ, 0, 0, flip, tok, b, a[u], sm[u], best, n_entry);
+                if (b < end) process_arc<1, LAZY>(d, lane, c, epoch, JG_LZ, JG_LZ, 0, 0, flip, tok, b, a[u], sm[u], best, n_entry);
             }
         }
     }
@@ -1340,4 +1343,103 @@ __global__ void __launch_bounds__(JG_THREADS) k_gc_sweep(Dev d)
             }
         }
     }
+}
+
+// =========================================================================================
+// Streaming partial results — tracePartialPath / traceWinningPaths (src/WFSTDecoderLite.cpp:822-897) on demand.
+// The word-boundary records every live hypothesis has in its history can no longer change; the reference finds
+// the newest of them by walking back from one token per active instance (the first one that has a path, :843-850)
+// and counting visits per record (jointCount == nActiveInsts, :853-855).  Same here, for one lane between two
+// steps (jgpu_partial_result): reset the counters, count, find the newest common record, write its chain out.
+// scratch[0] = roots (instances), [1] = an instance without any word in its history (the reference walks off its
+// token array there, :846-850: reported as "not traceable"), [2] = head record + 1.
+// =========================================================================================
+#define JG_PT_FLAG 0x40000000
+
+__global__ void k_partial_reset(Dev d, int lane, int* scratch)
+{
+    const LaneCtl* c = d.ctl + lane;
+    PathRec* paths = d.paths + (size_t)lane * d.cap_paths;
+    const int n = min(c->n_paths, d.cap_paths);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) paths[i].pad1 = 0;
+}
+
+__global__ void k_partial_count(Dev d, int lane, int* scratch)
+{
+    const LaneCtl* c = d.ctl + lane;
+    const size_t cap = (size_t)d.cap;
+    const int P = d.S - 1;
+    const int flip = c->flip ^ 1;                             // the list the last step built (k_boundary has not flipped yet)
+    const int4* meta = d.inst_meta + ((size_t)lane * 2 + flip) * cap;
+    const float4* tok = d.tok + ((size_t)lane * 2 + flip) * P * cap;
+    PathRec* paths = d.paths + (size_t)lane * d.cap_paths;
+    const int n = min(c->n_next, d.cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 m = meta[i];
+        const int nst = (m.y & JG_FRESH) ? 2 : (__ldg(d.hmm_info + (size_t)(m.y & ~JG_FRESH) * 8) & 0xff);
+        int root = -1;
+        bool live = false;
+        for (int p = 0; p < nst - 1 && p < P && root < 0; ++p) {
+            const float4 t = tok[(size_t)p * cap + i];
+            if (t.x > JG_LZ) { live = true; if (__float_as_int(t.w) >= 0) root = __float_as_int(t.w); }
+        }
+        if (!live) continue;                                  // (cannot happen for a listed instance)
+        atomicAdd(&scratch[0], 1);
+        if (root < 0) { scratch[1] = 1; continue; }
+        for (int p = root; p >= 0; p = paths[p].prev) atomicAdd(&paths[p].pad1, 1);
+    }
+}
+
+// a record every root passes through flags its predecessor: the newest common record is the one nobody flags
+__global__ void k_partial_flag(Dev d, int lane, int* scratch)
+{
+    const LaneCtl* c = d.ctl + lane;
+    PathRec* paths = d.paths + (size_t)lane * d.cap_paths;
+    const int n = min(c->n_paths, d.cap_paths), roots = scratch[0];
+    if (roots == 0 || scratch[1]) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if ((paths[i].pad1 & ~JG_PT_FLAG) == roots && paths[i].mark != JG_PATH_FREE && paths[i].prev >= 0)
+            atomicOr(&paths[paths[i].prev].pad1, JG_PT_FLAG);
+}
+
+__global__ void k_partial_head(Dev d, int lane, int* scratch)
+{
+    const LaneCtl* c = d.ctl + lane;
+    const PathRec* paths = d.paths + (size_t)lane * d.cap_paths;
+    const int n = min(c->n_paths, d.cap_paths), roots = scratch[0];
+    if (roots == 0 || scratch[1]) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (paths[i].pad1 == roots && paths[i].mark != JG_PATH_FREE) scratch[2] = i + 1;      // common and not flagged: unique
+}
+
+__global__ void k_partial_emit(Dev d, int lane, int slot, int* scratch)
+{
+    const LaneCtl* c = d.ctl + lane;
+    const PathRec* paths = d.paths + (size_t)lane * d.cap_paths;
+    ResHdr h;
+    h.status = 0; h.n_frames = c->frame; h.score = h.ac = h.lm = JG_LZ; h.error = 0; h.word_off = 0; h.n_words = 0;
+    if (scratch[0] == 0) h.status = -1;                        // no live hypothesis
+    else if (scratch[1]) h.status = -3;                        // not traceable (see above)
+    else if (scratch[2] > 0) {
+        const int head = scratch[2] - 1;
+        int n = 0;
+        for (int p = head; p >= 0; p = paths[p].prev) ++n;
+        const int off = atomicAdd(d.res_used, n);
+        h.n_words = n;
+        if (off + n > d.res_words_cap) { h.error = JG_ERR_WORDS; h.status = JGPU_E_CAPACITY - 10 - (JG_ERR_WORDS << 8); }
+        else {
+            h.status = n; h.word_off = off;
+            const PathRec r0 = paths[head];
+            h.score = r0.score; h.ac = r0.ac; h.lm = r0.lm;
+            int k = n;
+            for (int p = head; p >= 0; p = paths[p].prev) {
+                --k;
+                const PathRec r = paths[p];
+                JgpuWord o;
+                o.label = r.label; o.time = r.frame; o.score = r.score; o.ac = r.ac; o.lm = r.lm;
+                d.res_words[off + k] = o;
+            }
+        }
+    }
+    d.res_hdr[slot] = h;
 }

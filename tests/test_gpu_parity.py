@@ -372,3 +372,41 @@ def test_lazy_scoring_evaluates_a_tight_superset(c2_setup, monkeypatch):
     assert evals <= 1.02 * superset + 64, (exact, superset, evals, dense)
     assert evals < 0.9 * dense, (exact, superset, evals, dense)
     dec.close(); p.close()
+
+
+def test_streaming_partial_results_match_reference(tmp_path, port_lib):
+    """jgpu_partial_result vs tracePartialPath (src/WFSTDecoderLite.cpp:822-897) of the unmodified reference, asked
+    after every 10th frame of a c2 utterance: the converged words and their end frames are identical, and where the
+    reference cannot trace (an instance without any word in its history) the CUDA path says so."""
+    import os
+    from oracle import binding
+    if not os.path.exists(binding.REF_SO):
+        pytest.skip("oracle/_ref did not travel to this box")
+    m, net, tee, kw = synth.named_config("c2")
+    files = synth.make_fixture("c2", str(tmp_path), m, net)
+    tabs, netl, models = flat_tables_from_files(files)
+    x, words = synth.PathSampler(net, m).sample(240, np.random.default_rng(90))
+    ref = binding.OracleRef(files, **kw)
+    want = ref.decode_partials(x, 10)
+    assert sum(1 for _, lab, _ in want if lab) >= 5                  # the utterance does converge along the way
+    dec = make_decoder(netl, models, kw, n_lanes=2)
+    dec.init(1)
+    assert dec.partial_result(1).status == -1                        # nothing decoded yet
+    k = 0
+    for t0 in range(0, x.shape[0], 10):
+        dec.process_frames(x[t0:t0 + 10], lane=1)
+        if t0 + 10 > x.shape[0]:
+            break
+        frame, labels, frames = want[k]
+        assert frame == t0 + 9
+        got = dec.partial_result(1)
+        if labels is None:
+            assert got.status == -3, (frame, got)
+        else:
+            assert got.status == len(labels) and got.labels == labels and got.times == frames, (frame, labels, frames, got)
+        k += 1
+    final = dec.finish(1)
+    assert final.labels == words
+    last = [w for w in want if w[1]][-1]
+    assert final.labels[: len(last[1])] == last[1]                   # the partial results are a prefix of the final one
+    dec.close(); ref.close()
