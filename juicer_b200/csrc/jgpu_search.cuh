@@ -1369,11 +1369,11 @@ __global__ void k_partial_count(Dev d, int lane, int* scratch)
     const LaneCtl* c = d.ctl + lane;
     const size_t cap = (size_t)d.cap;
     const int P = d.S - 1;
-    const int flip = c->flip ^ 1;                             // the list the last step built (k_boundary has not flipped yet)
-    const int4* meta = d.inst_meta + ((size_t)lane * 2 + flip) * cap;
+    const int flip = c->flip;                                 // the streaming interface ends every call with the closing
+    const int4* meta = d.inst_meta + ((size_t)lane * 2 + flip) * cap;      // k_boundary, which has made the last step's list current
     const float4* tok = d.tok + ((size_t)lane * 2 + flip) * P * cap;
     PathRec* paths = d.paths + (size_t)lane * d.cap_paths;
-    const int n = min(c->n_next, d.cap);
+    const int n = min(c->n_cur, d.cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int4 m = meta[i];
         const int nst = (m.y & JG_FRESH) ? 2 : (__ldg(d.hmm_info + (size_t)(m.y & ~JG_FRESH) * 8) & 0xff);
