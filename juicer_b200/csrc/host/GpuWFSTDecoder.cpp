@@ -1,5 +1,6 @@
 // GpuWFSTDecoder.cpp — see GpuWFSTDecoder.h.
 #include "GpuWFSTDecoder.h"
+#include "LogFile.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -119,6 +120,10 @@ namespace Juicer
         cfg.device = dev ? atoi(dev) : 0;
         if (jgpu_create(&net, &hm, &gm, &cfg, &handle) != JGPU_OK)
             error("GpuWFSTDecoder - %s", jgpu_last_error());        // Torch error(): message + exit, like the reference
+        const char* pti = getenv("PartialTraceInterval");        // src/WFSTDecoderLite.cpp:117
+        partialTraceInterval = 0;
+        lastPartialTraceFrame = -1;
+        setPartialDecodeOptions(pti ? atoi(pti) : 0);
         pending.resize((size_t)kBlockFrames * vecSize);
         words.resize(65536);       // the device side has no per-utterance word limit; this is the host buffer
     }
@@ -129,8 +134,28 @@ namespace Juicer
         jgpu_destroy(handle);
     }
 
+    void GpuWFSTDecoder::setPartialDecodeOptions(int traceInterval)
+    {
+        partialTraceInterval = traceInterval > 0 ? traceInterval : 0;
+        LogFile::printf("WFSTDecoderLite::partialTraceInterval = %d frames\n", partialTraceInterval);   // :893-897
+    }
+
+    // the words every live hypothesis has in its history (tracePartialPath, src/WFSTDecoderLite.cpp:822-871)
+    void GpuWFSTDecoder::tracePartial()
+    {
+        JgpuResult res;
+        memset(&res, 0, sizeof(res));
+        res.max_words = (int)words.size();
+        res.words = words.data();
+        if (jgpu_partial_result(handle, 0, &res) != JGPU_OK) error("GpuWFSTDecoder::tracePartial - %s", jgpu_last_error());
+        if (res.status > 0) partialWords.assign(words.begin(), words.begin() + (res.status < res.max_words ? res.status : res.max_words));
+        lastPartialTraceFrame = nextFrame - 1;
+    }
+
     void GpuWFSTDecoder::init()
     {
+        partialWords.clear();
+        lastPartialTraceFrame = -1;
         delete bestDecHyp;                   // result of the last utterance stays valid until here
         bestDecHyp = NULL;
         hist.clear();
@@ -156,7 +181,10 @@ namespace Juicer
         memcpy(&pending[(size_t)nPending * vecSize], inputVec[0], sizeof(float) * vecSize);
         ++nPending;
         ++nextFrame;
-        if (nPending == kBlockFrames) flush();                       // launches asynchronously
+        if (nPending == kBlockFrames) {
+            flush();                                                 // launches asynchronously
+            if (partialTraceInterval > 0 && nextFrame - 1 - lastPartialTraceFrame > partialTraceInterval) tracePartial();
+        }
     }
 
     DecHyp* GpuWFSTDecoder::finish()
@@ -168,6 +196,12 @@ namespace Juicer
         res.words = words.data();
         if (jgpu_utt_end(handle, 0, &res) != JGPU_OK) error("GpuWFSTDecoder::finish - %s", jgpu_last_error());
         if (res.status <= -10) error("GpuWFSTDecoder::finish - device arena overflow (status %d)", res.status);
+        if (partialTraceInterval > 0) {                              // :246-257: the last trace runs from the best token
+            if (res.status > 0) partialWords.assign(words.begin(), words.begin() + (res.status < res.max_words ? res.status : res.max_words));
+            LogFile::printf("Partial paths recovered at frames: ");
+            for (size_t k = 0; k < partialWords.size(); ++k) LogFile::printf("%03d ", partialWords[k].time);
+            LogFile::printf("\n");
+        }
         if (res.status == -1) {
             fprintf(stderr, "WARNING: no token survived at the end of decoding\n");   // src/WFSTDecoderLite.cpp:264-267
             return NULL;

@@ -46,6 +46,13 @@ namespace Juicer
         // work counters of the last utterance (reference prints them at src/WFSTDecoderLite.cpp:231-241)
         JgpuStats stats();
 
+        // Streaming partial results (PARTIAL_DECODING, src/WFSTDecoderLite.h:196-206): same switch as the reference —
+        // setPartialDecodeOptions(n) or the environment variable PartialTraceInterval.  With n > 0 the decoder asks the
+        // device every n frames for the words all live hypotheses agree on (partialResult() returns the latest answer)
+        // and finish() prints "Partial paths recovered at frames: ..." like src/WFSTDecoderLite.cpp:247-257.
+        void setPartialDecodeOptions(int traceInterval);
+        const std::vector<JgpuWord>& partialResult() const { return partialWords; }
+
     private:
         jgpu_handle* handle;
         int vecSize;
@@ -57,6 +64,9 @@ namespace Juicer
         DecHyp* bestDecHyp;
 
         void flush();
+        int partialTraceInterval, lastPartialTraceFrame;
+        std::vector<JgpuWord> partialWords;  // converged prefix at the last trace
+        void tracePartial();
     };
 }
 
