@@ -135,6 +135,7 @@ struct Dev {
     LaneCtl*  ctl;
     int4*     inst_meta;
     float4*   tok;
+    unsigned char* live;       // [n_lanes][2][cap] per instance: bit i = emitting-state plane i holds a live token
     unsigned* slotmap;
     u64*      state_key;
     float4*   arr_tok;         // arrival records, two planes: token | {via arc (-1 seed, -2 dropped), state | JG_MULTI, out label, -}

@@ -546,7 +546,7 @@ static int bits_for(unsigned long long v)     // smallest b with v < 2^b
 
 // bytes of per-lane state per instance of capacity: two list buffers (record + S-1 token planes each), the arrival
 // records (two planes) and the round-0 work list at 2 per instance
-static double bytes_per_instance(int S) { return 16.0 * 2 + 16.0 * 2 * (S - 1) + 2 * (32.0 + 4.0); }
+static double bytes_per_instance(int S) { return 16.0 * 2 + 16.0 * 2 * (S - 1) + 2.0 + 2 * (32.0 + 4.0); }
 
 int build_state(jgpu_handle* h)
 {
@@ -626,6 +626,7 @@ int build_state(jgpu_handle* h)
     if ((rc = h->alloc(&d.ctl, L))) return rc;
     if ((rc = h->alloc(&d.inst_meta, 2 * h->pool_inst, false))) return rc;
     if ((rc = h->alloc(&d.tok, 2 * P * h->pool_inst, false))) return rc;
+    if ((rc = h->alloc(&d.live, 2 * h->pool_inst))) return rc;
     if ((rc = h->alloc(&d.slotmap, L * d.n_arcs))) return rc;
     if ((rc = h->alloc(&d.state_key, L * d.n_multi))) return rc;
     if ((rc = h->alloc(&d.arr_tok, h->pool_arr, false))) return rc;

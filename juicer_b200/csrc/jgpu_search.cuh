@@ -572,8 +572,18 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
     const int G = gridDim.x;
     const u64 l2_stream = l2_evict_first_policy();
 
-    // copies of chunk `ch` (lane `ln`) into buffer `buf`; returns whether this thread has an instance there
-    auto issue = [&](int ch, int ln, int buf) -> bool {
+    // Which emitting-state planes of an instance hold a live token is one byte per instance (Dev::live, written by
+    // whoever listed the instance): only those planes are copied — on c3 1.7 of 3 — and only those are written back.
+    __shared__ unsigned char s_mask[2][JG_THREADS];           // the mask the copies of a staged chunk were issued with
+    auto live_of = [&](int ch, int ln) -> unsigned {
+        if (ch >= total) return 0u;
+        const int k = (ch - sh.pref[ln]) * JG_CH + tid;
+        if (k >= sh.cnt[ln]) return 0u;
+        return d.live[((size_t)ln * 2 + sh.i1[ln]) * cap + k];
+    };
+    // copies of chunk `ch` (lane `ln`) into buffer `buf`: record, entry token and the planes in `mask`; returns whether
+    // this thread has an instance there
+    auto issue = [&](int ch, int ln, int buf, unsigned mask) -> bool {
         bool v = false;
         if (ch < total) {
             const int k = (ch - sh.pref[ln]) * JG_CH + tid;
@@ -584,8 +594,11 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
                 const float4* tok_cur = d.tok + ((size_t)ln * 2 + flip) * P * cap;
                 float4* dst = stage + (size_t)buf * (P + 1) * JG_THREADS + tid;
                 cp_async16(dst, meta_cur + k, l2_stream);
+                cp_async16(dst + JG_THREADS, tok_cur + k, l2_stream);
 #pragma unroll
-                for (int i = 0; i < P; ++i) cp_async16(dst + (i + 1) * JG_THREADS, tok_cur + (size_t)i * cap + k, l2_stream);
+                for (int i = 1; i < P; ++i)
+                    if ((mask >> i) & 1u) cp_async16(dst + (i + 1) * JG_THREADS, tok_cur + (size_t)i * cap + k, l2_stream);
+                s_mask[buf][tid] = (unsigned char)mask;
             }
         }
         cp_async_commit();
@@ -620,9 +633,14 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
 
     int ch = chunk_of(0);
     int lane = lane_of(0, ch, 0);
-    int lane1 = lane_of(1, chunk_of(1), lane), lane2 = lane1;
-    bool valid = issue(ch, lane, 0);
-    bool valid1 = issue(chunk_of(1), lane1, 1);
+    int lane1 = lane_of(1, chunk_of(1), lane), lane2 = lane_of(2, chunk_of(2), lane1);
+    bool valid, valid1;
+    {
+        const unsigned m0 = live_of(ch, lane), m1 = live_of(chunk_of(1), lane1);
+        valid = issue(ch, lane, 0, m0);
+        valid1 = issue(chunk_of(1), lane1, 1, m1);
+    }
+    unsigned mask_ahead = live_of(chunk_of(2), lane2);        // always one chunk ahead of the copies it steers
     // hmm_info + scores of the first chunk (exposed once per CTA)
     int4 h0 = make_int4(2, 0, 0, 0), h1 = make_int4(0, 0, 0, 0);
     float outp[S - 2];
@@ -656,15 +674,19 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
             const float4* src = stage + (size_t)buf * (P + 1) * JG_THREADS + tid;
             meta = *reinterpret_cast<const int4*>(src);
             old[0] = src[JG_THREADS];
-            if (!(meta.y & JG_FRESH)) {                        // a FRESH instance only has its entry token
+            const unsigned mask = s_mask[buf][tid];            // (0 for a FRESH instance: only its entry token exists)
 #pragma unroll
-                for (int i = 1; i < P; ++i) old[i] = src[(i + 1) * JG_THREADS];
-            }
+            for (int i = 1; i < P; ++i)
+                if ((mask >> i) & 1u) old[i] = src[(i + 1) * JG_THREADS];
         }
         // ---- chunk i+2 -> the buffer just read; chunk i+1 has landed: start its hmm_info gathers ----
         const int ch2 = chunk_of(it + 2);
         lane2 = lane_of(it + 2, ch2, lane1);
-        const bool valid2 = issue(ch2, lane2, buf);
+        const bool valid2 = issue(ch2, lane2, buf, mask_ahead);
+        {
+            const int ch3 = chunk_of(it + 3);
+            mask_ahead = live_of(ch3, lane_of(it + 3, ch3, lane2));
+        }
         JG_TRACE_AT(1);                                       // registers loaded, next copies issued
         cp_async_wait<1>();
         JG_TRACE_AT(2);                                       // chunk i+1 landed
@@ -840,9 +862,11 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
             float4* tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * P * cap;
             st_stream(meta_nxt + pos, make_int4(meta.x, meta.y & ~JG_FRESH, meta.z, meta.w));
             tok_nxt[pos] = null_tok();                    // entry token consumed (:426-435); k_walk<1> may overwrite it
+            unsigned nm = 0u;
 #pragma unroll
             for (int i = 1; i < P; ++i)
-                if (i < nst - 1) st_stream(tok_nxt + (size_t)i * cap + pos, nt[i]);
+                if (i < nst - 1 && nt[i].x > JG_LZ) { st_stream(tok_nxt + (size_t)i * cap + pos, nt[i]); nm |= 1u << i; }
+            d.live[((size_t)lane * 2 + (flip ^ 1)) * cap + pos] = (unsigned char)nm;
             d.slotmap[(size_t)lane * d.n_arcs + meta.x] = slot_entry(d, epoch, pos);
         }
         if (has_exit && e < d.cap_arr) {
@@ -1002,6 +1026,7 @@ __device__ __forceinline__ void process_arc(const Dev& d, int lane, LaneCtl* c, 
                     int4* meta_nxt = d.inst_meta + ((size_t)lane * 2 + (flip ^ 1)) * cap;
                     st_stream(meta_nxt + pos, make_int4(b, (a.z - 1) | JG_FRESH, a.x, a.w));
                     tok_nxt[pos] = t;
+                    d.live[((size_t)lane * 2 + (flip ^ 1)) * cap + pos] = 0;     // no emitting plane holds a token yet
                     d.slotmap[(size_t)lane * d.n_arcs + b] = slot_entry(d, epoch, pos);
                 }
             }
@@ -1301,13 +1326,9 @@ __global__ void __launch_bounds__(JG_THREADS) k_gc_mark(Dev d)
         const int4 m = meta[i];
         const float4 t0 = tok[i];
         if (t0.x > JG_LZ) gc_mark_chain(paths, __float_as_int(t0.w), gen);
-        if (!(m.y & JG_FRESH)) {
-            const int nst = __ldg(d.hmm_info + (size_t)(m.y & ~JG_FRESH) * 8) & 0xff;
-            for (int j = 1; j < nst - 1 && j < P; ++j) {
-                const float4 t = tok[(size_t)j * cap + i];
-                if (t.x > JG_LZ) gc_mark_chain(paths, __float_as_int(t.w), gen);
-            }
-        }
+        const unsigned lv = d.live[((size_t)lane * 2 + flip) * cap + i];   // planes that hold a live token
+        for (int j = 1; j < P; ++j)
+            if ((lv >> j) & 1u) gc_mark_chain(paths, __float_as_int(tok[(size_t)j * cap + i].w), gen);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         // the pending best final arrival (resolved by the next k_boundary)
@@ -1375,11 +1396,11 @@ __global__ void k_partial_count(Dev d, int lane, int* scratch)
     PathRec* paths = d.paths + (size_t)lane * d.cap_paths;
     const int n = min(c->n_cur, d.cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int4 m = meta[i];
-        const int nst = (m.y & JG_FRESH) ? 2 : (__ldg(d.hmm_info + (size_t)(m.y & ~JG_FRESH) * 8) & 0xff);
+        const unsigned lv = 1u | d.live[((size_t)lane * 2 + flip) * cap + i];     // entry plane + the live emitting planes
         int root = -1;
         bool live = false;
-        for (int p = 0; p < nst - 1 && p < P && root < 0; ++p) {
+        for (int p = 0; p < P && root < 0; ++p) {
+            if (!((lv >> p) & 1u)) continue;
             const float4 t = tok[(size_t)p * cap + i];
             if (t.x > JG_LZ) { live = true; if (__float_as_int(t.w) >= 0) root = __float_as_int(t.w); }
         }
