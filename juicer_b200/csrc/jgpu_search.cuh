@@ -34,6 +34,9 @@
 #ifndef JG_LR_SH
 #define JG_LR_SH 64              // left-to-right class constants kept in shared memory by k_internal (float4 entries, 2 per class)
 #endif
+#ifndef JG_SCORES_LATE
+#define JG_SCORES_LATE 1          // k_internal: the next chunk's score gathers are issued behind the first barrier of a chunk
+#endif
 #ifndef JG_INT_CTAS
 #define JG_INT_CTAS 3             // resident CTAs per SM of k_internal<5> (register budget 64 K / (256 * CTAs))
 #endif
@@ -794,6 +797,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
                 }
         }
         JG_TRACE_AT(3);                                       // Viterbi done
+#if !JG_SCORES_LATE
         // ---- chunk i+1: its hmm_info has landed, start its acoustic-score gathers ----
         h0 = n0; h1 = n1;
         if (valid1) {
@@ -803,6 +807,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
 #pragma unroll
             for (int j = 1; j < S - 1; ++j) outp[j - 1] = j < nstn - 1 ? __ldg(scores + gm[j - 1]) : 0.0f;
         }
+#endif
         // ---- block-wide allocation: survivors -> next list, exit tokens -> arrival records of round 0;
         //      instances that die simply stop being listed, their slotmap entry goes stale with the epoch (:924-925)
         JG_TRACE_AT(4);                                       // next scores issued
@@ -813,8 +818,18 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         const bool need_path = FUSE && has_exit && !to_round && meta.z >= 0 && meta.w != 0;   // (MULTI: the commit writes it)
         const unsigned m_s = __ballot_sync(0xffffffffu, survive), m_e = __ballot_sync(0xffffffffu, has_exit);
         const unsigned m_p = __ballot_sync(0xffffffffu, need_path), m_r = __ballot_sync(0xffffffffu, to_round);
-        const unsigned best_o = __reduce_max_sync(0xffffffffu, f2o(best));
-        const unsigned packed = __reduce_add_sync(0xffffffffu, (unsigned)cnt_emit | ((unsigned)cnt_hist << 16));
+        // warp totals by vote and shuffle: REDUX (the __reduce_*_sync instructions) answers through the uniform datapath,
+        // and its consumer was the single largest stall of the kernel (14 % of the samples, ncu source view)
+        unsigned packed = 0u;
+#pragma unroll
+        for (int j = 1; j < S - 1; ++j) packed += (unsigned)__popc(__ballot_sync(0xffffffffu, nt[j].x > JG_LZ));
+        if (hist_on) {
+            int ch_ = cnt_hist;
+            for (int o = 16; o > 0; o >>= 1) ch_ += __shfl_xor_sync(0xffffffffu, ch_, o);
+            packed |= (unsigned)ch_ << 16;
+        }
+        unsigned best_o = f2o(best);
+        for (int o = 16; o > 0; o >>= 1) best_o = max(best_o, __shfl_xor_sync(0xffffffffu, best_o, o));
         if (lane_id() == 0) {
             sh_w[wid][0] = __popc(m_s); sh_w[wid][1] = __popc(m_e); sh_w[wid][2] = (int)packed; sh_w[wid][3] = (int)best_o;
             sh_w[wid][4] = __popc(m_p); sh_w[wid][5] = __popc(m_r); sh_w[wid][6] = __popc(m_e);
@@ -852,6 +867,18 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
             if (FUSE && ne) atomicAdd(&c->c_end_proc, ne);
             if (n_hist) atomicAdd(&c->hist_count, n_hist);
         }
+#if JG_SCORES_LATE
+        // ---- chunk i+1: its hmm_info gathers (issued at the top of the iteration) have had the whole Viterbi and the
+        //      first barrier to land; its acoustic-score gathers go out here, in the shadow of the allocation atomics ----
+        h0 = n0; h1 = n1;
+        if (valid1) {
+            const float* __restrict__ scores = d.scores + (size_t)sh.i0[lane1] * d.n_gmms;
+            const int gm[6] = {h0.y, h0.z, h0.w, h1.y, h1.z, h1.w};
+            const int nstn = h0.x & 0xff;
+#pragma unroll
+            for (int j = 1; j < S - 1; ++j) outp[j - 1] = j < nstn - 1 ? __ldg(scores + gm[j - 1]) : 0.0f;
+        }
+#endif
         __syncthreads();
         JG_TRACE_AT(5);                                       // allocation known
         const unsigned lt = (1u << lane_id()) - 1u;
@@ -937,7 +964,7 @@ __global__ void __launch_bounds__(JG_THREADS, 6) k_filter(Dev d)
                 d.arr_meta[(size_t)lane * d.cap_arr + e].x = -2;
             }
         }
-        proc = __reduce_add_sync(0xffffffffu, proc);
+        proc = __popc(__ballot_sync(0xffffffffu, proc != 0));
         if (lane_id() == 0 && proc) atomicAdd(&d.ctl[lane].c_end_proc, proc);
     }
 }
@@ -1212,9 +1239,11 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
                                       a[u], sm[u], best, n_entry);
         }
         if (PASS == 1) {
-            arcs_done = __reduce_add_sync(0xffffffffu, arcs_done);
-            n_entry = __reduce_add_sync(0xffffffffu, n_entry);
-            for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+            for (int o = 16; o > 0; o >>= 1) {                // (shuffles, not REDUX: see k_internal)
+                arcs_done += __shfl_xor_sync(0xffffffffu, arcs_done, o);
+                n_entry += __shfl_xor_sync(0xffffffffu, n_entry, o);
+                best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+            }
             if (lane_id() == 0) {
                 if (arcs_done) atomicAdd(&c->c_arcs, arcs_done);
                 if (n_entry) atomicAdd(&c->c_entry, n_entry);

@@ -5,11 +5,13 @@
  *   usage: dropin_test models.jmbi net.fsm net.insyms net.outsyms feats.f32 mainBeam [endBeam wordBeam startBeam maxHyps]
  * feats.f32 = raw float32 rows of vecSize.  Prints both word chains; exit 0 iff identical. */
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "WFSTDecoderLite.h"
 #include "HTKFlatModels.h"
 #include "WFSTNetwork.h"
+#include "LogFile.h"
 #include "GpuWFSTDecoder.h"
 #include <log_add.h>
 
@@ -42,6 +44,9 @@ int main(int argc, char** argv)
     const float endBeam = argc > 7 ? atof(argv[7]) : 0.f, wordBeam = argc > 8 ? atof(argv[8]) : 0.f;
     const float startBeam = argc > 9 ? atof(argv[9]) : 0.f;
     const int maxHyps = argc > 10 ? atoi(argv[10]) : 0;
+    /* PARTIAL_DECODING: both decoders read the environment variable in their constructors (src/WFSTDecoderLite.cpp:117)
+     * and print "Partial paths recovered at frames: ..." through LogFile at finish() (:247-257) */
+    if (getenv("DROPIN_PARTIAL")) { setenv("PartialTraceInterval", getenv("DROPIN_PARTIAL"), 1); LogFile::open("stdout"); }
     HTKFlatModels* models = new HTKFlatModels;
     models->setBlockSize(5);
     models->readBinary(argv[1]);
