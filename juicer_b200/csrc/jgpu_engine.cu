@@ -1280,7 +1280,7 @@ int lane_stats(jgpu_handle* h, int lane, JgpuStats* out)
 extern "C" {
 
 const char* jgpu_last_error(void) { return jgpu_err_buf().c_str(); }
-const char* jgpu_version(void) { return "juicer_b200 0.1 (sm_100a)"; }
+const char* jgpu_version(void) { return "juicer_b200 0.2 (sm_100a)"; }
 
 int jgpu_create(const JgpuNet* net, const JgpuHmm* hmm, const JgpuGmm* gmm, const JgpuCfg* cfg, jgpu_handle** out)
 {

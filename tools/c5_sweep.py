@@ -74,7 +74,7 @@ def main():
                    "active_models_per_frame": st["total_active_models"] / nf,
                    "emit_hyps_per_frame": st["total_active_emit_hyps"] / nf,
                    "end_hyps_per_frame": st["total_active_end_hyps"] / nf,
-                   "planted_sequence_recovered": ok, "capacity_failures": failed, "capacity_error_bits": err_bits, "utterances": args.utts,
+                   "planted_sequence_recovered": ok, "capacity_failures": failed, "second_passes": dec.retry_count, "capacity_error_bits": err_bits, "utterances": args.utts,
                    "lanes": args.lanes}
             out.append(rec)
             print(json.dumps(rec), flush=True)
