@@ -160,7 +160,12 @@ const char* jgpu_last_error(void);
 const char* jgpu_version(void);
 
 /* Build device-resident tables and arenas.  Validates the reference's unchecked input
- * preconditions: label ranges, arc ranges, no epsilon/tee cycles. */
+ * preconditions: label ranges, arc ranges, no epsilon/tee cycles.
+ * Limits the reference does not have, each refused here with JGPU_E_ARG and a message: HMMs of at most 8 states
+ * (entry and exit included); feature dimension <= 64; <= 256 components per GMM; n_lanes <= 512; epsilon / tee
+ * chains of at most 15 arcs; < 65536 epsilon and < 65536 tee out-arcs per state; < 2^27 arcs and < 2^30 states.
+ * Per-frame statistics (cfg.frame_stats) keep the first max_frames frames of an utterance; decoding has no
+ * frame, instance or word limit (see JgpuResult.status). */
 int jgpu_create(const JgpuNet* net, const JgpuHmm* hmm, const JgpuGmm* gmm, const JgpuCfg* cfg,
                 jgpu_handle** out);
 int jgpu_destroy(jgpu_handle* h);

@@ -1347,12 +1347,10 @@ __global__ void __launch_bounds__(JG_THREADS) k_gc_mark(Dev d)
     const size_t cap = (size_t)d.cap;
     const int P = d.S - 1;
     const int flip = c->flip ^ 1;
-    const int4* meta = d.inst_meta + ((size_t)lane * 2 + flip) * cap;
     const float4* tok = d.tok + ((size_t)lane * 2 + flip) * P * cap;
     PathRec* paths = d.paths + (size_t)lane * d.cap_paths;
     const int n = min(c->n_next, d.cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int4 m = meta[i];
         const float4 t0 = tok[i];
         if (t0.x > JG_LZ) gc_mark_chain(paths, __float_as_int(t0.w), gen);
         const unsigned lv = d.live[((size_t)lane * 2 + flip) * cap + i];   // planes that hold a live token
@@ -1420,8 +1418,7 @@ __global__ void k_partial_count(Dev d, int lane, int* scratch)
     const size_t cap = (size_t)d.cap;
     const int P = d.S - 1;
     const int flip = c->flip;                                 // the streaming interface ends every call with the closing
-    const int4* meta = d.inst_meta + ((size_t)lane * 2 + flip) * cap;      // k_boundary, which has made the last step's list current
-    const float4* tok = d.tok + ((size_t)lane * 2 + flip) * P * cap;
+    const float4* tok = d.tok + ((size_t)lane * 2 + flip) * P * cap;       // k_boundary, which has made the last step's list current
     PathRec* paths = d.paths + (size_t)lane * d.cap_paths;
     const int n = min(c->n_cur, d.cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
