@@ -512,7 +512,9 @@ def main() -> None:
         # rate of each kernel's algorithmic bytes and WHERE those bytes live: only "hbm" entries compare with hbm_gbs
         "kernel_algorithmic_gbs": {k: {"gbs": round(ab[k]["bytes"] / (prof[k]["ms"] * 1e-3) / 1e9, 1) if prof[k]["ms"] > 0 else 0.0,
                                        "level": ab[k]["level"]} for k in prof},
-        "secondary": {"kernel": "k_gmm_scores (the scorer of the step: k_gmm_lazy over the stamped (GMM, lane) pairs)",
+        "secondary": {"kernel": ("k_gmm_scores = k_gmm_lazy over the stamped (GMM, lane) pairs of every step (JUICER_B200_LAZY=1)"
+                                 if os.environ.get("JUICER_B200_LAZY", "0") not in ("", "0")
+                                 else "k_gmm_scores: every GMM for every (lane, frame), 16 frames ahead per launch"),
                       "bound": "fp32 issue, no FMA", "achieved": gmm_tops, "peak": fp32_peak, "unit": "T op/s",
                       "frac": gmm_tops / fp32_peak if fp32_peak else None,
                       "ops": "4 per (Gaussian, dimension): sub, mul, mul, add", "peak_source": "jgpu_ubench_fp32 in this run",
