@@ -303,6 +303,7 @@ class Net:
     n_in: int                         # number of input symbols incl. <eps>
     n_out: int                        # number of output symbols incl. <eps>
     in_names: Optional[List[str]] = None
+    out_names: Optional[List[str]] = None   # output symbol names by id (index 0 = <eps>); default W<id-1>
 
     @property
     def n_arcs(self) -> int:
@@ -563,7 +564,7 @@ def write_fsm(net: Net, prefix: str) -> Tuple[str, str, str]:
     with open(outsyms, "w") as f:
         f.write("<eps> 0\n")
         for i in range(1, net.n_out):
-            f.write(f"W{i - 1} {i}\n")
+            f.write(f"{net.out_names[i] if net.out_names else 'W%d' % (i - 1)} {i}\n")
     return fsm, insyms, outsyms
 
 

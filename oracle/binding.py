@@ -18,7 +18,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "liboracle_ref.so")
-REF_O3_SO = os.path.join(HERE, "_ref", "liboracle_ref_o3.so")       # speed-only build (-O3, AVX2 + FMA), never used for parity
+REF_O3_SO = os.path.join(HERE, "_ref", "liboracle_ref_o3.so")
+HARNESS_SO = os.path.join(HERE, "_ref", "liboracle_harness.so")     # the reference's own DecoderBatchTest harness (make harness)       # speed-only build (-O3, AVX2 + FMA), never used for parity
 PORT_SO = os.path.join(HERE, "liboracle.so")
 DROPIN_BIN = os.path.join(HERE, "_ref", "dropin_test")
 LOG_ZERO = -np.finfo(np.float32).max
@@ -32,6 +33,7 @@ def build(ref: bool = True, port: bool = True) -> None:
     if ref and os.path.isdir(os.environ.get("JUICER_REF", "/root/reference")):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
         subprocess.check_call(["make", "-s", "-C", HERE, "ref_o3"])
+        subprocess.check_call(["make", "-s", "-C", HERE, "harness"])
         if os.path.exists(os.path.join(HERE, "..", "juicer_b200", "libjuicer_b200.so")):
             subprocess.check_call(["make", "-s", "-C", HERE, "dropin"])      # C++ adapter behind Juicer::IDecoder
 
@@ -307,3 +309,30 @@ class OraclePort:
         s = self._abi.JgpuStats()
         self.lib.jor_stats(self.h, C.byref(s))
         return s.as_dict()
+
+
+REF_FORMATS = {"verbose": 0, "trans": 1, "ref": 2, "mlf": 3, "xmlf": 4}      # DBTOutputFormat, src/DecoderBatchTest.h:29-38
+
+
+def ref_harness_run(files: Dict[str, str], lexicon: str, list_file: str, out_file: str, fmt: str, *, main_beam: float,
+                    start_beam: float = 0.0, end_beam: float = 0.0, word_beam: float = 0.0, max_hyps: int = 0,
+                    sent_start: str = "", sent_end: str = "", remove_sil: bool = False, frames_per_sec: int = 100) -> str:
+    """DecoderBatchTest::run of the UNMODIFIED reference (oracle/harness_driver.cpp) over a list of (extended) HTK feature file
+    names; returns the text it wrote.  Runs in a child process: the reference's error() exits."""
+    import subprocess as sp
+    import sys
+    code = (
+        "import ctypes as C, sys\n"
+        f"lib = C.CDLL({HARNESS_SO!r})\n"
+        "lib.oref_harness_run.argtypes = [C.c_char_p] * 7 + [C.c_int] + [C.c_float] * 4 + [C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int]\n"
+        "a = sys.argv[1:]\n"
+        "rc = lib.oref_harness_run(*[x.encode() for x in a[:7]], int(a[7]), *[float(x) for x in a[8:12]], int(a[12]), a[13].encode(), a[14].encode(), int(a[15]), int(a[16]))\n"
+        "sys.exit(rc)\n")
+    args = [files["jmbi"], files["fsm"], files["insyms"], files["outsyms"], lexicon, list_file, out_file, str(REF_FORMATS[fmt]),
+            str(start_beam), str(main_beam), str(end_beam), str(word_beam), str(max_hyps), sent_start, sent_end,
+            str(int(remove_sil)), str(frames_per_sec)]
+    p = sp.run([sys.executable, "-c", code] + args, capture_output=True, text=True, timeout=600)
+    if p.returncode != 0:
+        raise RuntimeError(f"reference harness failed ({p.returncode}): {p.stderr[-2000:]}")
+    with open(out_file) as f:
+        return f.read()

@@ -1,7 +1,10 @@
 """The callers either side of the decode path (juicer_b200/harness.py): HTK feature files, extended file
-names, result-word extraction and the output formats of the reference's batch harness.  The reference's
-own harness cannot be built here (Tracter is out of tree), so the expected strings below are derived by
-hand from the cited lines of src/DecoderSingleTest.cpp and src/DecoderBatchTest.cpp."""
+names, result-word extraction and the output formats of the reference's batch harness.  First the pieces against
+strings derived by hand from the cited lines of src/DecoderSingleTest.cpp and src/DecoderBatchTest.cpp; then the
+whole thing against the reference's OWN harness: DecoderBatchTest / DecoderSingleTest / DecVocabulary compiled
+unmodified (oracle/harness_driver.cpp, `make -C oracle harness`) behind stand-ins for the two out-of-tree
+libraries they use (Tracter's HTKSource / FrameSink, Torch3's DiskXFile / EditDistance)."""
+import os
 import struct
 
 import numpy as np
@@ -141,4 +144,86 @@ def test_decode_files_matches_decode_batch(tmp_path, product_lib):
     assert text == want and text.count(".rec") == 2
     for u in range(2):
         g.check(u, dec.decode_batch(feats)[u], what="harness")
+    dec.close()
+
+
+# ---------------------------------------------------------------------------------------
+# pinned against the reference's own harness (oracle/_ref/liboracle_harness.so: DecoderBatchTest / DecoderSingleTest /
+# DecVocabulary compiled unmodified, `make -C oracle harness`)
+# ---------------------------------------------------------------------------------------
+def _harness_fixture(tmp_path):
+    """Small bigram network whose output symbols sort alphabetically in id order (DecVocabulary keeps its words sorted, and
+    the decoder's output label - 1 is an index into it), three HTK feature files, and a list of extended file names:
+    whole files, segments from the start and from the middle, a segment that ends mid-word (no result) and one whose end
+    lies beyond the file."""
+    from juicer_b200 import synth
+    m = synth.make_models(120, 4, sigma_mu=0.9, seed=11, n_gmm_pool=150)
+    net = synth.bigram_net(100, 120, k_bigram=5, seed=12)
+    words = [f"w{i:04d}" for i in range(100)]
+    net.out_names = ["<eps>"] + words
+    kw = dict(main_beam=180.0, end_beam=140.0)
+    files = synth.make_fixture("h", str(tmp_path), m, net)
+    lex = str(tmp_path / "h.lex")
+    with open(lex, "w") as f:
+        f.write("".join(f"{w} a b\n" for w in words))
+    ps = synth.PathSampler(net, m)
+    rng = np.random.default_rng(3)
+    paths = []
+    for u in range(3):
+        x, _ = ps.sample(120, rng)
+        p = str(tmp_path / f"utt{u}.htk")
+        H.write_htk(p, x)
+        paths.append(p)
+    p0, p1, p2 = paths
+    specs = [p0, f"seg1={p1}[0,90]", f"mid={p2}[20,80]", f"cut={p0}[0,37]", f"late={p1}[25,200]", p2]
+    lst = str(tmp_path / "files.lst")
+    with open(lst, "w") as f:
+        f.write("".join(s + "\n" for s in specs))
+    return files, kw, words, lex, lst, specs
+
+
+class _PortDecoder:
+    """decode_batch over the oracle port: lets the CPU suite drive harness.decode_files without a GPU."""
+
+    def __init__(self, port):
+        self.p = port
+
+    def decode_batch(self, feats):
+        return [self.p.decode(x) for x in feats]
+
+
+@pytest.mark.parametrize("fmt", ["ref", "trans", "mlf", "xmlf", "verbose"])
+def test_output_matches_the_reference_harness(fmt, tmp_path, oracle_port_lib, product_lib):
+    """The text harness.decode_files writes equals, byte for byte, what the reference's own DecoderBatchTest::run writes
+    for the same file list, network, models and pruning: extended names, frame feeding, result extraction and the
+    output format are all the reference's compiled code on that side."""
+    from helpers import flat_tables_from_files
+    from juicer_b200 import _abi
+    from oracle import binding
+    if not os.path.exists(binding.HARNESS_SO):
+        pytest.skip("oracle/_ref/liboracle_harness.so not built (needs /root/reference)")
+    files, kw, words, lex, lst, specs = _harness_fixture(tmp_path)
+    want = binding.ref_harness_run(files, lex, lst, str(tmp_path / ("ref_" + fmt)), fmt, **kw)
+    tabs, _n, _m = flat_tables_from_files(files)
+    port = binding.OraclePort(tabs, _abi.make_cfg(**kw))
+    got = H.decode_files(_PortDecoder(port), specs, words, fmt=fmt, expected_dim=39)
+    assert got == want
+    assert "w0" in want                                      # something was decoded
+    port.close()
+
+
+@pytest.mark.gpu
+def test_gpu_output_matches_the_reference_harness(tmp_path, oracle_port_lib, product_lib):
+    """The same with the CUDA decoder behind harness.decode_files (xmlf: words, times and per-word scores)."""
+    from juicer_b200 import api
+    from oracle import binding
+    if not os.path.exists(binding.HARNESS_SO):
+        pytest.skip("oracle/_ref/liboracle_harness.so did not travel to this box")
+    files, kw, words, lex, lst, specs = _harness_fixture(tmp_path)
+    net = api.WFSTNetwork(files["fsm"], files["insyms"], files["outsyms"])
+    models = api.HTKFlatModels(files["jmbi"])
+    dec = api.WFSTDecoderLite(net, models, 0.0, kw["main_beam"], kw["end_beam"], 0.0, 0, n_lanes=4)
+    for fmt in ("xmlf", "verbose"):
+        want = binding.ref_harness_run(files, lex, lst, str(tmp_path / ("ref_" + fmt)), fmt, **kw)
+        assert H.decode_files(dec, specs, words, fmt=fmt, expected_dim=39) == want
     dec.close()
