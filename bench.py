@@ -98,10 +98,12 @@ def sample_utterances(net, m, tee, n, lo, hi, seed) -> List[np.ndarray]:
     return [ps.sample(int(rng.integers(lo, hi + 1)), rng)[0] for _ in range(n)]
 
 
-def make_config(args, kw, world: int) -> Dict:
+def make_config(args, kw, world: int, net=None) -> Dict:
     """The `config` object: identical in both arms (the reference arm decodes a bounded sample of the same batch)."""
     strong = args.scaling == "strong"
+    state_gb = (net.n_arcs * 12 + net.n_states * 8) * args.lanes / 1e9 if net is not None else 0.0
     return {"workload": f"{args.workload}: {WORKLOADS[args.workload]}", "decoder": kw,
+            "l2": f"CUDA arm: 256 MiB device buffer written between iterations; per-step state {state_gb:.1f} GB >> 126 MB L2",
             "utterances_per_step": args.total_utts if strong else args.utts * world,
             "utterances_per_step_per_gpu": None if strong else args.utts,
             "utterance_frames": [args.min_frames, args.max_frames], "utterance_seed": "1000 + rank",
@@ -236,7 +238,7 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (frames / max(len(per_step), 1)) / value,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": make_config(args, kw, world),
+        "config": make_config(args, kw, world, net),
         "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "xrt": value / 100.0,
@@ -570,16 +572,13 @@ def main() -> None:
         stats = r["stats"]
         value = r["frames_all"] / (r["ms_max"] * 1e-3)
         e2e_value = batch.rows * args.steps / (r["e2e_ms_max"] * 1e-3)
-        cfg = make_config(args, kw, world)
-        cfg["frames_per_step"] = batch.rows
-        cfg["l2"] = ("256 MiB device buffer written between iterations; per-step state "
-                     f"{(network.c.n_arcs * 12 + network.c.n_states * 8) * args.lanes / 1e9:.1f} GB >> 126 MB L2")
+        cfg = make_config(args, kw, world, net)
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["ms_max"] / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg,
-            "xrt": value / 100.0,
+            "xrt": value / 100.0, "frames_per_step": batch.rows,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                     "bytes_are": "rank 0's share of the batch" if use_queue else "the whole batch",
                     "timing": "host wall clock around jgpu_decode_batch / jgpu_decode_queue (pinned inputs), max over ranks",
