@@ -681,7 +681,7 @@ int build_state(jgpu_handle* h)
     if ((rc = h->alloc(&d.res_used, 1))) return rc;
     d.res_words_cap = (int)h->words_cap;
     {
-        const int smem = 2 * h->S * JG_THREADS * (int)sizeof(float4);
+        const int smem = (int)internal_smem_bytes(h->S, (int)L);
         cudaError_t e = cudaSuccess;
         void (*kerns[8])(Dev) = {k_internal<5, true, false>, k_internal<5, false, false>, k_internal<5, true, true>, k_internal<5, false, true>,
                                  k_internal<8, true, false>, k_internal<8, false, false>, k_internal<8, true, true>, k_internal<8, false, true>};
@@ -693,7 +693,7 @@ int build_state(jgpu_handle* h)
         // CTA can cost a whole CTA per SM, and a grid that no longer fits in one wave costs a second set-up)
         int n_sm = 148, occ = 0;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
-        const size_t smem_int = (size_t)2 * h->S * JG_THREADS * sizeof(float4);
+        const size_t smem_int = internal_smem_bytes(h->S, (int)L);
         cudaError_t e = h->S == 5 ? (h->lazy ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_internal<5, true, true>, JG_THREADS, smem_int)
                                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_internal<5, true, false>, JG_THREADS, smem_int))
                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_internal<8, true, false>, JG_THREADS, smem_int);
@@ -859,7 +859,7 @@ int launch_step(jgpu_handle* h)
     if (h->lazy) { int rc = launch_lazy(h); if (rc) return rc; }
     h->prof_begin(JGPU_K_INTERNAL);
     {
-        const size_t smem = (size_t)2 * h->S * JG_THREADS * sizeof(float4);   // two chunk buffers: record + S-1 token planes
+        const size_t smem = internal_smem_bytes(h->S, d.n_lanes);   // chunk buffers (record + S-1 token planes) + lane table
         void (*kern)(Dev);
         if (h->S == 5) kern = h->lazy ? (d.fuse_exits ? k_internal<5, true, true> : k_internal<5, false, true>)
                                       : (d.fuse_exits ? k_internal<5, true, false> : k_internal<5, false, false>);

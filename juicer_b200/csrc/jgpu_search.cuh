@@ -37,6 +37,10 @@
 #ifndef JG_SCORES_LATE
 #define JG_SCORES_LATE 1          // k_internal: the next chunk's score gathers are issued behind the first barrier of a chunk
 #endif
+#ifndef JG_DEFER
+#define JG_DEFER 0                // k_internal: a chunk's stores wait one chunk for their allocation atomics (see the kernel;
+                                  // measured slower, profiles/r02_defer_experiment.md)
+#endif
 #ifndef JG_INT_CTAS
 #define JG_INT_CTAS 3             // resident CTAs per SM of k_internal<5> (register budget 64 K / (256 * CTAs))
 #endif
@@ -152,8 +156,10 @@ struct LaneSh {                   // per-CTA shared copy of what a chunk needs t
 // word-boundary free list was not empty when the kernel started
 #define JG_SH_HAS_FREE 0x80000000u
 
-// sh.cnt[] must be filled (and __syncthreads() NOT yet called); returns the number of chunks
-__device__ __forceinline__ int chunk_scan(LaneSh& sh, int L, int items = JG_CH)
+// the per-lane item counts cnt(l) must be in shared memory (and __syncthreads() NOT yet called); fills pref[0..L] and
+// returns the number of chunks
+template <class CntF>
+__device__ __forceinline__ int chunk_scan_by(int* pref, int L, CntF cnt, int items = JG_CH)
 {
     __syncthreads();
     if (threadIdx.x < 32) {                                  // warp 0: scan L values, L/32 per thread
@@ -161,19 +167,32 @@ __device__ __forceinline__ int chunk_scan(LaneSh& sh, int L, int items = JG_CH)
         const int b = threadIdx.x * per;
         int sum = 0;
         for (int i = 0; i < per; ++i)
-            if (b + i < L) sum += (sh.cnt[b + i] + items - 1) / items;
+            if (b + i < L) sum += (cnt(b + i) + items - 1) / items;
         int incl = sum;
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, o);
             if ((int)threadIdx.x >= o) incl += t;
         }
         int run = incl - sum;
-        if (threadIdx.x == 0) sh.pref[0] = 0;
+        if (threadIdx.x == 0) pref[0] = 0;
         for (int i = 0; i < per; ++i)
-            if (b + i < L) { run += (sh.cnt[b + i] + items - 1) / items; sh.pref[b + i + 1] = run; }
+            if (b + i < L) { run += (cnt(b + i) + items - 1) / items; pref[b + i + 1] = run; }
     }
     __syncthreads();
-    return sh.pref[L];
+    return pref[L];
+}
+__device__ __forceinline__ int chunk_scan(LaneSh& sh, int L, int items = JG_CH)
+{
+    return chunk_scan_by(sh.pref, L, [&](int l) { return sh.cnt[l]; }, items);
+}
+
+// k_internal keeps its lane table in DYNAMIC shared memory, sized by the number of lanes, so that at up to 256 lanes
+// three CTAs per SM still fit beside the chunk buffers (LaneSh is sized for JG_MAX_LANES).
+struct IntLane { int cnt; unsigned epoch; float norm, thr_emit, thr_start; int srow, flip, frame; };
+#define JG_PREF_PAD ((JG_MAX_LANES + 1 + 3) & ~3)            // ints reserved for the chunk prefix (keeps IntLane 16-byte aligned)
+__host__ __device__ inline size_t internal_smem_bytes(int S, int n_lanes)
+{
+    return (size_t)(JG_DEFER ? 3 : 2) * S * JG_THREADS * sizeof(float4) + JG_PREF_PAD * sizeof(int) + (size_t)n_lanes * sizeof(IntLane);
 }
 
 // lane of chunk `ch` (largest l with pref[l] <= ch), walked upwards from the lane of the CTA's previous chunk:
@@ -552,10 +571,17 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
     JG_TRACE_SCOPE(JGPU_K_INTERNAL, 0);
     constexpr int P = S - 1;
     constexpr int NW = JG_THREADS / 32;
-    __shared__ LaneSh sh;
-    __shared__ int sh_w[NW][7];                               // per warp: survivors, exits, packed counters, best, path records, round-0 entries, exits (copy)
-    __shared__ int sh_base[6];
-    extern __shared__ float4 stage[];                         // [2][P + 1][JG_THREADS]; plane 0 = instance record
+    constexpr bool DEFER = JG_DEFER != 0;
+    constexpr int NPAR = DEFER ? 2 : 1;
+    __shared__ int sh_w[NPAR][NW][7];                         // per warp: survivors, exits, packed counters, best, path records, round-0 entries, exits (copy)
+    __shared__ int sh_base[NPAR][6];
+    // dynamic shared memory (internal_smem_bytes): [2][P + 1][JG_THREADS] chunk buffers (plane 0 = instance record),
+    // DEFER: [P + 1][JG_THREADS] results of the previous chunk, then the lane table (sized by the number of lanes)
+    extern __shared__ float4 stage[];
+    float4* const defer = stage + 2 * (P + 1) * JG_THREADS;
+    int* const pref = reinterpret_cast<int*>(stage + (DEFER ? 3 : 2) * (P + 1) * JG_THREADS);
+    IntLane* const sh = reinterpret_cast<IntLane*>(pref + JG_PREF_PAD);
+    __shared__ int s_dflags[DEFER ? JG_THREADS : 1];
     __shared__ float4 s_lr[JG_LR_SH];                         // left-to-right class constants: the Viterbi of a chunk starts with
                                                               // them (an LDS instead of an L1 round trip; the host clears the class
                                                               // flag of every HMM when the table does not fit)
@@ -564,12 +590,14 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
     if (tid < min(d.n_lr, JG_LR_SH)) s_lr[tid] = __ldg(d.lr + tid);
     for (int l = tid; l < L; l += blockDim.x) {
         const LaneCtl* c = d.ctl + l;
-        sh.cnt[l] = c->mode == JG_MODE_FRAME ? c->n_cur : 0;
-        sh.f0[l] = c->norm; sh.f1[l] = c->thr_emit; sh.f2[l] = c->thr_start;
-        sh.i0[l] = c->srow; sh.i1[l] = c->flip; sh.i2[l] = c->frame;
-        sh.epoch[l] = (c->epoch & ~JG_SH_HAS_FREE) | (c->n_free > 0 ? JG_SH_HAS_FREE : 0u);
+        IntLane r;
+        r.cnt = c->mode == JG_MODE_FRAME ? c->n_cur : 0;
+        r.norm = c->norm; r.thr_emit = c->thr_emit; r.thr_start = c->thr_start;
+        r.srow = c->srow; r.flip = c->flip; r.frame = c->frame;
+        r.epoch = (c->epoch & ~JG_SH_HAS_FREE) | (c->n_free > 0 ? JG_SH_HAS_FREE : 0u);
+        sh[l] = r;
     }
-    const int total = chunk_scan(sh, L);
+    const int total = chunk_scan_by(pref, L, [&](int l) { return sh[l].cnt; });
     const size_t cap = (size_t)d.cap;
     const bool hist_on = d.max_hyps > 0;
     const int G = gridDim.x;
@@ -580,19 +608,19 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
     __shared__ unsigned char s_mask[2][JG_THREADS];           // the mask the copies of a staged chunk were issued with
     auto live_of = [&](int ch, int ln) -> unsigned {
         if (ch >= total) return 0u;
-        const int k = (ch - sh.pref[ln]) * JG_CH + tid;
-        if (k >= sh.cnt[ln]) return 0u;
-        return d.live[((size_t)ln * 2 + sh.i1[ln]) * cap + k];
+        const int k = (ch - pref[ln]) * JG_CH + tid;
+        if (k >= sh[ln].cnt) return 0u;
+        return d.live[((size_t)ln * 2 + sh[ln].flip) * cap + k];
     };
     // copies of chunk `ch` (lane `ln`) into buffer `buf`: record, entry token and the planes in `mask`; returns whether
     // this thread has an instance there
     auto issue = [&](int ch, int ln, int buf, unsigned mask) -> bool {
         bool v = false;
         if (ch < total) {
-            const int k = (ch - sh.pref[ln]) * JG_CH + tid;
-            if (k < sh.cnt[ln]) {
+            const int k = (ch - pref[ln]) * JG_CH + tid;
+            if (k < sh[ln].cnt) {
                 v = true;
-                const int flip = sh.i1[ln];
+                const int flip = sh[ln].flip;
                 const int4* meta_cur = d.inst_meta + ((size_t)ln * 2 + flip) * cap;
                 const float4* tok_cur = d.tok + ((size_t)ln * 2 + flip) * P * cap;
                 float4* dst = stage + (size_t)buf * (P + 1) * JG_THREADS + tid;
@@ -622,7 +650,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         if (c_t < total)
             while (lo + 1 < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (sh.pref[mid] <= c_t) lo = mid; else hi = mid;
+                if (pref[mid] <= c_t) lo = mid; else hi = mid;
             }
         my_lane[tid] = (unsigned short)lo;
     }
@@ -630,7 +658,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
     auto lane_of = [&](int i, int ch, int ln) -> int {
         if (i < JG_THREADS) return my_lane[i];
         if (ch < total)
-            while (sh.pref[ln + 1] <= ch) ++ln;               // (more than 256 chunks per CTA: walk on)
+            while (pref[ln + 1] <= ch) ++ln;                  // (more than 256 chunks per CTA: walk on)
         return ln;
     };
 
@@ -654,7 +682,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         const int hmm = reinterpret_cast<const int4*>(stage)[tid].y & ~JG_FRESH;
         h0 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2);
         if (S > 5) h1 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2 + 1);
-        const float* __restrict__ scores = d.scores + (size_t)sh.i0[lane] * d.n_gmms;
+        const float* __restrict__ scores = d.scores + (size_t)sh[lane].srow * d.n_gmms;
         const int gm[6] = {h0.y, h0.z, h0.w, h1.y, h1.z, h1.w};
         const int nst0 = h0.x & 0xff;
 #pragma unroll
@@ -662,11 +690,19 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
     }
 
     JG_TRACE_AT(0);                                           // setup + first chunk's loads done
-    for (int it = 0; ch < total; ++it, ch = chunk_of(it)) {
+    // DEFER: the allocation atomics of chunk i are issued after its barrier and their results are only read one chunk
+    // later — the threads that issued them publish them just before chunk i+1's barrier, and chunk i's survivors and
+    // exit tokens, parked in shared memory meanwhile, are stored behind it.  One barrier per chunk, and no warp waits
+    // for an L2 round trip (the second barrier and the wait behind it were 20 % of the kernel's stall samples).
+    // The loop runs one extra, empty iteration to store the last chunk.
+    bool pending = false;                                     // a chunk's results are parked (CTA-uniform)
+    int lane_d = 0;                                           // ... and this is its lane
+    int held0 = 0, held1 = 0, held2 = 0;                      // allocation results on their way (allocating threads only)
+    for (int it = 0; ch < total || (DEFER && pending); ++it, ch = chunk_of(it)) {
         const int buf = it & 1;
-        const float norm = sh.f0[lane], thr_emit = sh.f1[lane], thr_start = sh.f2[lane];
-        const unsigned epoch = sh.epoch[lane];
-        const int flip = sh.i1[lane];
+        const int par = DEFER ? (it & 1) : 0;
+        const float norm = sh[lane].norm, thr_emit = sh[lane].thr_emit, thr_start = sh[lane].thr_start;
+        const unsigned epoch = sh[lane].epoch;
         LaneCtl* c = d.ctl + lane;
         // ---- registers <- buffer (chunk i) ----
         int4 meta = make_int4(0, 0, 0, 0);
@@ -801,7 +837,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         // ---- chunk i+1: its hmm_info has landed, start its acoustic-score gathers ----
         h0 = n0; h1 = n1;
         if (valid1) {
-            const float* __restrict__ scores = d.scores + (size_t)sh.i0[lane1] * d.n_gmms;
+            const float* __restrict__ scores = d.scores + (size_t)sh[lane1].srow * d.n_gmms;
             const int gm[6] = {h0.y, h0.z, h0.w, h1.y, h1.z, h1.w};
             const int nstn = h0.x & 0xff;
 #pragma unroll
@@ -831,8 +867,15 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         unsigned best_o = f2o(best);
         for (int o = 16; o > 0; o >>= 1) best_o = max(best_o, __shfl_xor_sync(0xffffffffu, best_o, o));
         if (lane_id() == 0) {
-            sh_w[wid][0] = __popc(m_s); sh_w[wid][1] = __popc(m_e); sh_w[wid][2] = (int)packed; sh_w[wid][3] = (int)best_o;
-            sh_w[wid][4] = __popc(m_p); sh_w[wid][5] = __popc(m_r); sh_w[wid][6] = __popc(m_e);
+            sh_w[par][wid][0] = __popc(m_s); sh_w[par][wid][1] = __popc(m_e); sh_w[par][wid][2] = (int)packed; sh_w[par][wid][3] = (int)best_o;
+            sh_w[par][wid][4] = __popc(m_p); sh_w[par][wid][5] = __popc(m_r); sh_w[par][wid][6] = __popc(m_e);
+        }
+        if (DEFER && pending) {                               // the previous chunk's allocation has had a whole chunk to come back
+            if (wid == 0) {
+                if (lane_id() < 3) sh_base[par ^ 1][lane_id() == 2 ? 3 : lane_id()] = held0;
+            } else if (tid == 32) {
+                sh_base[par ^ 1][2] = held0; sh_base[par ^ 1][4] = held1; sh_base[par ^ 1][5] = held2;
+            }
         }
         __syncthreads();
         // The allocation counters are bumped by DIFFERENT threads so that their round trips to L2 overlap: one
@@ -843,23 +886,28 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
             if (li < 3) {                                     // lanes 0..2: next list, round-0 arrivals, round-0 work list
                 const int col = li == 2 ? 5 : li;
                 int tot = 0;
-                for (int w = 0; w < NW; ++w) { const int a = sh_w[w][col]; sh_w[w][col] = tot; tot += a; }   // exclusive offsets of the warps
+                for (int w = 0; w < NW; ++w) { const int a = sh_w[par][w][col]; sh_w[par][w][col] = tot; tot += a; }   // exclusive offsets of the warps
                 int* ctr = li == 0 ? &c->n_next : li == 1 ? &c->n_arr[0] : &c->n_r0;
                 int base = 0;
                 if (tot) base = atomicAdd(ctr, tot);          // one predicated ATOMG for the three lanes
-                sh_base[li == 2 ? 3 : li] = base;
+                if (DEFER) held0 = base;
+                else sh_base[0][li == 2 ? 3 : li] = base;
             }
         } else if (tid == 32) {                               // word-boundary records
             int np = 0;
-            for (int w = 0; w < NW; ++w) { const int a = sh_w[w][4]; sh_w[w][4] = np; np += a; }
-            if (np) { const PathAlloc pa = path_alloc(c, np, (sh.epoch[lane] & JG_SH_HAS_FREE) != 0); sh_base[2] = pa.bump_base; sh_base[4] = pa.from_free; sh_base[5] = pa.free_top; }
+            for (int w = 0; w < NW; ++w) { const int a = sh_w[par][w][4]; sh_w[par][w][4] = np; np += a; }
+            if (np) {
+                const PathAlloc pa = path_alloc(c, np, (epoch & JG_SH_HAS_FREE) != 0);
+                if (DEFER) { held0 = pa.bump_base; held1 = pa.from_free; held2 = pa.free_top; }
+                else { sh_base[0][2] = pa.bump_base; sh_base[0][4] = pa.from_free; sh_base[0][5] = pa.free_top; }
+            }
         } else if (tid == 64) {                               // counters nobody waits for
             int ne = 0, n_emit = 0, n_hist = 0;
             unsigned bo = 0;
             for (int w = 0; w < NW; ++w) {
-                ne += sh_w[w][6];
-                n_emit += sh_w[w][2] & 0xffff; n_hist += (unsigned)sh_w[w][2] >> 16;
-                bo = max(bo, (unsigned)sh_w[w][3]);
+                ne += sh_w[par][w][6];
+                n_emit += sh_w[par][w][2] & 0xffff; n_hist += (unsigned)sh_w[par][w][2] >> 16;
+                bo = max(bo, (unsigned)sh_w[par][w][3]);
             }
             if (bo > f2o(JG_LZ)) atomicMax(&c->best_int, bo);
             if (n_emit) atomicAdd(&c->c_active_emit, n_emit);
@@ -872,55 +920,90 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         //      first barrier to land; its acoustic-score gathers go out here, in the shadow of the allocation atomics ----
         h0 = n0; h1 = n1;
         if (valid1) {
-            const float* __restrict__ scores = d.scores + (size_t)sh.i0[lane1] * d.n_gmms;
+            const float* __restrict__ scores = d.scores + (size_t)sh[lane1].srow * d.n_gmms;
             const int gm[6] = {h0.y, h0.z, h0.w, h1.y, h1.z, h1.w};
             const int nstn = h0.x & 0xff;
 #pragma unroll
             for (int j = 1; j < S - 1; ++j) outp[j - 1] = j < nstn - 1 ? __ldg(scores + gm[j - 1]) : 0.0f;
         }
 #endif
-        __syncthreads();
+        // ---- what is stored now: this chunk (after a second barrier, once its allocation is known) or, DEFER, the
+        //      previous one, whose place in shared memory this chunk's results take ----
+        int4 e_meta = meta;
+        float4 e_ex = ex;
+        float4 e_nt[S];
+#pragma unroll
+        for (int i = 1; i < P; ++i) e_nt[i] = nt[i];
+        unsigned e_flags = (survive ? 1u : 0u) | (has_exit ? 2u : 0u) | (need_path ? 4u : 0u) | (to_round ? 8u : 0u);
+        int e_lane = lane;
+        if (DEFER) {
+            const unsigned now = e_flags;
+            float4* dq = defer + tid;
+            e_flags = pending ? (unsigned)s_dflags[tid] : 0u;
+            e_lane = lane_d;
+            s_dflags[tid] = (int)now;
+            if (e_flags) e_meta = *reinterpret_cast<const int4*>(dq);
+            if (now) *reinterpret_cast<int4*>(dq) = meta;
+            if (e_flags & 2u) e_ex = dq[P * JG_THREADS];
+            if (now & 2u) dq[P * JG_THREADS] = ex;
+#pragma unroll
+            for (int i = 1; i < P; ++i) {
+                if (e_flags & 1u) e_nt[i] = dq[i * JG_THREADS];
+                if (now & 1u) dq[i * JG_THREADS] = nt[i];
+            }
+            lane_d = lane;
+            pending = ch < total;
+        } else {
+            __syncthreads();
+        }
         JG_TRACE_AT(5);                                       // allocation known
+        const int pe = DEFER ? par ^ 1 : 0;
+        const bool e_survive = e_flags & 1u, e_has_exit = e_flags & 2u, e_need_path = e_flags & 4u, e_to_round = e_flags & 8u;
+        const unsigned q_s = DEFER ? __ballot_sync(0xffffffffu, e_survive) : m_s, q_e = DEFER ? __ballot_sync(0xffffffffu, e_has_exit) : m_e;
+        const unsigned q_p = DEFER ? __ballot_sync(0xffffffffu, e_need_path) : m_p, q_r = DEFER ? __ballot_sync(0xffffffffu, e_to_round) : m_r;
         const unsigned lt = (1u << lane_id()) - 1u;
-        const int pos = sh_base[0] + sh_w[wid][0] + __popc(m_s & lt);
-        const int e = sh_base[1] + sh_w[wid][1] + __popc(m_e & lt);
-        if (survive && pos < d.cap) {
-            int4* meta_nxt = d.inst_meta + ((size_t)lane * 2 + (flip ^ 1)) * cap;
-            float4* tok_nxt = d.tok + ((size_t)lane * 2 + (flip ^ 1)) * P * cap;
-            st_stream(meta_nxt + pos, make_int4(meta.x, meta.y & ~JG_FRESH, meta.z, meta.w));
+        const int pos = sh_base[pe][0] + sh_w[pe][wid][0] + __popc(q_s & lt);
+        const int e = sh_base[pe][1] + sh_w[pe][wid][1] + __popc(q_e & lt);
+        const unsigned e_epoch = sh[e_lane].epoch;
+        if (e_survive && pos < d.cap) {
+            const int flip = sh[e_lane].flip;
+            int4* meta_nxt = d.inst_meta + ((size_t)e_lane * 2 + (flip ^ 1)) * cap;
+            float4* tok_nxt = d.tok + ((size_t)e_lane * 2 + (flip ^ 1)) * P * cap;
+            st_stream(meta_nxt + pos, make_int4(e_meta.x, e_meta.y & ~JG_FRESH, e_meta.z, e_meta.w));
             tok_nxt[pos] = null_tok();                    // entry token consumed (:426-435); k_walk<1> may overwrite it
             unsigned nm = 0u;
 #pragma unroll
             for (int i = 1; i < P; ++i)
-                if (i < nst - 1 && nt[i].x > JG_LZ) { st_stream(tok_nxt + (size_t)i * cap + pos, nt[i]); nm |= 1u << i; }
-            d.live[((size_t)lane * 2 + (flip ^ 1)) * cap + pos] = (unsigned char)nm;
-            d.slotmap[(size_t)lane * d.n_arcs + meta.x] = slot_entry(d, epoch, pos);
+                if (e_nt[i].x > JG_LZ) { st_stream(tok_nxt + (size_t)i * cap + pos, e_nt[i]); nm |= 1u << i; }
+            d.live[((size_t)e_lane * 2 + (flip ^ 1)) * cap + pos] = (unsigned char)nm;
+            d.slotmap[(size_t)e_lane * d.n_arcs + e_meta.x] = slot_entry(d, e_epoch, pos);
         }
-        if (has_exit && e < d.cap_arr) {
-            int via = meta.x;
-            if (need_path) {
+        if (e_has_exit && e < d.cap_arr) {
+            int via = e_meta.x;
+            if (e_need_path) {
                 PathAlloc pa;
-                pa.bump_base = sh_base[2]; pa.from_free = sh_base[4]; pa.free_top = sh_base[5];
-                const int p = path_index(pa, d.path_free + (size_t)lane * d.cap_paths, sh_w[wid][4] + __popc(m_p & lt));
+                pa.bump_base = sh_base[pe][2]; pa.from_free = sh_base[pe][4]; pa.free_top = sh_base[pe][5];
+                const int p = path_index(pa, d.path_free + (size_t)e_lane * d.cap_paths, sh_w[pe][wid][4] + __popc(q_p & lt));
                 if (p < d.cap_paths) {
-                    PathRec* pr = d.paths + (size_t)lane * d.cap_paths + p;
-                    st_stream(reinterpret_cast<int4*>(pr), make_int4(__float_as_int(ex.w), sh.i2[lane], meta.w, __float_as_int(ex.x)));
-                    st_stream(reinterpret_cast<int4*>(pr) + 1, make_int4(__float_as_int(ex.y), __float_as_int(ex.z), 0, 0));
-                    ex.w = __int_as_float(p);
+                    PathRec* pr = d.paths + (size_t)e_lane * d.cap_paths + p;
+                    st_stream(reinterpret_cast<int4*>(pr), make_int4(__float_as_int(e_ex.w), sh[e_lane].frame, e_meta.w, __float_as_int(e_ex.x)));
+                    st_stream(reinterpret_cast<int4*>(pr) + 1, make_int4(__float_as_int(e_ex.y), __float_as_int(e_ex.z), 0, 0));
+                    e_ex.w = __int_as_float(p);
                 } else {
                     via = -2;                             // arena full: the record is dropped, k_boundary flags the lane
                 }
             }
-            if (to_round) d.r0_list[(size_t)lane * d.cap_arr + sh_base[3] + sh_w[wid][5] + __popc(m_r & lt)] = e;
-            d.arr_tok[(size_t)lane * d.cap_arr + e] = ex;
-            d.arr_meta[(size_t)lane * d.cap_arr + e] = make_int4(via, meta.z, meta.w, 0);
-            if (FUSE && meta.z < 0)                       // destination can see several arrivals this frame
-                atomicMax(d.state_key + (size_t)lane * d.n_multi + (meta.z & JG_STATE_MASK),
-                          state_key_of(d, epoch, ex.x, arrival_id(meta.x, 0)));
+            if (e_to_round) d.r0_list[(size_t)e_lane * d.cap_arr + sh_base[pe][3] + sh_w[pe][wid][5] + __popc(q_r & lt)] = e;
+            d.arr_tok[(size_t)e_lane * d.cap_arr + e] = e_ex;
+            d.arr_meta[(size_t)e_lane * d.cap_arr + e] = make_int4(via, e_meta.z, e_meta.w, 0);
+            if (FUSE && e_meta.z < 0)                     // destination can see several arrivals this frame
+                atomicMax(d.state_key + (size_t)e_lane * d.n_multi + (e_meta.z & JG_STATE_MASK),
+                          state_key_of(d, e_epoch, e_ex.x, arrival_id(e_meta.x, 0)));
         }
-        JG_TRACE_AT(6);                                       // stores issued: end of the first chunk
-        // (no barrier needed here: a warp only rewrites its own sh_w row, and the allocating threads rewrite the offsets
-        //  and sh_base after the next chunk's first barrier, which every warp reaches after reading its positions)
+        JG_TRACE_AT(6);                                       // stores issued: end of the chunk
+        // (no barrier needed here: a warp only rewrites its own sh_w row, the allocating threads rewrite the offsets and
+        //  sh_base after / before the next chunk's first barrier, which every warp reaches after reading its positions,
+        //  and a thread only ever touches its own entries of the parked results)
         lane = lane1; lane1 = lane2;
         valid = valid1; valid1 = valid2;
     }
