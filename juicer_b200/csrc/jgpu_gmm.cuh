@@ -5,7 +5,11 @@
 //
 // Exactness rules:
 //   * the d-sum is a sequential fp32 accumulation with separate sub, mul, mul, add — written
-//     with __fsub_rn/__fmul_rn/__fadd_rn so ptxas can never contract it into an FMA;
+//     with round-to-nearest intrinsics so ptxas can never contract it into an FMA.  The sub and
+//     the two muls of two neighbouring dimensions go through the packed f32x2 forms (SASS FADD2 /
+//     FMUL2, jg_acc4 below): IEEE per element, so the bits do not change, but a register-operand
+//     FP32 instruction issues every other cycle per scheduler on sm_100 and the packed form
+//     does two elements in that slot;
 //   * "-0.5*sumxmu + det" (double, narrowed once, :254) is evaluated as fadd(fmul(-0.5f, s), det), which is
 //     bit-identical for every pair of floats (see the comment at the store);
 //   * components are folded in order 0..n-1 by logAdd: float diff, double threshold -18.42,
@@ -30,6 +34,9 @@
 #endif
 #ifndef JG_GMM_P2
 #define JG_GMM_P2 1           // (row, GMM) logAdd chains folded side by side per thread in phase 2
+#endif
+#ifndef JG_GMM_PACKED
+#define JG_GMM_PACKED 1       // packed f32x2 arithmetic in the d-sum (0: scalar instructions, same bits)
 #endif
 #define JG_PRAGMA_(x) _Pragma(#x)
 #define JG_PRAGMA_UNROLL(n) JG_PRAGMA_(unroll n)
@@ -64,6 +71,33 @@ __device__ __forceinline__ double jg_softplus(const double* __restrict__ tab, do
     r = fma(r, t, c01.y);
     r = fma(r, t, c01.x);
     return r;
+}
+
+// s + sum over the four dimensions of xv, IN ORDER, of ((x - mu)^2 * ivar): what the loop at
+// src/HTKFlatModels.cpp:247-251 adds for them.  nmu = -mu (x - mu == x + (-mu) bit for bit, signed zeros included).
+__device__ __forceinline__ float jg_acc4(float s, float4 xv, float2 nmu01, float2 nmu23, float2 iv01, float2 iv23)
+{
+#if JG_GMM_PACKED
+    float2 d01 = __fadd2_rn(make_float2(xv.x, xv.y), nmu01);
+    float2 d23 = __fadd2_rn(make_float2(xv.z, xv.w), nmu23);
+    d01 = __fmul2_rn(d01, d01);
+    d23 = __fmul2_rn(d23, d23);
+    d01 = __fmul2_rn(d01, iv01);
+    d23 = __fmul2_rn(d23, iv23);
+    s = __fadd_rn(s, d01.x);
+    s = __fadd_rn(s, d01.y);
+    s = __fadd_rn(s, d23.x);
+    return __fadd_rn(s, d23.y);
+#else
+    const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+    const float na[4] = {nmu01.x, nmu01.y, nmu23.x, nmu23.y}, va[4] = {iv01.x, iv01.y, iv23.x, iv23.y};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float xmu = __fadd_rn(xa[e], na[e]);
+        s = __fadd_rn(s, __fmul_rn(__fmul_rn(xmu, xmu), va[e]));
+    }
+    return s;
+#endif
 }
 
 __device__ __forceinline__ float jg_log_add(const double* __restrict__ tab, float x, float y)
@@ -103,7 +137,7 @@ gmm_scores_body(const GmmDev& g, int gpb, const float* __restrict__ x, const int
     const int cstride = RT * gpb + (gpb & 31);   // consecutive components land on different banks
     const int tid = threadIdx.x;
     const int c = tid / gpb, gl = tid - c * gpb;
-    float mu[D], iv[D];
+    float2 nmu[D / 2], iv[D / 2];                // -mean and inverse variance of dimensions (2k, 2k+1)
     float det = 0.0f;
     int loaded_bx = -1;
 
@@ -147,9 +181,9 @@ gmm_scores_body(const GmmDev& g, int gpb, const float* __restrict__ x, const int
         if (active && loaded_bx != bx) {
             const size_t plane = (size_t)C * g.g_pad, off = (size_t)c * g.g_pad + gi;
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                mu[d] = __ldg(g.mu + d * plane + off);
-                iv[d] = __ldg(g.iv + d * plane + off);
+            for (int k = 0; k < D / 2; ++k) {
+                nmu[k] = make_float2(-__ldg(g.mu + (2 * k) * plane + off), -__ldg(g.mu + (2 * k + 1) * plane + off));
+                iv[k] = make_float2(__ldg(g.iv + (2 * k) * plane + off), __ldg(g.iv + (2 * k + 1) * plane + off));
             }
             det = __ldg(g.det + off);
         }
@@ -161,16 +195,7 @@ JG_PRAGMA_UNROLL(JG_GMM_UNROLL)
                 const float4* xr = reinterpret_cast<const float4*>(xs + r * DP);
                 float s = 0.0f;
 #pragma unroll
-                for (int q = 0; q < DP / 4; ++q) {
-                    const float4 xv = xr[q];
-                    const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int d = q * 4 + e;
-                        const float xmu = __fsub_rn(xa[e], mu[d]);
-                        s = __fadd_rn(s, __fmul_rn(__fmul_rn(xmu, xmu), iv[d]));
-                    }
-                }
+                for (int q = 0; q < DP / 4; ++q) s = jg_acc4(s, xr[q], nmu[2 * q], nmu[2 * q + 1], iv[2 * q], iv[2 * q + 1]);
                 // the reference evaluates -0.5*s + det in double and narrows (:254).  The fp32 form below is the same
                 // value bit for bit: -0.5f*s is exact, and the sum of two floats rounded to double and then to float
                 // equals the sum rounded to float directly — exact in double when the exponents differ by <= 29, and
@@ -386,7 +411,7 @@ __global__ void __launch_bounds__(JG_LAZY_WARPS * 32, (DP <= 40 ? 2 : 1)) k_gmm_
         // ---- this thread's Gaussian ----
         const int nc = __ldg(a.ncomp + g);
         const bool active = c < nc;
-        float mu[DP], iv[DP];
+        float2 nmu[DP / 2], iv[DP / 2];
         float det = JG_LZ;
         {
             const float4* pm = reinterpret_cast<const float4*>(a.mu + ((size_t)g * a.C + (active ? c : 0)) * DP);
@@ -394,8 +419,8 @@ __global__ void __launch_bounds__(JG_LAZY_WARPS * 32, (DP <= 40 ? 2 : 1)) k_gmm_
 #pragma unroll
             for (int q = 0; q < DP / 4; ++q) {
                 const float4 m4 = __ldg(pm + q), v4 = __ldg(pv + q);
-                mu[4 * q] = m4.x; mu[4 * q + 1] = m4.y; mu[4 * q + 2] = m4.z; mu[4 * q + 3] = m4.w;
-                iv[4 * q] = v4.x; iv[4 * q + 1] = v4.y; iv[4 * q + 2] = v4.z; iv[4 * q + 3] = v4.w;
+                nmu[2 * q] = make_float2(-m4.x, -m4.y); nmu[2 * q + 1] = make_float2(-m4.z, -m4.w);
+                iv[2 * q] = make_float2(v4.x, v4.y); iv[2 * q + 1] = make_float2(v4.z, v4.w);
             }
             if (active) det = __ldg(a.det + (size_t)g * a.C + c);
         }
@@ -417,15 +442,8 @@ __global__ void __launch_bounds__(JG_LAZY_WARPS * 32, (DP <= 40 ? 2 : 1)) k_gmm_
 #pragma unroll
                 for (int q = 0; q < DP / 4; ++q) {
 #pragma unroll
-                    for (int u = 0; u < JG_LAZY_U; ++u) {
-                        const float4 xv = xs4[xo[u] + q];
-                        const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float xmu = __fsub_rn(xa[e], mu[4 * q + e]);
-                            s[u] = __fadd_rn(s[u], __fmul_rn(__fmul_rn(xmu, xmu), iv[4 * q + e]));
-                        }
-                    }
+                    for (int u = 0; u < JG_LAZY_U; ++u)
+                        s[u] = jg_acc4(s[u], xs4[xo[u] + q], nmu[2 * q], nmu[2 * q + 1], iv[2 * q], iv[2 * q + 1]);
                 }
 #pragma unroll
                 for (int u = 0; u < JG_LAZY_U; ++u) {
