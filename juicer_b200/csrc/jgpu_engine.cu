@@ -788,8 +788,7 @@ int launch_gmm(jgpu_handle* h, const float* d_x, const int* d_rows, int n_rows, 
     const GmmDev& G = h->g;
     const int gpb = G.gpb;
     const int n_bx = (G.n_gmms + gpb - 1) / gpb, n_by = (n_rows + JG_GMM_RT - 1) / JG_GMM_RT;
-    const int cstride = JG_GMM_RT * gpb + (gpb & 31);
-    const size_t smem = ((size_t)JG_GMM_RT * h->DP + (size_t)G.C * cstride) * sizeof(float);
+    const size_t smem = gmm_smem_bytes(JG_GMM_RT, h->DP, G.C, gpb);
     h->prof_begin(JGPU_K_GMM, st);
     switch (h->DP) {
 #define GMM_CASE(DPV)                                                                                          \

@@ -35,6 +35,14 @@
 #ifndef JG_GMM_P2
 #define JG_GMM_P2 1           // (row, GMM) logAdd chains folded side by side per thread in phase 2
 #endif
+#ifndef JG_LOGADD_BRANCHFREE
+#define JG_LOGADD_BRANCHFREE 0   // (1 + JG_GMM_P2 = 4 measured 27 % slower: the logAdd phase is bound by the L1 wavefronts of its
+                                  //  table gathers, not by the latency of a chain — profiles/r02_logadd.md)
+#endif
+#ifndef JG_SP_SHARED
+#define JG_SP_SHARED 1            // the scorer keeps the softplus table in shared memory (80-byte rows: a thread's 16-byte reads
+                                  // of a random row spread over 8 bank groups)
+#endif
 #ifndef JG_GMM_PACKED
 #define JG_GMM_PACKED 1       // packed f32x2 arithmetic in the d-sum (0: scalar instructions, same bits)
 #endif
@@ -55,13 +63,28 @@ struct GmmDev {
 // 1/16).  Exhaustively compared with glibc's log(1.0 + exp(d)) over all 1.1e9 float32 arguments of the
 // range: max |difference| 2.2e-16 (one ulp of 0.693), i.e. as accurate as the libm composite the
 // reference calls (src/HTKFlatModels.cpp:289), at ~1/6 of the instructions of exp() + log().
+// dynamic shared memory of the dense scorer: feature tile + per-component values (in floats, rounded to 16 bytes),
+// then the softplus table
+__host__ __device__ inline size_t gmm_vals_floats(int RT, int DP, int C, int gpb)
+{
+    return ((size_t)RT * DP + (size_t)C * (RT * gpb + (gpb & 31)) + 3) & ~(size_t)3;
+}
+// SMEM: the table is a shared-memory copy with rows JG_SP_SROW doubles apart (see gmm_scores_body).
+#define JG_SP_SROW 10
+__host__ __device__ inline size_t gmm_smem_bytes(int RT, int DP, int C, int gpb)
+{
+    return gmm_vals_floats(RT, DP, C, gpb) * sizeof(float) + (JG_SP_SHARED ? (size_t)JG_SP_INTERVALS * JG_SP_SROW * sizeof(double) : 0);
+}
+template <bool SMEM>
 __device__ __forceinline__ double jg_softplus(const double* __restrict__ tab, double d)
 {
     int k = (int)(-d * 16.0);
     k = min(k, JG_SP_INTERVALS - 1);
     const double t = d + ((double)k + 0.5) * 0.0625;
-    const double2* T = reinterpret_cast<const double2*>(tab + k * 8);
-    const double2 c01 = __ldg(T), c23 = __ldg(T + 1), c45 = __ldg(T + 2), c67 = __ldg(T + 3);
+    const double2* T = reinterpret_cast<const double2*>(tab + k * (SMEM ? JG_SP_SROW : 8));
+    double2 c01, c23, c45, c67;
+    if (SMEM) { c01 = T[0]; c23 = T[1]; c45 = T[2]; c67 = T[3]; }
+    else { c01 = __ldg(T); c23 = __ldg(T + 1); c45 = __ldg(T + 2); c67 = __ldg(T + 3); }
     double r = c67.y;
     r = fma(r, t, c67.x);
     r = fma(r, t, c45.y);
@@ -100,12 +123,27 @@ __device__ __forceinline__ float jg_acc4(float s, float4 xv, float2 nmu01, float
 #endif
 }
 
+// logAdd (src/HTKFlatModels.cpp:266-293).  Branch-free: some thread of a warp needs the softplus in practically every
+// call (ncu: its instructions execute as often as the call itself), and without the early return the compiler can
+// interleave the JG_GMM_P2 independent chains a thread folds side by side — each chain is ~250 cycles of dependent
+// conversions, fp64 arithmetic and a table gather per component, and the logAdd phase was 45 % of the scorer's
+// stall samples at 17 % of its instructions.  A diff below the threshold (down to -inf) indexes the last table
+// interval and its value is discarded.
+template <bool SMEM = false>
 __device__ __forceinline__ float jg_log_add(const double* __restrict__ tab, float x, float y)
 {
+#if JG_LOGADD_BRANCHFREE
+    const float hi = x < y ? y : x, lo = x < y ? x : y;
+    const float diff = __fsub_rn(lo, hi);
+    const double dd = (double)diff;
+    const float r = (float)((double)hi + jg_softplus<SMEM>(tab, dd));
+    return dd < -18.42 ? hi : r;                               // MINUS_LOG_THRESHOLD, compared in double
+#else
     if (x < y) { const float t = x; x = y; y = t; }
     const float diff = __fsub_rn(y, x);
     if ((double)diff < -18.42) return x;                       // MINUS_LOG_THRESHOLD, compared in double
-    return (float)((double)x + jg_softplus(tab, (double)diff));
+    return (float)((double)x + jg_softplus<SMEM>(tab, (double)diff));
+#endif
 }
 
 // rows: list of feature-row indices into x (row-major [*, D]); -1 = skip.  Output row i of
@@ -132,6 +170,16 @@ gmm_scores_body(const GmmDev& g, int gpb, const float* __restrict__ x, const int
     float* xs = smem;                          // [RT][DP]
     float* vals = smem + RT * DP;              // [C][RT*gpb + pad]
     __shared__ int row_id[RT];
+    // softplus table: the logAdd phase reads one 64-byte row per (thread, component) at a data-dependent index; from
+    // global memory that is one L1 wavefront per distinct row and instruction (as many wavefronts as all the feature
+    // tile loads of phase 1, ncu r02f), from shared memory with padded rows it is a bank-conflict count
+    double* sp_tab = reinterpret_cast<double*>(smem + gmm_vals_floats(RT, DP, g.C, gpb));
+    if (JG_SP_SHARED) {
+        for (int i = threadIdx.x; i < JG_SP_INTERVALS * 4; i += NT) {
+            const int k = i >> 2, j = i & 3;
+            reinterpret_cast<double2*>(sp_tab + k * JG_SP_SROW)[j] = __ldg(reinterpret_cast<const double2*>(g.softplus + k * 8) + j);
+        }
+    }
 
     const int C = g.C;
     const int cstride = RT * gpb + (gpb & 31);   // consecutive components land on different banks
@@ -224,8 +272,11 @@ JG_PRAGMA_UNROLL(JG_GMM_UNROLL)
             }
             for (int cc = 0; cc < nc_max; ++cc) {
 #pragma unroll
-                for (int u = 0; u < PP; ++u)
-                    if (cc < nc[u]) lp[u] = jg_log_add(g.softplus, lp[u], vals[cc * cstride + pp[u]]);
+                for (int u = 0; u < PP; ++u) {
+                    const float v = JG_SP_SHARED ? jg_log_add<true>(sp_tab, lp[u], vals[cc * cstride + min(pp[u], RT * gpb - 1)])
+                                                 : jg_log_add<false>(g.softplus, lp[u], vals[cc * cstride + min(pp[u], RT * gpb - 1)]);
+                    lp[u] = cc < nc[u] ? v : lp[u];
+                }
             }
 #pragma unroll
             for (int u = 0; u < PP; ++u)
