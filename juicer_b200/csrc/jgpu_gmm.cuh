@@ -32,12 +32,13 @@
 #ifndef JG_GMM_UNROLL
 #define JG_GMM_UNROLL 4       // feature rows in flight per thread (independent accumulation chains)
 #endif
-#ifndef JG_GMM_P2
-#define JG_GMM_P2 1           // (row, GMM) logAdd chains folded side by side per thread in phase 2
-#endif
 #ifndef JG_LOGADD_BRANCHFREE
 #define JG_LOGADD_BRANCHFREE 0   // (1 + JG_GMM_P2 = 4 measured 27 % slower: the logAdd phase is bound by the L1 wavefronts of its
                                   //  table gathers, not by the latency of a chain — profiles/r02_logadd.md)
+#endif
+#ifndef JG_LOGSUM_PREFILTER
+#define JG_LOGSUM_PREFILTER 0     // jg_mix_logsum first finds the logAdd steps that cannot change the accumulator (exact, same bits;
+                                  // measured 6 % slower on the synthetic mixtures, whose components overlap: profiles/r02_logadd.md)
 #endif
 #ifndef JG_SP_SHARED
 #define JG_SP_SHARED 1            // the scorer keeps the softplus table in shared memory (80-byte rows: a thread's 16-byte reads
@@ -144,6 +145,40 @@ __device__ __forceinline__ float jg_log_add(const double* __restrict__ tab, floa
     if ((double)diff < -18.42) return x;                       // MINUS_LOG_THRESHOLD, compared in double
     return (float)((double)x + jg_softplus<SMEM>(tab, (double)diff));
 #endif
+}
+
+// logAdd over the nc component values v[0], v[stride], ... IN ORDER (src/HTKFlatModels.cpp:252-255).
+// A step whose component lies more than the threshold below the running maximum of the EARLIER components is a no-op
+// in the reference: the accumulator is >= that maximum (logAdd never returns less than its larger operand), so the
+// float difference the reference forms is <= fl(v - max), and its branch `diff < -18.42` returns the accumulator
+// unchanged (:272-276).  Those steps are found first with four fp32 instructions each and only the others run the
+// fp64 logAdd, in the same order — the same sequence of roundings, at a fraction of the table gathers and fp64
+// chains (a Gaussian mixture is dominated by a few components for any one frame).
+// (double)f < -18.42  <=>  f < -18.419998 (0xc1935c28, the smallest float above the double threshold).
+template <bool SMEM>
+__device__ __forceinline__ float jg_mix_logsum(const double* __restrict__ tab, const float* __restrict__ v, int stride, int nc)
+{
+    float lp = JG_LZ;
+#if JG_LOGSUM_PREFILTER
+    if (nc <= 32) {
+        const float thr = __uint_as_float(0xc1935c28u);
+        float m = JG_LZ;
+        unsigned todo = 0u;
+        for (int cc = 0; cc < nc; ++cc) {
+            const float x = v[cc * stride];
+            if (!(__fsub_rn(x, m) < thr)) todo |= 1u << cc;
+            m = fmaxf(m, x);
+        }
+        while (todo) {
+            const int cc = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            lp = jg_log_add<SMEM>(tab, lp, v[cc * stride]);
+        }
+        return lp;
+    }
+#endif
+    for (int cc = 0; cc < nc; ++cc) lp = jg_log_add<SMEM>(tab, lp, v[cc * stride]);
+    return lp;
 }
 
 // rows: list of feature-row indices into x (row-major [*, D]); -1 = skip.  Output row i of
@@ -253,37 +288,15 @@ JG_PRAGMA_UNROLL(JG_GMM_UNROLL)
         }
         __syncthreads();
 
-        // phase 2: thread <-> (row, gmm); serial logAdd chain in component order.  JG_GMM_P2 pairs per thread are
-        // folded side by side: each chain is a string of dependent fp64 operations, the pairs are independent.
-        constexpr int PP = JG_GMM_P2;
-        for (int p0 = tid; p0 < RT * gpb; p0 += NT * PP) {
-            float lp[PP];
-            int nc[PP], pp[PP];
-            int nc_max = 0;
-#pragma unroll
-            for (int u = 0; u < PP; ++u) {
-                const int p = p0 + u * NT;
-                pp[u] = p; nc[u] = 0; lp[u] = JG_LZ;
-                if (p < RT * gpb) {
-                    const int r = p / gpb, l = p - r * gpb;
-                    if (g0 + l < g.n_gmms && row_id[r] >= 0) nc[u] = __ldg(g.ncomp + g0 + l);
-                }
-                nc_max = max(nc_max, nc[u]);
+        // phase 2: thread <-> (row, gmm); serial logAdd chain in component order (jg_mix_logsum)
+        for (int p = tid; p < RT * gpb; p += NT) {
+            const int r = p / gpb, l = p - r * gpb;
+            if (g0 + l < g.n_gmms && row_id[r] >= 0) {
+                const int nc = __ldg(g.ncomp + g0 + l);
+                const float lp = JG_SP_SHARED ? jg_mix_logsum<true>(sp_tab, vals + p, cstride, nc)
+                                              : jg_mix_logsum<false>(g.softplus, vals + p, cstride, nc);
+                if (nc > 0) out[(size_t)(out_base + r0 + r) * g.n_gmms + g0 + l] = lp;
             }
-            for (int cc = 0; cc < nc_max; ++cc) {
-#pragma unroll
-                for (int u = 0; u < PP; ++u) {
-                    const float v = JG_SP_SHARED ? jg_log_add<true>(sp_tab, lp[u], vals[cc * cstride + min(pp[u], RT * gpb - 1)])
-                                                 : jg_log_add<false>(g.softplus, lp[u], vals[cc * cstride + min(pp[u], RT * gpb - 1)]);
-                    lp[u] = cc < nc[u] ? v : lp[u];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < PP; ++u)
-                if (nc[u] > 0) {
-                    const int r = pp[u] / gpb, l = pp[u] - r * gpb;
-                    out[(size_t)(out_base + r0 + r) * g.n_gmms + g0 + l] = lp[u];
-                }
         }
         if (PERSIST) __syncthreads();            // row_id / xs / vals are rewritten by the next tile
     }
@@ -505,8 +518,7 @@ __global__ void __launch_bounds__(JG_LAZY_WARPS * 32, (DP <= 40 ? 2 : 1)) k_gmm_
             __syncwarp();
             // phase 2: thread <-> (row, GMM): logAdd over the components IN ORDER (:252-255, :266-293)
             if (lane < nb) {
-                float lp = JG_LZ;
-                for (int cc = 0; cc < nc; ++cc) lp = jg_log_add(a.softplus, lp, vw[lane * vstride + cc]);
+                const float lp = jg_mix_logsum<false>(a.softplus, vw + lane * vstride, 1, nc);
                 const int row = (int)rl[b0 + lane];
                 a.scores[(size_t)row * a.n_gmms + g] = lp;
                 if (a.scored) a.scored[(size_t)row * a.need_gp + g] = (unsigned char)s_stamp[row];
