@@ -111,6 +111,9 @@ struct Dev {
     const int4*  states;       // {first arc, n arcs, final weight bits, n_eps | n_tee << 16}
     const float* arc_tee;      // per-arc tee weight of the arc's HMM, nullptr when no tee model exists
     const int*   hmm_info;     // [n_hmms][8] : nst | class<<8, gmm of states 1..3 | tee bits, gmm of states 4..6
+    const uint2* hmm8;         // [n_hmms] the same for <= 5-state sets with < 64 K GMMs and < 4 K classes, in 8 bytes:
+                               // {nst | lr << 3 | class << 4 | gmm1 << 16, gmm2 | gmm3 << 16} — a quarter of the bytes k_internal's
+                               // per-instance gather pulls through L1 (nullptr when the set does not fit)
     const float* trp;          // [n_class][S*S]
     const int2*  se;           // [n_class][S]
     const float4* lr;          // [n_class][2]: left-to-right classes {a01,a11,a12,a22 | a23,a33,a34,-}

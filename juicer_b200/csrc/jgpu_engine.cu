@@ -452,7 +452,22 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
     if ((int)lrtab.size() > JG_LR_SH)
         for (int i = 0; i < H; ++i) info[(size_t)i * 8 + 0] &= ~JG_LR_CLASS;
     const size_t b_lr = pad256(lrtab.size() * sizeof(float4));
-    h->static_bytes = b_arcs + b_states + b_tee + b_info + b_trp + b_se + b_lr;
+    // 8-byte form of hmm_info for k_internal<5> (see Dev::hmm8)
+    std::vector<uint2> info8;
+    {
+        const char* off8 = getenv("JUICER_B200_HMM8");
+        bool fits = S == 5 && g->n_gmms < 65536 && cls_of.size() < 4096 && !(off8 && atoi(off8) == 0);
+        if (fits) {
+            info8.resize(H);
+            for (int i = 0; i < H; ++i) {
+                const int* e = &info[(size_t)i * 8];
+                const unsigned ns = e[0] & 0xff, cls = (unsigned)(e[0] & ~JG_LR_CLASS) >> 8, lr = (e[0] & JG_LR_CLASS) ? 1u : 0u;
+                info8[i] = make_uint2(ns | (lr << 3) | (cls << 4) | ((unsigned)e[1] << 16), (unsigned)e[2] | ((unsigned)e[3] << 16));
+            }
+        }
+    }
+    const size_t b_info8 = pad256(info8.size() * sizeof(uint2));
+    h->static_bytes = b_arcs + b_states + b_tee + b_info + b_trp + b_se + b_lr + b_info8;
     char* base = nullptr;
     if ((rc = h->alloc(&base, h->static_bytes, false))) return rc;
     h->static_base = base;
@@ -471,6 +486,7 @@ int build_tables(jgpu_handle* h, const JgpuNet* n, const JgpuHmm* m, const JgpuG
     int2* d_se = (int2*)put(se.data(), se.size() * sizeof(int2), b_se);
     d.lr = (const float4*)put(lrtab.data(), lrtab.size() * sizeof(float4), b_lr);
     d.n_lr = (int)lrtab.size();
+    d.hmm8 = info8.empty() ? nullptr : (const uint2*)put(info8.data(), info8.size() * sizeof(uint2), b_info8);
     CK(cudaGetLastError());
     d.hmm_info = d_info; d.trp = d_trp; d.se = d_se;
 
@@ -686,6 +702,18 @@ int build_state(jgpu_handle* h)
         void (*kerns[8])(Dev) = {k_internal<5, true, false>, k_internal<5, false, false>, k_internal<5, true, true>, k_internal<5, false, true>,
                                  k_internal<8, true, false>, k_internal<8, false, false>, k_internal<8, true, true>, k_internal<8, false, true>};
         for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        // Shared-memory carve-out: exactly what the resident CTAs need and no more — what is left of the 256 KB is the
+        // L1 that the per-instance hmm_info / score gathers go through (measured on c3: 233.8 us per launch at 72 %,
+        // 237.0 at the driver's default choice, 286.6 at 100 %).  JUICER_B200_INT_CARVEOUT overrides (percent).
+        for (int i = 0; i < 8 && e == cudaSuccess; ++i) {
+            cudaFuncAttributes fa;
+            int occ = 0;
+            if (cudaFuncGetAttributes(&fa, kerns[i]) != cudaSuccess ||
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kerns[i], JG_THREADS, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); continue; }
+            int pct = (int)std::min<size_t>(100, ((size_t)occ * (smem + fa.sharedSizeBytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+            if (const char* cv = getenv("JUICER_B200_INT_CARVEOUT")) pct = atoi(cv);
+            e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
         if (e != cudaSuccess) return fail(JGPU_E_CUDA, "k_internal shared memory opt-in: %s", cudaGetErrorString(e));
     }
     {

@@ -662,6 +662,15 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         return ln;
     };
 
+    // first int4 of an HMM's hmm_info row, from the 8-byte table when the model set has one
+    auto load_h0 = [&](int hmm) -> int4 {
+        if (S == 5 && d.hmm8) {
+            const uint2 p = __ldg(d.hmm8 + hmm);
+            return make_int4((int)((p.x & 7u) | ((p.x >> 4 & 0xfffu) << 8) | ((p.x & 8u) ? (unsigned)JG_LR_CLASS : 0u)),
+                             (int)(p.x >> 16), (int)(p.y & 0xffffu), (int)(p.y >> 16));
+        }
+        return __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2);
+    };
     int ch = chunk_of(0);
     int lane = lane_of(0, ch, 0);
     int lane1 = lane_of(1, chunk_of(1), lane), lane2 = lane_of(2, chunk_of(2), lane1);
@@ -680,7 +689,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
     cp_async_wait<1>();
     if (valid) {
         const int hmm = reinterpret_cast<const int4*>(stage)[tid].y & ~JG_FRESH;
-        h0 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2);
+        h0 = load_h0(hmm);
         if (S > 5) h1 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2 + 1);
         const float* __restrict__ scores = d.scores + (size_t)sh[lane].srow * d.n_gmms;
         const int gm[6] = {h0.y, h0.z, h0.w, h1.y, h1.z, h1.w};
@@ -732,7 +741,7 @@ __global__ void __launch_bounds__(JG_THREADS, (S <= 5 ? JG_INT_CTAS : 2)) k_inte
         int4 n0 = make_int4(2, 0, 0, 0), n1 = make_int4(0, 0, 0, 0);
         if (valid1) {
             const int hmm = reinterpret_cast<const int4*>(stage + (size_t)(buf ^ 1) * (P + 1) * JG_THREADS)[tid].y & ~JG_FRESH;
-            n0 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2);
+            n0 = load_h0(hmm);
             if (S > 5) n1 = __ldg(reinterpret_cast<const int4*>(d.hmm_info) + hmm * 2 + 1);
         }
 
