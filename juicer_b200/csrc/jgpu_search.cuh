@@ -28,6 +28,9 @@
 #define JG_WALK_CTAS 5            // resident CTAs per SM of k_walk (51 registers per thread; at 6 the commit spills since the
                                   // arrival ids and the demand stamps were added, and 5 vs 6 measured the same in round 1)
 #endif
+#ifndef JG_WALK_ILP
+#define JG_WALK_ILP 2            // arcs in flight per thread in the flattened arc list of k_walk
+#endif
 #ifndef JG_HUGE_ILP
 #define JG_HUGE_ILP 2            // arcs in flight per thread in k_commit_huge (1: 32.8 us, 2: 29.0 us, 4: 31.1 us — 54 registers, two waves)
 #endif
@@ -1197,11 +1200,25 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
         sh.epoch[l] = (c->epoch & ~JG_SH_HAS_FREE) | (c->n_free > 0 ? JG_SH_HAS_FREE : 0u);
     }
     const int total_chunks = chunk_scan(sh, L);
+    // lane of this CTA's i-th chunk, bisected once by thread i (walking pref[] from the previous chunk's lane, all
+    // threads in step, was 17 % of the commit's instructions: a CTA's chunks are gridDim.x apart, ~20 lanes on c3)
+    __shared__ unsigned short s_lane_of[JG_THREADS];
+    {
+        const long long c_t = (long long)blockIdx.x + (long long)tid * gridDim.x;
+        int lo = 0, hi = L;                                   // largest l with pref[l] <= c_t
+        if (c_t < total_chunks)
+            while (lo + 1 < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (sh.pref[mid] <= (int)c_t) lo = mid; else hi = mid;
+            }
+        s_lane_of[tid] = (unsigned short)lo;
+    }
+    __syncthreads();
     JG_TRACE_AT(0);                                           // setup done
 
-    int lane = 0;
-    for (int ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
-        lane = lane_of_chunk(sh, L, lane, ch);
+    int lane = 0, it = 0;
+    for (int ch = blockIdx.x; ch < total_chunks; ch += gridDim.x, ++it) {
+        lane = it < JG_THREADS ? (int)s_lane_of[it] : lane_of_chunk(sh, L, lane, ch);
         LaneCtl* c = d.ctl + lane;
         const unsigned epoch = sh.epoch[lane];
         const float thr_end = sh.f0[lane], thr_word = sh.f1[lane];
@@ -1294,8 +1311,15 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
         if (lane_id() == 31) s_wsum[wid] = incl;
         s_first[tid] = first; s_tok[tid] = tok;
         __syncthreads();
-        int woff = 0;
-        for (int w = 0; w < wid; ++w) woff += s_wsum[w];
+        int woff;
+        {                                                     // exclusive prefix of the warp totals: one load + shuffles
+            int ws = lane_id() < JG_THREADS / 32 ? s_wsum[lane_id()] : 0, wi = ws;
+            for (int o = 1; o < JG_THREADS / 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane_id() >= o) wi += t;
+            }
+            woff = __shfl_sync(0xffffffffu, wi - ws, wid);
+        }
         s_off[tid] = woff + incl - deg;
         if (tid == JG_THREADS - 1) s_off[JG_THREADS] = woff + incl;
         __syncthreads();
@@ -1304,12 +1328,13 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
         // ---- (B) the rows of the chunk as ONE flattened arc list, two arcs in flight per thread ----
         int n_entry = 0;
         float best = JG_LZ;
-        for (int jb = 0; jb < total; jb += 2 * JG_THREADS) {
-            int b[2], src[2];
-            int4 a[2];
-            unsigned sm[2] = {0u, 0u};
+        for (int jb = 0; jb < total; jb += JG_WALK_ILP * JG_THREADS) {
+            int b[JG_WALK_ILP], src[JG_WALK_ILP];
+            int4 a[JG_WALK_ILP];
+            unsigned sm[JG_WALK_ILP];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < JG_WALK_ILP; ++u) {
+                sm[u] = 0u;
                 const int j = jb + u * JG_THREADS + tid;
                 b[u] = -1; src[u] = 0;
                 if (j < total) {
@@ -1325,7 +1350,7 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < JG_WALK_ILP; ++u)
                 if (b[u] >= 0)
                     process_arc<PASS, LAZY>(d, lane, c, epoch, thr_end, thr_word, round + 1, out_base, sh.i2[lane], s_tok[src[u]], b[u],
                                       a[u], sm[u], best, n_entry);
