@@ -28,6 +28,13 @@
 #define JG_WALK_CTAS 5            // resident CTAs per SM of k_walk (51 registers per thread; at 6 the commit spills since the
                                   // arrival ids and the demand stamps were added, and 5 vs 6 measured the same in round 1)
 #endif
+#ifndef JG_COMMIT_PREFETCH
+#define JG_COMMIT_PREFETCH 0     // k_walk<1>: the next chunk's arrival records, state rows and state keys are fetched by cp.async
+                                 // while the current chunk's arcs are walked (two of the four dependent round trips of a chunk).
+                                 // Bit-exact and slower (108.4 us per launch against 86.4): the 14 KB of staging per CTA come out
+                                 // of the L1 that the arc-row, state-row and slotmap gathers live in.  What stays from it: the
+                                 // state row and the state key are requested together (91.5 -> 86.4 us).
+#endif
 #ifndef JG_WALK_ILP
 #define JG_WALK_ILP 2            // arcs in flight per thread in the flattened arc list of k_walk
 #endif
@@ -557,6 +564,15 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// plain (L1-allocating) 16- and 8-byte copies
+__device__ __forceinline__ void cp_async_ca16(void* smem_dst, const void* gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_ca8(void* smem_dst, const void* gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
 
 // Software pipeline over the CTA's chunks (chunk i = the i-th chunk this CTA owns):
 //   iteration i:  registers <- shared buffer (i & 1)          [chunk i: instance record + token planes]
@@ -1214,6 +1230,47 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
         s_lane_of[tid] = (unsigned short)lo;
     }
     __syncthreads();
+    // The commit's prefetch (PASS 1): a chunk is four dependent round trips — arrival record, state row + state key,
+    // [prefix], arc row + slotmap, token.  While the arcs of chunk i are walked, the record of chunk i+1 (issued at
+    // the top of chunk i) has landed, and its state row and key are fetched; a thread only ever touches its own slots.
+    constexpr bool PF = PASS == 1 && JG_COMMIT_PREFETCH != 0;
+    __shared__ float4 p_tok[PF ? JG_THREADS : 1];
+    __shared__ int4 p_meta[PF ? JG_THREADS : 1], p_st[PF ? JG_THREADS : 1];
+    __shared__ u64 p_key[PF ? JG_THREADS : 1];
+    const bool pf_on = PF && (long long)total_chunks <= (long long)JG_THREADS * gridDim.x;   // (s_lane_of covers every chunk)
+    // this thread's record of the CTA's it2-th chunk: lane and index, or -1
+    auto pf_slot = [&](int it2, int& ln) -> int {
+        const long long ch2 = (long long)blockIdx.x + (long long)it2 * gridDim.x;
+        if (ch2 >= total_chunks) return -1;
+        ln = (int)s_lane_of[it2];
+        const int e2 = ((int)ch2 - sh.pref[ln]) * JG_CH + tid;
+        return e2 < sh.cnt[ln] ? e2 : -1;
+    };
+    auto pf_record = [&](int it2) {
+        int ln = 0;
+        const int e2 = pf_slot(it2, ln);
+        if (e2 >= 0) {
+            cp_async_ca16(&p_tok[tid], d.arr_tok + (size_t)ln * d.cap_arr + e2);
+            cp_async_ca16(&p_meta[tid], d.arr_meta + (size_t)ln * d.cap_arr + e2);
+        }
+        cp_async_commit();
+    };
+    auto pf_state = [&](int it2) {                            // (its record has landed)
+        int ln = 0;
+        const int e2 = pf_slot(it2, ln);
+        if (e2 >= 0) {
+            const int my = p_meta[tid].y;
+            const int q = my & JG_STATE_MASK;
+            cp_async_ca16(&p_st[tid], &d.states[q]);
+            if (my < 0) cp_async_ca8(&p_key[tid], d.state_key + (size_t)ln * d.n_multi + q);
+        }
+        cp_async_commit();
+    };
+    if (pf_on) {
+        pf_record(0);
+        cp_async_wait<0>();
+        pf_state(0);
+    }
     JG_TRACE_AT(0);                                           // setup done
 
     int lane = 0, it = 0;
@@ -1233,12 +1290,26 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
         int first = 0, deg = 0, arcs_done = 0;
         float4 tok = null_tok();
         u64 fin = 0;
+        if (pf_on) cp_async_wait<0>();                        // this chunk's record, state row and key are in shared memory
+        int4 m = make_int4(0, 0, 0, 0), st = make_int4(0, 0, 0, 0);
+        u64 key_now = 0;
         if (valid) {
-            tok = arr_tok[r];
-            const int4 m = arr_meta[r];                       // {via, q | MULTI, olab, -}
+            if (pf_on) {
+                tok = p_tok[tid]; m = p_meta[tid]; st = p_st[tid];
+                if (m.y < 0) key_now = p_key[tid];
+            } else {
+                tok = arr_tok[r];
+                m = arr_meta[r];                              // {via, q | MULTI, olab, -}
+            }
+        }
+        if (pf_on) pf_record(it + 1);                         // (the slots just read are free again)
+        if (valid) {
             const int q = m.y & JG_STATE_MASK;
             JG_TRACE_AT(1);                                   // record loaded
-            const int4 st = __ldg(&d.states[q]);
+            if (!pf_on) {
+                st = __ldg(&d.states[q]);
+                if (m.y < 0) key_now = d.state_key[(size_t)lane * d.n_multi + q];
+            }
             valid = m.x != -2;
             if (PASS == 1 && valid && m.x >= 0 && __int_as_float(st.z) > JG_LZ) {
                 // best final token (:513-520): the rounds max-reduced (score + final weight | arrival id); the record
@@ -1247,7 +1318,7 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
                 if (bf != 0 && (((u64)f2o(tok.x + __int_as_float(st.z)) << 32) | (u64)arrival_id(m.x, m.w)) == bf) c->final_rec = (int)r;
             }
             if (valid && m.y < 0)                             // still the best arrival of q?
-                valid = d.state_key[(size_t)lane * d.n_multi + q] == state_key_of(d, epoch, tok.x, arrival_id(m.x, m.w));
+                valid = key_now == state_key_of(d, epoch, tok.x, arrival_id(m.x, m.w));
             if (valid) {
                 const int n_eps = st.w & 0xffff, n_tee = (unsigned)st.w >> 16;
                 JG_TRACE_AT(2);                               // state row (and key) loaded
@@ -1326,6 +1397,7 @@ __global__ void __launch_bounds__(JG_THREADS, JG_WALK_CTAS) k_walk(Dev d, int ro
         const int total = s_off[JG_THREADS];
         JG_TRACE_AT(4);                                       // prefix done
         // ---- (B) the rows of the chunk as ONE flattened arc list, two arcs in flight per thread ----
+        if (pf_on) { cp_async_wait<0>(); pf_state(it + 1); }  // the next chunk's record has landed: fetch its state row and key
         int n_entry = 0;
         float best = JG_LZ;
         for (int jb = 0; jb < total; jb += JG_WALK_ILP * JG_THREADS) {
