@@ -727,6 +727,11 @@ int build_state(jgpu_handle* h)
                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_internal<8, true, false>, JG_THREADS, smem_int);
         if (e == cudaSuccess && occ > 0) d.grid_internal = n_sm * occ;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_walk<1, false>, JG_THREADS, 0) == cudaSuccess && occ > 0) d.grid_walk = n_sm * occ;
+        if (const char* cv = getenv("JUICER_B200_WALK_CARVEOUT")) {   // tuning: preferred shared-memory carve-out of the walk kernels, percent
+            cudaFuncSetAttribute(k_walk<0, false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
+            cudaFuncSetAttribute(k_walk<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
+            cudaFuncSetAttribute(k_commit_huge<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
+        }
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_filter, JG_THREADS, 0) == cudaSuccess && occ > 0) d.grid_other = n_sm * occ;
         cudaGetLastError();
     }
