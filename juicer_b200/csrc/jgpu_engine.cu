@@ -908,7 +908,13 @@ int launch_step(jgpu_handle* h)
     }
     for (int r = 0; r < d.n_rounds; ++r) {
         h->prof_begin(r == 0 ? JGPU_K_EXPAND : r == 1 ? JGPU_K_EXPAND_R1 : JGPU_K_EXPAND_R2);
-        k_walk<0, false><<<d.grid_walk, JG_THREADS, 0, st>>>(d, r);
+        // The expansion rounds have little to do (a few chunks per lane) and every CTA first reads the control block of
+        // every lane: fewer CTAs per SM means less of that fixed cost (JUICER_B200_EXPAND_CTAS: CTAs per SM, rounds 0 / >= 1)
+        static const int ex0 = getenv("JUICER_B200_EXPAND_CTAS0") ? atoi(getenv("JUICER_B200_EXPAND_CTAS0")) : 0;
+        static const int ex1 = getenv("JUICER_B200_EXPAND_CTAS1") ? atoi(getenv("JUICER_B200_EXPAND_CTAS1")) : 0;
+        const int per_sm = r == 0 ? ex0 : ex1;
+        const int grid_r = per_sm > 0 ? std::min(d.grid_walk, h->n_sm * per_sm) : d.grid_walk;
+        k_walk<0, false><<<grid_r, JG_THREADS, 0, st>>>(d, r);
         h->prof_end();
     }
     h->prof_begin(JGPU_K_COMMIT);
